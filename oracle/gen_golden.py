@@ -1,0 +1,201 @@
+"""ORACLE (test infrastructure only) — generate tests/golden/*.pt from the reference's
+UNMODIFIED model files (/root/reference, this container only) run behind oracle/thirdparty.
+
+    python -m oracle.gen_golden            # rewrites tests/golden/
+
+Inputs come from magnet_b200/synthetic.py seeds (also stored in the fixture when small);
+weights from synthetic.seeded_state_dict (order independent), loaded into the reference
+modules with strict=True.  Each fixture stores what the reference produced: edge lists,
+kNN assignment, per-layer outputs, predictions, and gradients.
+"""
+import os
+import sys
+
+import torch
+
+from oracle import reference_loader as rl
+from oracle import graph as G
+from magnet_b200 import synthetic as S
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _shapes(module):
+    return {k: tuple(v.shape) for k, v in module.state_dict().items()}
+
+
+def _load_seeded(module, seed):
+    sd = S.seeded_state_dict(_shapes(module), seed)
+    module.load_state_dict(sd, strict=True)
+    return sd
+
+
+def _checked_mesh_batch(make, r_of, loop_max, tries=20):
+    """redraw until no pair sits within 4 ulp of the radius (SURVEY §7 hard part 1)"""
+    for k in range(tries):
+        b, seed = make(k)
+        x, r, batch = r_of(b)
+        if G.radius_margin_ulps(x, r, batch) > 4:
+            return b, seed
+    raise RuntimeError("could not draw a mesh with a safe radius margin")
+
+
+def gen_radius(ref):
+    cases = {}
+    specs = [  # name, kind, B, N, d, r, loop
+        ("uniform2d_r012_noloop", "uniform", 3, 300, 2, 0.12, False),
+        ("uniform2d_r012_loop", "uniform", 3, 300, 2, 0.12, True),
+        ("uniform2d_r03_trunc_noloop", "uniform", 2, 400, 2, 0.3, False),
+        ("uniform2d_r03_trunc_loop", "uniform", 2, 400, 2, 0.3, True),
+        ("regular2d_16_trunc_noloop", "regular", 2, 256, 2, 0.31, False),
+        ("concentrated2d_r008_loop", "concentrated", 2, 512, 2, 0.08, True),
+        ("sorted1d_noloop", "sorted1d", 4, 50, 1, 1.0, False),
+        ("sorted1d_loop", "sorted1d", 4, 50, 1, 1.0, True),
+        ("huge_radius_loop", "uniform", 2, 70, 2, 5.0, True),
+        ("tiny_radius_noloop", "uniform", 2, 70, 2, 1e-4, False),
+    ]
+    for idx, (name, kind, B, N, d, r, loop) in enumerate(specs):
+        for attempt in range(50):
+            g = S._gen(1000 + 50 * idx + attempt)
+            x = torch.cat([S.mesh(kind, N, d, g) for _ in range(B)], 0)
+            if kind == "concentrated":
+                x = 2 * x - 1
+            batch = torch.arange(B).repeat_interleave(N)
+            if G.radius_margin_ulps(x, r, batch) > 4:
+                break
+        # the reference's own call: torch_geometric.nn.radius_graph (models/magnet_gnn.py:293)
+        from torch_geometric.nn import radius_graph
+        ei = radius_graph(x, r=r, batch=batch, loop=loop)
+        ei_nofma = G.radius_graph(x, r, batch, loop=loop, fma=False)
+        assert torch.equal(ei, ei_nofma), "margin check failed to make the graph rounding independent"
+        cases[name] = dict(x=x, batch=batch, r=r, loop=loop, edge_index=ei)
+    torch.save(cases, os.path.join(OUT, "radius_graph.pt"))
+    return cases
+
+
+def gen_knn(ref):
+    from torch_geometric.nn import knn
+    cases = {}
+    specs = [("2d_k4", 2, 3, 200, 150, 4), ("2d_k16", 2, 2, 300, 100, 16), ("1d_k4", 1, 4, 25, 16, 4),
+             ("2d_k32", 2, 1, 500, 64, 32), ("2d_k4_dupes", 2, 2, 64, 40, 4)]
+    for idx, (name, d, B, L, Nq, k) in enumerate(specs):
+        g = S._gen(2000 + idx)
+        xl = torch.cat([2 * S.mesh("uniform", L, d, g) - 1 for _ in range(B)], 0)
+        xq = torch.cat([2 * S.mesh("uniform", Nq, d, g) - 1 for _ in range(B)], 0)
+        if name.endswith("dupes"):           # exact ties: duplicated low-res points
+            xl[1::2] = xl[0::2]
+        bl = torch.arange(B).repeat_interleave(L)
+        bq = torch.arange(B).repeat_interleave(Nq)
+        ai = knn(xl, xq, k, bl, bq)
+        cases[name] = dict(x=xl, y=xq, k=k, batch_x=bl, batch_y=bq, assign_index=ai)
+    torch.save(cases, os.path.join(OUT, "knn.pt"))
+
+
+def gen_gnn_layer(ref):
+    """One GNN_Layer (2-D flavour, models/mpnn_2d.py:27-90) forward + backward."""
+    out = {}
+    for name, mod, dp, tw in (("mpnn_2d", ref.mpnn_2d, 2, 10), ("mpnn_1d", ref.mpnn, 1, 25)):
+        layer = mod.GNN_Layer(128, 128, 128, tw, 1)
+        _load_seeded(layer, 11)
+        g = S._gen(3000 + dp)
+        B, N = 3, 150
+        pos = torch.rand(B * N, dp, generator=g)
+        batch = torch.arange(B).repeat_interleave(N)
+        ei = G.radius_graph(pos if dp == 2 else pos, 0.16 if dp == 2 else 0.05, batch, loop=False)
+        x = torch.randn(B * N, 128, generator=g).requires_grad_()
+        u = torch.randn(B * N, tw, generator=g).requires_grad_()
+        var = torch.rand(B * N, 1, generator=g)
+        posx = pos.clone().requires_grad_()
+        y = layer(x, u, posx, var, ei, batch)
+        gy = torch.randn(y.shape, generator=g)
+        (y * gy).sum().backward()
+        out[name] = dict(x=x.detach(), u=u.detach(), pos=pos, variables=var, edge_index=ei, batch=batch,
+                         time_window=tw, seed=11, y=y.detach(), grad_y=gy, grad_x=x.grad, grad_u=u.grad,
+                         grad_pos=posx.grad,
+                         grads={k: p.grad.clone() for k, p in layer.named_parameters()})
+    torch.save(out, os.path.join(OUT, "gnn_layer.pt"))
+
+
+def gen_mpnn(ref):
+    out = {}
+    # config 2 shape, reduced: MPNN_2d on an irregular-uniform mesh
+    m = ref.mpnn_2d.MPNN_2d(rl.mpnn_2d_hparams()).eval()
+    _load_seeded(m, 21)
+    b = S.graph_batch(B=2, N=256, nt=50, d=2, kind="uniform", seed=21)
+    u = b["u"].float().permute(0, 2, 1)
+    graph = m._build_graph(u[:, :10], b["t"], b["x"], steps=[9] * 2)
+    with torch.no_grad():
+        y = m.forward(graph, b["x"][0, -1], b["t"][0, -1], b["t"][0][1] - b["t"][0][0])
+    m.validation_step(b, 0)
+    out["mpnn_2d"] = dict(batch=b, seed=21, hparams=dict(rl.mpnn_2d_hparams()), edge_index=graph.edge_index,
+                          pos=graph.pos, y=y, val_loss=m.logged["val_loss"])
+    # training step gradient (BPTT through u, teacher_forcing False)
+    m.train()
+    loss = m.training_step(b, 0)
+    loss.backward()
+    out["mpnn_2d"]["train_loss"] = loss.detach()
+    out["mpnn_2d"]["grad_norms"] = {k: p.grad.norm() for k, p in m.named_parameters()}
+    out["mpnn_2d"]["grad_embedding0"] = m.embedding_mlp[0].weight.grad.clone()
+    # config 1 flavour: 1-D MPNN, tw=25
+    m1 = ref.mpnn.MPNN(rl.mpnn_hparams(time_window=25)).eval()
+    _load_seeded(m1, 22)
+    b1 = S.graph_batch(B=4, N=50, nt=250, d=1, kind="sorted1d", seed=22)
+    u1 = b1["u"].permute(0, 2, 1)
+    x1 = b1["x"].squeeze(-1)
+    g1 = m1._build_graph(u1[:, :25], b1["t"], x1, steps=[0] * 4)
+    with torch.no_grad():
+        y1 = m1.forward(g1, x1[0, -1], b1["t"][0, -1], b1["t"][0][1] - b1["t"][0][0])
+    out["mpnn_1d"] = dict(batch=b1, seed=22, hparams=dict(rl.mpnn_hparams(time_window=25)),
+                          edge_index=g1.edge_index, y=y1)
+    torch.save(out, os.path.join(OUT, "mpnn.pt"))
+
+
+def gen_magnet(ref):
+    out = {}
+    hp = rl.magnet_gnn_hparams()
+    m = ref.magnet_gnn.MAgNetGNN(hp).eval()
+    sd = _load_seeded(m, 31)
+    b = S.implicit_batch(B=2, L=96, Nq=64, nt=50, d=2, kind="concentrated", seed=31)
+    inp, hr_last = b["lr_frames"][:, :10], b["hr_points"][:, 9]
+    tt = b["t"][:, :20]
+    with torch.no_grad():
+        u = inp.permute(0, 3, 1, 2).reshape(2, 96, -1)
+        nf, ei, ef = m._build_graph(u, b["coords_lr"], tt[:, :10])
+        nfe, efe = m.encoder(nf, ei, ef)
+        x1, e1 = m.processor.gnn_stacks[0](nfe, ei, efe)
+        lr_encoded, _ = m.processor(nfe, ei, efe)
+        z = m.continuous_decoder(inp, lr_encoded, b["coords_lr"], b["coords_hr"], tt)
+        out_hr, out_lr, hr_points = m.forward(inp, b["coords_lr"], b["coords_hr"], tt, hr_last)
+    m.validation_step(b, 0)
+    out["forward"] = dict(batch=b, seed=31, hparams=dict(hp), node_features=nf, edge_index=ei, edge_features=ef,
+                          enc_nodes=nfe, enc_edges=efe, in0_x=x1, lr_encoded=lr_encoded, z=z,
+                          out_hr=out_hr, out_lr=out_lr, hr_points=hr_points, val_loss=m.logged["val_loss"])
+    m.train()
+    loss = m.training_step(b, 0)
+    loss.backward()
+    out["forward"]["train_loss"] = loss.detach()
+    out["forward"]["grad_norms"] = {k: p.grad.norm() for k, p in m.named_parameters()}
+    out["forward"]["grad_proj_head"] = m.proj_head.weight.grad.clone()
+    # interpolation variants of the decoder
+    for interp in ("knn", "sph"):
+        m.interpolation = interp
+        with torch.no_grad():
+            out[f"z_{interp}"] = m.continuous_decoder(inp, lr_encoded, b["coords_lr"], b["coords_hr"], tt)
+    torch.save(out, os.path.join(OUT, "magnet_gnn.pt"))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = rl.load()
+    torch.manual_seed(0)
+    gen_radius(ref)
+    gen_knn(ref)
+    gen_gnn_layer(ref)
+    gen_mpnn(ref)
+    gen_magnet(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
