@@ -1,0 +1,152 @@
+/*
+ * magnet_b200 — C ABI of the B200-native MAgNet hot path (libmagnet_b200.so).
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface
+ * (jaggbow/magnet, file:line) it replaces.  Conventions:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless marked host;
+ *   - the CALLER owns every buffer, including workspaces (size them with the *_workspace
+ *     queries); the library never allocates or frees device memory;
+ *   - every call takes an explicit cudaStream_t (pass as void*), assumes the caller has set
+ *     the device, is re-entrant, and never synchronises the host unless stated;
+ *   - return 0 on success, <0 on error (-1 bad argument, -2 workspace too small, -3 capacity
+ *     overflow, -4 CUDA error); mgb_last_error() returns a thread-local message;
+ *   - features are fp32 row-major; public indices are int64 exactly as the reference's
+ *     (edge_index, assign_index); private plans are int32.
+ * Hidden width is fixed at 128 (hidden_features / latent_dim / n_chan of every reference config).
+ */
+#ifndef MAGNET_B200_H
+#define MAGNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_ABI_VERSION 1
+
+int mgb_abi_version(void);
+const char* mgb_last_error(void);
+/* kernels launched by this library in this process so far (bench.py reports the per-step delta) */
+int64_t mgb_launch_count(void);
+/* Optional per-kernel device timing (CUDA events on the launching stream) for bench.py's roofline.
+ * kernel ids: 0 GNN edge fwd, 1 GNN edge bwd, 2 node GEMM, 3 weight-grad, 4 graph build,
+ * 5 InteractionNetwork edge fwd, 6 InteractionNetwork edge bwd, 7 INR decode.
+ * total_ms / count are HOST pointers; collect synchronises on the recorded events. */
+int mgb_profile_enable(int on);
+int mgb_profile_collect(int kernel_id, double* total_ms, int64_t* count);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph construction.
+ * Replaces torch_geometric.nn.radius_graph as called at models/mpnn_2d.py:245, models/mpnn.py:245
+ * (loop=False) and models/magnet_gnn.py:293 (loop=True); torch_cluster CUDA ordering, default
+ * max_num_neighbors = 32, bit-exact including the index-order truncation.
+ *
+ * Phase 1 (no host sync): neighbour lists.  cap = max_num_neighbors + (loop ? 0 : 1).
+ *   pos [n, d] fp32 (d = 1 or 2), ptr [n_samples+1] int64 node offsets of the samples,
+ *   nbr [n, cap] int32 (out), deg [n] int32 (out), rowptr [n+1] int32 (out; rowptr[n] = E).
+ * Phase 2: edge_index [2, E] int64 in the reference's order (sorted by centre, then neighbour);
+ *   centre_row = 1 gives PyG's [neighbour; centre] (mpnn*), centre_row = 0 gives MAgNetGNN's
+ *   swapped [centre; neighbour] (models/magnet_gnn.py:294-296).  col [E] int32 (optional) = the
+ *   neighbour of every edge.
+ * ------------------------------------------------------------------------------------------- */
+size_t mgb_radius_graph_workspace(int64_t n, int n_samples);
+int mgb_radius_graph_search(const float* pos, int64_t n, int d, const int64_t* ptr, int n_samples, double r,
+                            int max_num_neighbors, int loop, int32_t* nbr, int32_t* deg, int32_t* rowptr,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int mgb_radius_graph_emit(const int32_t* nbr, const int32_t* rowptr, int64_t n, int cap, int centre_row,
+                          int64_t n_edges, int64_t* edge_index, int32_t* col, void* stream);
+
+/* Replaces torch_geometric.nn.knn as called at models/magnet_gnn.py:247.
+ *   x [nx, d] (searched set), y [ny, d] (queries), ptr_x/ptr_y [n_samples+1] int64, k <= 64.
+ *   out_idx [ny, k] int64: ascending distance, ties -> lower index, -1 where the sample has < k rows.
+ *   out_dist [ny, k] fp32 (optional, may be NULL). */
+size_t mgb_knn_workspace(int64_t nx, int n_samples);
+int mgb_knn(const float* x, int64_t nx, const float* y, int64_t ny, int d, const int64_t* ptr_x, const int64_t* ptr_y,
+            int n_samples, int k, int64_t* out_idx, float* out_dist, void* workspace, size_t workspace_bytes,
+            void* stream);
+
+/* Aggregation plan for an arbitrary edge_index (what MessagePassing.propagate + scatter(reduce='mean')
+ * do implicitly, models/mpnn_2d.py:46,69; models/magnet_gnn.py:54,76): stable sort of the edges by
+ * the aggregation endpoint agg = edge_index[1], plus the transposed plan by other = edge_index[0].
+ *   rowptr [n_nodes+1], perm [E] (COO edge id at each position), dst [E], src [E],
+ *   rowptr_t [n_nodes+1], pos_t [E] (positions grouped by source) — all int32;
+ *   bad_flag [1] int32 device: set to 1 when an index is outside [0, n_nodes). */
+size_t mgb_csr_plan_workspace(int64_t n_edges);
+int mgb_csr_plan(const int64_t* agg, const int64_t* other, int64_t n_edges, int64_t n_nodes, int32_t* rowptr,
+                 int32_t* perm, int32_t* dst, int32_t* src, int32_t* rowptr_t, int32_t* pos_t, int32_t* bad_flag,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MP-PDE message-passing layer.  Replaces GNN_Layer.forward (models/mpnn_2d.py:65-71; message
+ * :73-79, update :81-90, mean aggregation :46, InstanceNorm :63,70) and its autograd backward.
+ *   x [N,128], u [N,tw], pos [N,dp], var [N,nv];  dp = 2 (mpnn_2d) or 1 (mpnn), nv = 1.
+ *   plan from mgb_csr_plan (or mgb_radius_graph_*: for PyG-ordered graphs rowptr/col ARE the plan);
+ *   gptr [G+1] int64 node offsets of the graphs (the `batch` vector as offsets).
+ *   Weights in PyTorch layout: W1 [128, 256+tw+dp+nv], W2 [128,128], W3 [128, 256+nv], W4 [128,128].
+ *   packed: mgb_gnn_layer_packed_floats() floats, filled by mgb_gnn_layer_pack (re-run when the
+ *   parameters change).
+ *   Saved for backward: pq [N,256], agg [N,128], y1_pre [N,128], y2_pre [N,128], rstd [G,128].
+ * ------------------------------------------------------------------------------------------- */
+size_t mgb_gnn_layer_packed_floats(int tw, int dp, int nv);
+int mgb_gnn_layer_pack(const float* W1, const float* b1, const float* W2, const float* W3, const float* W4, int tw,
+                       int dp, int nv, float* packed, void* stream);
+size_t mgb_gnn_layer_fwd_workspace(int64_t n_nodes, int64_t n_edges, int n_graphs, int max_nodes_per_graph);
+int mgb_gnn_layer_fwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs, int max_nodes_per_graph,
+                      const float* x, const float* u, const float* pos, const float* var, const int32_t* rowptr,
+                      const int32_t* dst, const int32_t* src, const int64_t* gptr, const float* packed,
+                      const float* b2, const float* b3, const float* b4, float* y, float* pq, float* agg,
+                      float* y1_pre, float* y2_pre, float* rstd, void* workspace, size_t workspace_bytes,
+                      void* stream);
+size_t mgb_gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs,
+                                   int max_nodes_per_graph);
+/* du / dpos / dvar may be NULL.  accumulate_params != 0 adds into the d* parameter buffers. */
+int mgb_gnn_layer_bwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs, int max_nodes_per_graph,
+                      const float* dy, const float* x, const float* u, const float* pos, const float* var,
+                      const float* y, const float* pq, const float* agg, const float* y1_pre, const float* y2_pre,
+                      const float* rstd, const int32_t* rowptr, const int32_t* dst, const int32_t* src,
+                      const int32_t* rowptr_t, const int32_t* pos_t, const int64_t* gptr, const float* packed,
+                      const float* W2, const float* b2, const float* W3, const float* W4, float* dx, float* du,
+                      float* dpos, float* dvar, float* dW1, float* db1, float* dW2, float* db2, float* dW3,
+                      float* db3, float* dW4, float* db4, int accumulate_params, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row-wise dense stages (nn.Linear + activation, nn.LayerNorm) used by embedding_mlp
+ * (models/mpnn_2d.py:130-135), MLP (models/backbones/mlp.py:9-28), Encoder/Decoder/projector
+ * (models/magnet_gnn.py:11-42,119-137,194-197).  act: 0 none, 1 ReLU, 2 Swish.
+ *   y = act(x W^T + b) (+ residual);  W [out, in] PyTorch layout; wt = W^T [in, out] (mgb_transpose).
+ * ------------------------------------------------------------------------------------------- */
+int mgb_transpose(const float* in, int rows, int cols, float* out, void* stream);
+int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* wt, const float* bias,
+                   int act, const float* residual, float* y, float* y_pre, void* stream);
+size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features);
+/* dx = (dy * act'(y_pre)) W;  dW (+)= (dy * act'(y_pre))^T x;  db (+)= colsum.  dx may be NULL. */
+int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features,
+                   int out_features, const float* w, float* dx, float* dw, float* db, int accumulate_params,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int mgb_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int cols, float* y,
+                      float* stats /* [rows,2] mean,rstd */, void* stream);
+size_t mgb_layernorm_bwd_workspace(int64_t rows, int cols);
+int mgb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int64_t rows, int cols,
+                      float* dx, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* InstanceNorm alone (PyG InstanceNorm, models/mpnn_2d.py:63,70) — exposed for tests. */
+size_t mgb_instance_norm_workspace(int n_graphs, int max_nodes_per_graph);
+int mgb_instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes_per_graph, float* y,
+                          float* rstd, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hooks for the integer primitives (stable radix sort, exclusive scan). */
+size_t mgb_sort_workspace(int64_t n);
+int mgb_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       int64_t n, int bits, void* workspace, size_t workspace_bytes, void* stream);
+size_t mgb_scan_workspace(int64_t n);
+int mgb_exclusive_scan_i32(const int32_t* in, int32_t* out /* n+1 */, int64_t n, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGNET_B200_H */

@@ -1,0 +1,178 @@
+// magnet_b200 — extern "C" entry points (see include/magnet_b200.h for the contract).
+#include "internal.cuh"
+#include "../../include/magnet_b200.h"
+
+using namespace mgb;
+
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int mgb_abi_version(void) { return MGB_ABI_VERSION; }
+const char* mgb_last_error(void) { return mgb::last_error(); }
+int64_t mgb_launch_count(void) { return (int64_t)mgb::launch_count(); }
+
+int mgb_profile_enable(int on) { mgb::prof_enable(on != 0); return MGB_OK; }
+int mgb_profile_collect(int kernel_id, double* total_ms, int64_t* count) {
+    MGB_REQUIRE(kernel_id >= 0 && kernel_id < mgb::PROF_COUNT, "profile_collect: unknown kernel id %d", kernel_id);
+    long long c = 0;
+    int rc = mgb::prof_collect(kernel_id, total_ms, &c);
+    *count = c;
+    return rc;
+}
+
+size_t mgb_radius_graph_workspace(int64_t n, int n_samples) { return radius_workspace_bytes(n, n_samples); }
+
+int mgb_radius_graph_search(const float* pos, int64_t n, int d, const int64_t* ptr, int n_samples, double r,
+                            int max_num_neighbors, int loop, int32_t* nbr, int32_t* deg, int32_t* rowptr,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    return radius_search(pos, n, d, ptr, n_samples, r, max_num_neighbors, loop, nbr, deg, rowptr, workspace,
+                         workspace_bytes, STREAM(stream));
+}
+
+int mgb_radius_graph_emit(const int32_t* nbr, const int32_t* rowptr, int64_t n, int cap, int centre_row,
+                          int64_t n_edges, int64_t* edge_index, int32_t* col, void* stream) {
+    return radius_emit(nbr, rowptr, n, cap, centre_row, n_edges, edge_index, col, STREAM(stream));
+}
+
+size_t mgb_knn_workspace(int64_t nx, int n_samples) { return knn_workspace_bytes(nx, n_samples); }
+
+int mgb_knn(const float* x, int64_t nx, const float* y, int64_t ny, int d, const int64_t* ptr_x, const int64_t* ptr_y,
+            int n_samples, int k, int64_t* out_idx, float* out_dist, void* workspace, size_t workspace_bytes,
+            void* stream) {
+    return knn_search(x, nx, y, ny, d, ptr_x, ptr_y, n_samples, k, out_idx, out_dist, workspace, workspace_bytes,
+                      STREAM(stream));
+}
+
+size_t mgb_csr_plan_workspace(int64_t n_edges) { return csr_plan_workspace_bytes(n_edges); }
+
+int mgb_csr_plan(const int64_t* agg, const int64_t* other, int64_t n_edges, int64_t n_nodes, int32_t* rowptr,
+                 int32_t* perm, int32_t* dst, int32_t* src, int32_t* rowptr_t, int32_t* pos_t, int32_t* bad_flag,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    return csr_plan(agg, other, n_edges, n_nodes, rowptr, perm, dst, src, rowptr_t, pos_t, bad_flag, workspace,
+                    workspace_bytes, STREAM(stream));
+}
+
+size_t mgb_gnn_layer_packed_floats(int tw, int dp, int nv) { return gnn_layer_packed_floats(tw, dp, nv); }
+
+int mgb_gnn_layer_pack(const float* W1, const float* b1, const float* W2, const float* W3, const float* W4, int tw,
+                       int dp, int nv, float* packed, void* stream) {
+    MGB_REQUIRE(tw >= 1 && dp >= 1 && nv >= 1, "gnn_layer_pack: tw, dp, nv must be positive");
+    return gnn_layer_pack(W1, b1, W2, W3, W4, tw, dp, nv, packed, STREAM(stream));
+}
+
+size_t mgb_gnn_layer_fwd_workspace(int64_t n_nodes, int64_t n_edges, int n_graphs, int max_nodes_per_graph) {
+    return gnn_layer_fwd_workspace(n_nodes, n_edges, n_graphs, max_nodes_per_graph);
+}
+
+int mgb_gnn_layer_fwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs, int max_nodes_per_graph,
+                      const float* x, const float* u, const float* pos, const float* var, const int32_t* rowptr,
+                      const int32_t* dst, const int32_t* src, const int64_t* gptr, const float* packed,
+                      const float* b2, const float* b3, const float* b4, float* y, float* pq, float* agg,
+                      float* y1_pre, float* y2_pre, float* rstd, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph};
+    GnnFwdIO io{x, u, pos, var, rowptr, dst, src, gptr, packed, b2, b3, b4, y, pq, agg, y1_pre, y2_pre, rstd};
+    return gnn_layer_fwd(sh, io, workspace, workspace_bytes, STREAM(stream));
+}
+
+size_t mgb_gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs,
+                                   int max_nodes_per_graph) {
+    return gnn_layer_bwd_workspace(n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph);
+}
+
+int mgb_gnn_layer_bwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs, int max_nodes_per_graph,
+                      const float* dy, const float* x, const float* u, const float* pos, const float* var,
+                      const float* y, const float* pq, const float* agg, const float* y1_pre, const float* y2_pre,
+                      const float* rstd, const int32_t* rowptr, const int32_t* dst, const int32_t* src,
+                      const int32_t* rowptr_t, const int32_t* pos_t, const int64_t* gptr, const float* packed,
+                      const float* W2, const float* b2, const float* W3, const float* W4, float* dx, float* du,
+                      float* dpos, float* dvar, float* dW1, float* db1, float* dW2, float* db2, float* dW3,
+                      float* db3, float* dW4, float* db4, int accumulate_params, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph};
+    GnnBwdIO io{dy, x, u, pos, var, y, pq, agg, y1_pre, y2_pre, rstd, rowptr, dst, src, rowptr_t, pos_t, gptr, packed,
+                W2, b2, W3, W4, dx, du, dpos, dvar, dW1, db1, dW2, db2, dW3, db3, dW4, db4, accumulate_params};
+    return gnn_layer_bwd(sh, io, workspace, workspace_bytes, STREAM(stream));
+}
+
+int mgb_transpose(const float* in, int rows, int cols, float* out, void* stream) {
+    return launch_transpose(in, rows, cols, cols, out, rows, STREAM(stream));
+}
+
+int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* wt, const float* bias,
+                   int act, const float* residual, float* y, float* y_pre, void* stream) {
+    MGB_REQUIRE(rows >= 0 && rows < ((int64_t)1 << 31), "linear_fwd: row count out of range");
+    MGB_REQUIRE(act >= 0 && act <= 2, "linear_fwd: unknown activation %d", act);
+    GemmArgs g{};
+    g.a.p[0] = x; g.a.ld[0] = in_features; g.a.k[0] = in_features; g.a.nseg = 1;
+    g.b = wt; g.ldb = out_features; g.bias = bias;
+    g.residual = residual; g.ldr = out_features;
+    g.c = y; g.ldc = out_features; g.c_pre = y_pre; g.ldcp = out_features; g.act = act;
+    g.M = (int)rows; g.N = out_features; g.K = in_features;
+    return launch_gemm(g, STREAM(stream));
+}
+
+size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features) {
+    return wgrad_workspace_bytes((int)rows, out_features, in_features) + 1024;
+}
+
+int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features,
+                   int out_features, const float* w, float* dx, float* dw, float* db, int accumulate_params,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+    MGB_REQUIRE(rows >= 0 && rows < ((int64_t)1 << 31), "linear_bwd: row count out of range");
+    MGB_REQUIRE(act == 0 || y_pre != nullptr, "linear_bwd: an activation needs the saved pre-activation");
+    if (dw) {
+        WgradArgs wg{};
+        wg.dy = dy; wg.lddy = out_features; wg.y_pre = act ? y_pre : nullptr; wg.y_act = act;
+        wg.a.p[0] = x; wg.a.ld[0] = in_features; wg.a.k[0] = in_features; wg.a.nseg = 1;
+        wg.rows = (int)rows; wg.N = out_features; wg.K = in_features;
+        wg.dw = dw; wg.lddw = in_features; wg.db = db; wg.accumulate = accumulate_params;
+        MGB_TRY(launch_wgrad(wg, workspace, workspace_bytes, STREAM(stream)));
+    }
+    if (dx) {
+        GemmArgs g{};
+        g.a.p[0] = dy; g.a.ld[0] = out_features; g.a.k[0] = out_features; g.a.nseg = 1;
+        g.a.pre = act ? y_pre : nullptr; g.a.pre_act = act;
+        g.b = w; g.ldb = in_features; g.c = dx; g.ldc = in_features;
+        g.M = (int)rows; g.N = in_features; g.K = out_features;
+        MGB_TRY(launch_gemm(g, STREAM(stream)));
+    }
+    return MGB_OK;
+}
+
+int mgb_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int cols, float* y,
+                      float* stats, void* stream) {
+    return launch_layernorm_fwd(x, gamma, beta, y, stats, rows, cols, STREAM(stream));
+}
+
+size_t mgb_layernorm_bwd_workspace(int64_t rows, int cols) { return layernorm_bwd_workspace_bytes(rows, cols); }
+
+int mgb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int64_t rows, int cols,
+                      float* dx, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    return launch_layernorm_bwd(dy, x, gamma, stats, dx, dgamma, dbeta, accumulate_params, rows, cols, workspace,
+                                workspace_bytes, STREAM(stream));
+}
+
+size_t mgb_instance_norm_workspace(int n_graphs, int max_nodes_per_graph) {
+    return inorm_workspace_bytes(n_graphs, max_nodes_per_graph);
+}
+
+int mgb_instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes_per_graph, float* y,
+                          float* rstd, void* workspace, size_t workspace_bytes, void* stream) {
+    return instance_norm_fwd(x, gptr, n_graphs, max_nodes_per_graph, y, rstd, workspace, workspace_bytes, STREAM(stream));
+}
+
+size_t mgb_sort_workspace(int64_t n) { return sort_workspace_bytes(n); }
+int mgb_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                       int64_t n, int bits, void* workspace, size_t workspace_bytes, void* stream) {
+    return radix_sort_pairs(keys_in, vals_in, keys_out, vals_out, n, bits, workspace, workspace_bytes, STREAM(stream));
+}
+size_t mgb_scan_workspace(int64_t n) { return scan_workspace_bytes(n); }
+int mgb_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+    return exclusive_scan_i32(in, out, n, workspace, workspace_bytes, STREAM(stream));
+}
+
+}  // extern "C"

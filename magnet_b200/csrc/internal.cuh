@@ -1,0 +1,67 @@
+// magnet_b200 — declarations shared between the kernel translation units and capi.cu
+#pragma once
+#include "dense.cuh"
+
+namespace mgb {
+
+const char* last_error();
+void prof_enable(bool on);
+int prof_collect(int id, double* total_ms, long long* count);
+
+// graph.cu
+size_t radius_workspace_bytes(int64_t n, int n_samples);
+int radius_search(const float* pos, int64_t n, int d, const int64_t* ptr, int n_samples, double r, int max_num_neighbors,
+                  int loop, int32_t* nbr, int32_t* deg, int32_t* rowptr, void* ws, size_t ws_bytes, cudaStream_t s);
+int radius_emit(const int32_t* nbr, const int32_t* rowptr, int64_t n, int cap, int centre_row, int64_t n_edges,
+                int64_t* edge_index, int32_t* col, cudaStream_t s);
+size_t knn_workspace_bytes(int64_t nx, int n_samples);
+int knn_search(const float* x, int64_t nx, const float* y, int64_t ny, int d, const int64_t* ptr_x, const int64_t* ptr_y,
+               int n_samples, int k, int64_t* out_idx, float* out_dist, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t csr_plan_workspace_bytes(int64_t n_edges);
+int csr_plan(const int64_t* agg, const int64_t* other, int64_t n_edges, int64_t n_nodes, int32_t* rowptr, int32_t* perm,
+             int32_t* dst, int32_t* src, int32_t* rowptr_t, int32_t* pos_t, int* bad_flag, void* ws, size_t ws_bytes,
+             cudaStream_t s);
+
+// gnn_layer.cu
+struct GnnLayerShape {
+    int64_t n_nodes, n_edges;
+    int tw, dp, nv;
+    int n_graphs, max_nodes_per_graph;
+    int Kc() const { return 128 + tw + dp + nv; }
+    int K1() const { return 256 + tw + dp + nv; }
+    int K3() const { return 256 + nv; }
+};
+struct GnnFwdIO {
+    const float *x, *u, *pos, *var;
+    const int32_t *rowptr, *dstv, *srcv;
+    const int64_t* gptr;
+    const float* packed;
+    const float *b2, *b3, *b4;
+    float* y;
+    float *pq, *agg, *y1_pre, *y2_pre, *rstd;
+};
+struct GnnBwdIO {
+    const float* dy;
+    const float *x, *u, *pos, *var;
+    const float* y;
+    const float *pq, *agg, *y1_pre, *y2_pre, *rstd;
+    const int32_t *rowptr, *dstv, *srcv, *rowptr_t, *pos_t;
+    const int64_t* gptr;
+    const float* packed;
+    const float *W2, *b2, *W3, *W4;
+    float *dx, *du, *dpos, *dvar;
+    float *dW1, *db1, *dW2, *db2, *dW3, *db3, *dW4, *db4;
+    int accumulate_params;
+};
+size_t gnn_layer_packed_floats(int tw, int dp, int nv);
+int gnn_layer_pack(const float* W1, const float* b1, const float* W2, const float* W3, const float* W4, int tw, int dp,
+                   int nv, float* packed, cudaStream_t s);
+size_t gnn_layer_fwd_workspace(int64_t n_nodes, int64_t n_edges, int n_graphs, int max_nodes);
+int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs, int max_nodes);
+int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t inorm_workspace_bytes(int n_graphs, int max_nodes);
+int instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes, float* y, float* rstd_out, void* ws,
+                      size_t ws_bytes, cudaStream_t s);
+
+}  // namespace mgb

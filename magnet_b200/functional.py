@@ -1,0 +1,191 @@
+"""Autograd bindings of the C-ABI kernels.  Forward and backward both run hand-written CUDA;
+nothing here computes on the CPU or through PyTorch ops (torch is used for allocation only).
+Backward runs on PyTorch's autograd thread: every call passes the current stream explicitly.
+"""
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .graph import AggregationPlan, GraphSegments
+
+ACT = {"none": 0, "relu": 1, "swish": 2}
+
+
+def _empty(shape, ref):
+    return torch.empty(shape, dtype=torch.float32, device=ref.device)
+
+
+# --------------------------------------------------------------------------------------------
+# GNN_Layer (models/mpnn_2d.py:27-90)
+# --------------------------------------------------------------------------------------------
+def pack_gnn_layer(W1, b1, W2, W3, W4, tw: int, dp: int, nv: int) -> torch.Tensor:
+    L = _lib.lib()
+    packed = _empty((L.mgb_gnn_layer_packed_floats(tw, dp, nv),), W1)
+    _lib.check(L.mgb_gnn_layer_pack(_lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(W3), _lib.ptr(W4), tw, dp, nv,
+                                    _lib.ptr(packed), _lib.stream()), "gnn_layer_pack")
+    return packed
+
+
+class GNNLayerFn(torch.autograd.Function):
+    """y = InstanceNorm(x + update(x, mean_j message(x_i, x_j, u, pos, var)))"""
+
+    @staticmethod
+    def forward(ctx, x, u, pos, var, W1, b1, W2, b2, W3, b3, W4, b4, plan: AggregationPlan, seg: GraphSegments):
+        _lib.require_cuda(x, u, pos, var, W1)
+        L = _lib.lib()
+        x, u, pos, var = (_lib.f32c(t) for t in (x, u, pos, var))
+        W1, b1, W2, b2, W3, b3, W4, b4 = (_lib.f32c(t.detach()) for t in (W1, b1, W2, b2, W3, b3, W4, b4))
+        N, H = x.shape
+        tw, dp, nv = u.shape[1], pos.shape[1], var.shape[1]
+        if H != 128 or W2.shape != (128, 128) or W1.shape != (128, 256 + tw + dp + nv) or W3.shape != (128, 256 + nv):
+            raise RuntimeError("GNN_Layer kernels are built for in=out=hidden=128 and message_net_1 of width "
+                               f"256+tw+dp+nv; got x {tuple(x.shape)}, W1 {tuple(W1.shape)}, W3 {tuple(W3.shape)}")
+        if plan.n_nodes != N:
+            raise RuntimeError("aggregation plan was built for a different node count")
+        packed = pack_gnn_layer(W1, b1, W2, W3, W4, tw, dp, nv)
+        y = _empty((N, H), x)
+        pq = _empty((N, 2 * H), x)
+        agg = _empty((N, H), x)
+        y1_pre = _empty((N, H), x)
+        y2_pre = _empty((N, H), x)
+        rstd = _empty((max(seg.n_graphs, 1), H), x)
+        ws = _lib.workspace(L.mgb_gnn_layer_fwd_workspace(N, plan.n_edges, seg.n_graphs, seg.max_nodes), x.device)
+        _lib.check(L.mgb_gnn_layer_fwd(N, plan.n_edges, tw, dp, nv, seg.n_graphs, seg.max_nodes, _lib.ptr(x), _lib.ptr(u),
+                                       _lib.ptr(pos), _lib.ptr(var), _lib.ptr(plan.rowptr), _lib.ptr(plan.dst),
+                                       _lib.ptr(plan.src), _lib.ptr(seg.gptr), _lib.ptr(packed), _lib.ptr(b2),
+                                       _lib.ptr(b3), _lib.ptr(b4), _lib.ptr(y), _lib.ptr(pq), _lib.ptr(agg),
+                                       _lib.ptr(y1_pre), _lib.ptr(y2_pre), _lib.ptr(rstd), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream()), "gnn_layer_fwd")
+        ctx.save_for_backward(x, u, pos, var, y, pq, agg, y1_pre, y2_pre, rstd, packed, W1, W2, b2, W3, W4)
+        ctx.plan, ctx.seg = plan, seg
+        ctx.dims = (N, tw, dp, nv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x, u, pos, var, y, pq, agg, y1_pre, y2_pre, rstd, packed, W1, W2, b2, W3, W4 = ctx.saved_tensors
+        plan, seg = ctx.plan, ctx.seg
+        N, tw, dp, nv = ctx.dims
+        dy = _lib.f32c(dy)
+        need = ctx.needs_input_grad
+        dx = _empty(x.shape, x)
+        du = _empty(u.shape, x) if need[1] else None
+        dpos = _empty(pos.shape, x) if need[2] else None
+        dvar = _empty(var.shape, x) if need[3] else None
+        dW1, db1 = _empty(W1.shape, x), _empty((128,), x)
+        dW2, db2 = _empty((128, 128), x), _empty((128,), x)
+        dW3, db3 = _empty(W3.shape, x), _empty((128,), x)
+        dW4, db4 = _empty((128, 128), x), _empty((128,), x)
+        with torch.cuda.device(x.device):
+            ws = _lib.workspace(L.mgb_gnn_layer_bwd_workspace(N, plan.n_edges, tw, dp, nv, seg.n_graphs, seg.max_nodes),
+                                x.device)
+            _lib.check(L.mgb_gnn_layer_bwd(
+                N, plan.n_edges, tw, dp, nv, seg.n_graphs, seg.max_nodes, _lib.ptr(dy), _lib.ptr(x), _lib.ptr(u),
+                _lib.ptr(pos), _lib.ptr(var), _lib.ptr(y), _lib.ptr(pq), _lib.ptr(agg), _lib.ptr(y1_pre),
+                _lib.ptr(y2_pre), _lib.ptr(rstd), _lib.ptr(plan.rowptr), _lib.ptr(plan.dst), _lib.ptr(plan.src),
+                _lib.ptr(plan.rowptr_t), _lib.ptr(plan.pos_t), _lib.ptr(seg.gptr), _lib.ptr(packed), _lib.ptr(W2),
+                _lib.ptr(b2), _lib.ptr(W3), _lib.ptr(W4), _lib.ptr(dx), _lib.ptr(du), _lib.ptr(dpos), _lib.ptr(dvar),
+                _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2), _lib.ptr(dW3), _lib.ptr(db3),
+                _lib.ptr(dW4), _lib.ptr(db4), 0, _lib.ptr(ws), ws.numel(), _lib.stream()), "gnn_layer_bwd")
+        return dx, du, dpos, dvar, dW1, db1, dW2, db2, dW3, db3, dW4, db4, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# row-wise Linear (+activation, +residual) and LayerNorm
+# --------------------------------------------------------------------------------------------
+class LinearActFn(torch.autograd.Function):
+    """y = act(x W^T + b) (+ residual) — nn.Linear followed by Swish/ReLU (models/backbones/mlp.py:24-27)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act: int, residual: Optional[torch.Tensor]):
+        _lib.require_cuda(x, W)
+        L = _lib.lib()
+        shape = x.shape
+        x2 = _lib.f32c(x).reshape(-1, shape[-1])
+        Wc, bc = _lib.f32c(W.detach()), _lib.f32c(b.detach())
+        rows, fin = x2.shape
+        fout = Wc.shape[0]
+        wt = _empty((fin, fout), x2)
+        _lib.check(L.mgb_transpose(_lib.ptr(Wc), fout, fin, _lib.ptr(wt), _lib.stream()), "transpose")
+        y = _empty((rows, fout), x2)
+        y_pre = _empty((rows, fout), x2) if act != 0 else None
+        res = _lib.f32c(residual).reshape(rows, fout) if residual is not None else None
+        _lib.check(L.mgb_linear_fwd(_lib.ptr(x2), rows, fin, fout, _lib.ptr(wt), _lib.ptr(bc), act, _lib.ptr(res),
+                                    _lib.ptr(y), _lib.ptr(y_pre), _lib.stream()), "linear_fwd")
+        ctx.save_for_backward(x2, Wc, y_pre)
+        ctx.act, ctx.shape, ctx.has_res = act, shape, residual is not None
+        return y.reshape(*shape[:-1], fout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x2, Wc, y_pre = ctx.saved_tensors
+        rows, fin = x2.shape
+        fout = Wc.shape[0]
+        dy2 = _lib.f32c(dy).reshape(rows, fout)
+        dx = _empty((rows, fin), x2) if ctx.needs_input_grad[0] else None
+        dW, db = _empty(Wc.shape, x2), _empty((fout,), x2)
+        with torch.cuda.device(x2.device):
+            ws = _lib.workspace(L.mgb_linear_bwd_workspace(rows, fin, fout), x2.device)
+            _lib.check(L.mgb_linear_bwd(_lib.ptr(dy2), _lib.ptr(y_pre), ctx.act, _lib.ptr(x2), rows, fin, fout,
+                                        _lib.ptr(Wc), _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db), 0, _lib.ptr(ws),
+                                        ws.numel(), _lib.stream()), "linear_bwd")
+        dres = dy if ctx.has_res else None
+        return (dx.reshape(ctx.shape) if dx is not None else None), dW, db, None, dres
+
+
+def linear_act(x, W, b, act: str = "none", residual=None):
+    return LinearActFn.apply(x, W, b, ACT[act], residual)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(128): eps 1e-5, biased variance, affine (models/magnet_gnn.py:27,35,60,67)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        _lib.require_cuda(x, gamma)
+        L = _lib.lib()
+        shape = x.shape
+        x2 = _lib.f32c(x).reshape(-1, shape[-1])
+        g, b = _lib.f32c(gamma.detach()), _lib.f32c(beta.detach())
+        rows, cols = x2.shape
+        y = _empty((rows, cols), x2)
+        stats = _empty((max(rows, 1), 2), x2)
+        _lib.check(L.mgb_layernorm_fwd(_lib.ptr(x2), _lib.ptr(g), _lib.ptr(b), rows, cols, _lib.ptr(y), _lib.ptr(stats),
+                                       _lib.stream()), "layernorm_fwd")
+        ctx.save_for_backward(x2, g, stats)
+        ctx.shape = shape
+        return y.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _lib.lib()
+        x2, g, stats = ctx.saved_tensors
+        rows, cols = x2.shape
+        dy2 = _lib.f32c(dy).reshape(rows, cols)
+        dx = _empty((rows, cols), x2)
+        dg, db = _empty((cols,), x2), _empty((cols,), x2)
+        with torch.cuda.device(x2.device):
+            ws = _lib.workspace(L.mgb_layernorm_bwd_workspace(rows, cols), x2.device)
+            _lib.check(L.mgb_layernorm_bwd(_lib.ptr(dy2), _lib.ptr(x2), _lib.ptr(g), _lib.ptr(stats), rows, cols,
+                                           _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db), 0, _lib.ptr(ws), ws.numel(),
+                                           _lib.stream()), "layernorm_bwd")
+        return dx.reshape(ctx.shape), dg, db
+
+
+def layer_norm(x, gamma, beta):
+    return LayerNormFn.apply(x, gamma, beta)
+
+
+def instance_norm(x: torch.Tensor, seg: GraphSegments) -> torch.Tensor:
+    """Forward-only PyG InstanceNorm (tests / inference helper)."""
+    L = _lib.lib()
+    x = _lib.f32c(x)
+    y = torch.empty_like(x)
+    rstd = _empty((max(seg.n_graphs, 1), x.shape[1]), x)
+    ws = _lib.workspace(L.mgb_instance_norm_workspace(seg.n_graphs, seg.max_nodes), x.device)
+    _lib.check(L.mgb_instance_norm_fwd(_lib.ptr(x), _lib.ptr(seg.gptr), seg.n_graphs, seg.max_nodes, _lib.ptr(y),
+                                       _lib.ptr(rstd), _lib.ptr(ws), ws.numel(), _lib.stream()), "instance_norm_fwd")
+    return y

@@ -1,0 +1,293 @@
+"""Drop-in MAgNet[GNN] modules: ``MLP``, ``Encoder``, ``InteractionNetwork``, ``Processor``,
+``Decoder`` and ``MAgNetGNN`` — same names, constructor arguments, ``forward`` signatures and
+``state_dict`` keys as models/backbones/mlp.py and models/magnet_gnn.py of the reference.
+
+Deviation (flagged): the reference hard-codes d = 2 (`time_slice+3`, `time_slice+2`,
+`latent_dim+4`); here the widths are `time_slice+d+1`, `time_slice+d`, `latent_dim+d+2` with
+``hparams.dim`` (default 2), which is what BASELINE config 1 (1-D E1) needs.  For d = 2 the
+parameter shapes are identical to the reference's.
+"""
+import weakref
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import functional as MF
+from . import graph as MG
+from ._compat import LightningModule
+
+_ACT = {"relu": nn.ReLU(), "tanh": nn.Tanh(), "gelu": nn.GELU()}
+
+
+class MLP(nn.Module):
+    """models/backbones/mlp.py:9-28 — Linear at even indices of ``layers``, activation between,
+    none after the last.  Only 'relu' runs on the fused kernels (every reference use is relu)."""
+
+    def __init__(self, in_dim, hidden_list, out_dim, activation="relu"):
+        super().__init__()
+        assert activation in ("relu", "tanh", "gelu")
+        self.activation = activation
+        self.layers = nn.ModuleList()
+        self.layers.append(nn.Linear(in_dim, hidden_list[0]))
+        self.layers.append(_ACT[activation])
+        for i in range(len(hidden_list) - 1):
+            self.layers.append(nn.Linear(hidden_list[i], hidden_list[i + 1]))
+            self.layers.append(_ACT[activation])
+        self.layers.append(nn.Linear(hidden_list[-1], out_dim))
+
+    def linears(self):
+        return [m for m in self.layers if isinstance(m, nn.Linear)]
+
+    def forward(self, x, first_preact: Optional[torch.Tensor] = None):
+        """``first_preact``: pre-activation of the first Linear computed elsewhere (factorised
+        gather form used by InteractionNetwork); then ``x`` is ignored for that layer."""
+        if self.activation != "relu":
+            raise RuntimeError("magnet_b200 MLP kernels implement the reference's ReLU MLPs only")
+        lin = self.linears()
+        out = x
+        for n, l in enumerate(lin):
+            last = n + 1 == len(lin)
+            if n == 0 and first_preact is not None:
+                out = MF.relu(first_preact) if not last else first_preact
+                continue
+            out = MF.linear_act(out, l.weight, l.bias, "none" if last else "relu")
+        return out
+
+
+def _mlp_ln(seq: nn.Sequential, x, first_preact=None):
+    y = seq[0](x, first_preact=first_preact)
+    return MF.layer_norm(y, seq[1].weight, seq[1].bias)
+
+
+class Encoder(nn.Module):
+    """models/magnet_gnn.py:11-42."""
+
+    def __init__(self, node_in, node_out, edge_in, edge_out, mlp_layers, mlp_hidden):
+        super().__init__()
+        self.node_fn = nn.Sequential(MLP(node_in, [mlp_hidden] * mlp_layers, node_out), nn.LayerNorm(node_out))
+        self.edge_fn = nn.Sequential(MLP(edge_in, [mlp_hidden] * mlp_layers, edge_out), nn.LayerNorm(edge_out))
+
+    def forward(self, x, edge_index, e_features):
+        return _mlp_ln(self.node_fn, x), _mlp_ln(self.edge_fn, e_features)
+
+
+class InteractionNetwork(nn.Module):
+    """models/magnet_gnn.py:44-90.  x_i = x[edge_index[1]], x_j = x[edge_index[0]], mean at
+    edge_index[1]; returns (x_new + x, 2 * e_features) — the edge features are never updated from
+    the messages (quirk F3)."""
+
+    def __init__(self, node_in, node_out, edge_in, edge_out, mlp_layers, mlp_hidden):
+        super().__init__()
+        self.node_in = node_in
+        self.node_fn = nn.Sequential(MLP(node_in + edge_out, [mlp_hidden] * mlp_layers, node_out), nn.LayerNorm(node_out))
+        self.edge_fn = nn.Sequential(MLP(node_in + node_in + edge_in, [mlp_hidden] * mlp_layers, edge_out),
+                                     nn.LayerNorm(edge_out))
+
+    def forward(self, x, edge_index, e_features, *, plan=None):
+        n = x.shape[0]
+        if plan is None:
+            plan = MG.plan_for(edge_index, n)
+        h = self.node_in
+        first = self.edge_fn[0].layers[0]
+        W, b = first.weight, first.bias
+        # first Linear factorised over its three inputs: W [x_i, x_j, e] = P[dst] + Q[src] + R
+        p = MF.linear_act(x, W[:, :h], b, "none")
+        q = MF.linear_act(x, W[:, h:2 * h], torch.zeros_like(b), "none")
+        r = MF.linear_act(e_features, W[:, 2 * h:], torch.zeros_like(b), "none")
+        z0 = MF.edge_gather_add(p, q, r, edge_index, plan)
+        m = _mlp_ln(self.edge_fn, None, first_preact=z0)
+        agg = MF.scatter_mean(m, plan)
+        x_new = _mlp_ln(self.node_fn, torch.cat([agg, x], dim=-1))
+        return x_new + x, e_features + e_features
+
+
+class Processor(nn.Module):
+    """models/magnet_gnn.py:92-117 (the reference's aggr='max' base class is never exercised)."""
+
+    def __init__(self, node_in, node_out, edge_in, edge_out, num_message_passing_steps, mlp_num_layers, mlp_hidden_dim):
+        super().__init__()
+        self.gnn_stacks = nn.ModuleList([
+            InteractionNetwork(node_in, node_out, edge_in, edge_out, mlp_num_layers, mlp_hidden_dim)
+            for _ in range(num_message_passing_steps)])
+
+    def forward(self, x, edge_index, e_features, *, plan=None):
+        if plan is None:
+            plan = MG.plan_for(edge_index, x.shape[0])
+        for gnn in self.gnn_stacks:
+            x, e_features = gnn(x, edge_index, e_features, plan=plan)
+        return x, e_features
+
+
+class Decoder(nn.Module):
+    """models/magnet_gnn.py:119-137."""
+
+    def __init__(self, node_in, node_out, mlp_layers, mlp_hidden):
+        super().__init__()
+        self.node_fn = MLP(node_in, [mlp_hidden] * mlp_layers, node_out)
+
+    def forward(self, x):
+        return self.node_fn(x)
+
+
+class MAgNetGNN(LightningModule):
+    """models/magnet_gnn.py:139-475 (FACTORY key 'magnet_gnn')."""
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.save_hyperparameters()
+        self.lr = hparams.lr
+        self.weight_decay = hparams.weight_decay
+        self.factor = hparams.factor
+        self.step_size = hparams.step_size
+        self.loss = hparams.loss
+        self.time_slice = hparams.time_slice
+        self.num_message_passing_steps = hparams.num_message_passing_steps
+        self.latent_dim = hparams.latent_dim
+        self.mlp_layers = hparams.mlp_layers
+        self.mlp_hidden = hparams.mlp_hidden
+        self.n_chan = hparams.n_chan
+        self.radius = hparams.radius
+        self.codec_neighbors = hparams.codec_neighbors
+        self.teacher_forcing = hparams.teacher_forcing
+        self.noise = hparams.noise
+        self.interpolation = hparams.interpolation
+        self.dim = int(hparams["dim"]) if hasattr(hparams, "keys") and "dim" in hparams.keys() else int(getattr(hparams, "dim", 2))
+        d, ts, ld = self.dim, self.time_slice, self.latent_dim
+        self.criterion = {"l1": nn.L1Loss(), "l2": nn.MSELoss(), "smooth_l1": nn.SmoothL1Loss()}[self.loss]
+        self.mse_criterion = nn.MSELoss()
+        self.mae_criterion = nn.L1Loss()
+        enc = dict(node_in=ts + d + 1, node_out=ld, edge_in=ts + d, edge_out=ld, mlp_layers=self.mlp_layers,
+                   mlp_hidden=self.mlp_hidden)
+        proc = dict(node_in=ld, node_out=ld, edge_in=ld, edge_out=ld,
+                    num_message_passing_steps=self.num_message_passing_steps, mlp_num_layers=self.mlp_layers,
+                    mlp_hidden_dim=self.mlp_hidden)
+        self.encoder = Encoder(**enc)
+        self.processor = Processor(**proc)
+        self.proj_head = nn.Linear(ld + d + 2, self.n_chan)
+        self.projector = MLP(self.n_chan, [self.mlp_hidden] * self.mlp_layers, 1)
+        self._encoder = Encoder(**enc)
+        self._processor = Processor(**proc)
+        self._decoder = Decoder(node_in=ld, node_out=ts, mlp_layers=self.mlp_layers, mlp_hidden=self.mlp_hidden)
+        self._graph_cache = {}
+
+    # ---- graph -------------------------------------------------------------------------
+    def _edges(self, x_flat: torch.Tensor, key_tensor: torch.Tensor, B: int, N: int):
+        """radius graph (r = hparams.radius, loop=True) + plan, cached on the coordinate tensor."""
+        key = (key_tensor.data_ptr(), key_tensor._version, tuple(key_tensor.shape), B, N, float(self.radius))
+        hit = self._graph_cache.get(key)
+        if hit is not None and hit[0]() is key_tensor:
+            return hit[1]
+        seg = MG.uniform_segments(B, N, x_flat.device)
+        # PyG returns [neighbour; centre]; the reference swaps the rows (models/magnet_gnn.py:294-296)
+        edge_index = MG.radius_graph(x_flat, self.radius, loop=True, ptr=seg.gptr, swap_rows=True)
+        plan = MG.plan_for(edge_index, B * N)
+        if len(self._graph_cache) > 4:
+            self._graph_cache.clear()
+        self._graph_cache[key] = (weakref.ref(key_tensor), (edge_index, plan))
+        return edge_index, plan
+
+    def _build_graph(self, u, x, t, *, cache_key: Optional[torch.Tensor] = None, return_plan: bool = False):
+        """u [B,N,C], x [B,N,d], t [B,T] -> node_features [B*N, C+d+1], edge_index [2,E], edge_features [E, C+d]."""
+        B, N, _ = u.shape
+        u_ = u.reshape(B * N, -1)
+        x_ = x.reshape(B * N, -1)
+        edge_index, plan = self._edges(x_, x if cache_key is None else cache_key, B, N)
+        senders, receivers = edge_index[0], edge_index[1]
+        node_features = torch.cat([u_, x_, t[:, -1:].repeat(N, 1)], dim=-1)       # time is TILED (quirk F7)
+        edge_features = torch.cat([u_[senders] - u_[receivers], x_[senders] - x_[receivers]], dim=-1)
+        if return_plan:
+            return node_features, edge_index, edge_features, plan
+        return node_features, edge_index, edge_features
+
+    # ---- INR decoder ---------------------------------------------------------------------
+    def continuous_decoder(self, x_lr, lr_encoded, lr_coords, hr_coords, t):
+        """models/magnet_gnn.py:224-283: z [B*Nq, T, n_chan].  Fused kNN search + gather + proj_head +
+        interpolation of neighbours 0 and 1 (F9) in one kernel (csrc/inr_decode.cu)."""
+        B, T, _, L = x_lr.shape
+        return MF.inr_decode(x_lr.reshape(B, T, L), lr_encoded.reshape(B * L, -1), lr_coords.reshape(B * L, -1),
+                             hr_coords.reshape(B * hr_coords.shape[1], -1), t[:, :T], self.proj_head.weight,
+                             self.proj_head.bias, B, L, hr_coords.shape[1], self.codec_neighbors, self.interpolation)
+
+    # ---- model ---------------------------------------------------------------------------
+    def forward(self, x_lr, lr_coords, hr_coords, t, hr_last):
+        B, T, C, L = x_lr.shape
+        N = hr_coords.shape[1]
+        T_out = t.shape[1] - T
+        u = x_lr.permute(0, 3, 1, 2).reshape(B, L, -1)
+        nf, ei, ef, plan = self._build_graph(u, lr_coords, t[:, :T], return_plan=True)
+        nf, ef = self.encoder(nf, ei, ef)
+        lr_encoded, _ = self.processor(nf, ei, ef, plan=plan)
+
+        z = self.continuous_decoder(x_lr, lr_encoded, lr_coords, hr_coords, t)
+        hr_points = self.projector(z).reshape(B, N, -1)
+
+        all_coords = self._all_coords(lr_coords, hr_coords)
+        all_feats = torch.cat([u, hr_points], dim=1)
+        nf, ei, ef, plan = self._build_graph(all_feats, all_coords, t[:, :T], return_plan=True)
+        nf, ef = self._encoder(nf, ei, ef)
+        nf, _ = self._processor(nf, ei, ef, plan=plan)
+        ret = self._decoder(nf).reshape(B, L + N, -1)
+
+        last_values = torch.cat([x_lr[:, -1].permute(0, 2, 1), hr_last], dim=1)            # [B, L+N, 1]
+        delta_t = (t[:, T:T + T_out] - t[:, T - 1:T])[:, :, None, None]                    # [B, T_out, 1, 1]
+        outputs = last_values[:, None] + delta_t * ret.permute(0, 2, 1)[..., None]          # [B, T_out, L+N, 1]
+        hr_points = hr_points.reshape(B, N, T, -1).permute(0, 2, 1, 3)
+        return outputs[:, :, L:], outputs[:, :, :L], hr_points
+
+    def _all_coords(self, lr_coords, hr_coords):
+        """cat([lr, hr]) cached on the input tensors so the stage-3 graph is built once per mesh."""
+        key = (lr_coords.data_ptr(), lr_coords._version, hr_coords.data_ptr(), hr_coords._version)
+        hit = getattr(self, "_coords_cache", None)
+        if hit is not None and hit[0] == key and hit[1]() is lr_coords and hit[2]() is hr_coords:
+            return hit[3]
+        cat = torch.cat([lr_coords, hr_coords], dim=1)
+        self._coords_cache = (key, weakref.ref(lr_coords), weakref.ref(hr_coords), cat)
+        return cat
+
+    def configure_optimizers(self):
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=self.step_size, gamma=self.factor)
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler}}
+
+    # ---- rollout ---------------------------------------------------------------------------
+    def rollout(self, batch: dict, teacher_forcing: bool, noise: float = 0.0):
+        """Autoregressive unroll of training_step / validation_step (models/magnet_gnn.py:388-475).
+        Returns (u_values_hat [B, T_fut, Nq+L, 1], hr_values_hat [B, T_in.., Nq, 1], target, hr_target)."""
+        t = batch["t"].float()
+        u = batch["lr_frames"].float()
+        uv = batch["hr_points"].float()
+        coords = batch["coords_hr"].float()
+        lr_coords = batch["coords_lr"].float()
+        ts = self.time_slice
+        T_future = uv.shape[1] - ts
+
+        def noisy(v):
+            return v + noise * torch.randn_like(v) if noise else v
+
+        inp, hr_last = noisy(u[:, :ts]), noisy(uv[:, ts - 1])
+        preds, hr_preds = [], []
+        for i in range(T_future // ts):
+            out_hr, out_lr, hr_points = self.forward(inp, lr_coords, coords, t[:, i * ts:(i + 2) * ts], hr_last)
+            preds.append(torch.cat([out_hr, out_lr], dim=2))
+            hr_preds.append(hr_points)
+            if teacher_forcing:
+                inp, hr_last = u[:, (i + 1) * ts:(i + 2) * ts], uv[:, (i + 2) * ts - 1]
+            else:
+                inp, hr_last = out_lr.permute(0, 1, 3, 2), out_hr[:, -1]
+            inp, hr_last = noisy(inp), noisy(hr_last)
+        target = torch.cat([uv[:, ts:], u[:, ts:].permute(0, 1, 3, 2)], dim=2)
+        return torch.cat(preds, dim=1), torch.cat(hr_preds, dim=1), target, uv[:, :-ts]
+
+    def training_step(self, train_batch, batch_idx):
+        pred, hr_pred, target, hr_target = self.rollout(train_batch, self.teacher_forcing, self.noise)
+        loss = self.criterion(pred, target) + self.criterion(hr_pred, hr_target)
+        self.log("train_loss", loss, prog_bar=True)
+        self.log("train_mae_loss", self.mae_criterion(pred, target), prog_bar=True)
+        self.log("train_interp_loss", self.mae_criterion(hr_pred, hr_target), prog_bar=True)
+        return loss
+
+    def validation_step(self, val_batch, batch_idx):
+        pred, _, target, _ = self.rollout(val_batch, teacher_forcing=False)
+        self.log("val_loss", self.criterion(pred, target), prog_bar=True)
+        self.log("val_mae_loss", self.mae_criterion(pred, target), prog_bar=True)

@@ -1,0 +1,217 @@
+"""Drop-in MP-PDE modules: ``Swish``, ``GNN_Layer``, ``MPNN`` (1-D) and ``MPNN_2d``.
+
+Same class names, constructor arguments, ``forward`` signatures and ``state_dict`` keys as
+models/mpnn.py and models/mpnn_2d.py of the reference, so ``FACTORY['mpnn' | 'mpnn_2d']``,
+hydra configs and Lightning checkpoints keep working.  The message-passing
+layer runs the fused CUDA kernels of csrc/gnn_layer.cu; graphs come from csrc/graph.cu and are
+cached per mesh instead of being rebuilt every rollout step.
+"""
+import math
+import weakref
+from typing import List, Optional
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import functional as MF
+from . import graph as MG
+from ._compat import Data, LightningModule
+
+
+class Swish(nn.Module):
+    """x * sigmoid(beta x) — models/mpnn_2d.py:15-24.  Kept for state_dict/module-tree parity; the
+    fused kernels apply it in their epilogues (beta = 1 only)."""
+
+    def __init__(self, beta=1):
+        super().__init__()
+        self.beta = beta
+
+    def forward(self, x):
+        return x * torch.sigmoid(self.beta * x)
+
+
+class GNN_Layer(nn.Module):
+    """models/mpnn_2d.py:27-90 (pos_dim=2) / models/mpnn.py:27-90 (pos_dim=1).
+
+    forward(x, u, pos, variables, edge_index, batch) -> InstanceNorm(x + update(...)) with
+    x_i = x[edge_index[1]], x_j = x[edge_index[0]], mean aggregation at edge_index[1].
+    """
+
+    def __init__(self, in_features: int, out_features: int, hidden_features: int, time_window: int,
+                 n_variables: int, pos_dim: int = 2):
+        super().__init__()
+        self.in_features = in_features
+        self.out_features = out_features
+        self.hidden_features = hidden_features
+        self.time_window = time_window
+        self.n_variables = n_variables
+        self.pos_dim = pos_dim
+        self.message_net_1 = nn.Sequential(
+            nn.Linear(2 * in_features + time_window + pos_dim + n_variables, hidden_features), Swish())
+        self.message_net_2 = nn.Sequential(nn.Linear(hidden_features, hidden_features), Swish())
+        self.update_net_1 = nn.Sequential(nn.Linear(in_features + hidden_features + n_variables, hidden_features), Swish())
+        self.update_net_2 = nn.Sequential(nn.Linear(hidden_features, out_features), Swish())
+        # the reference's `norm = InstanceNorm(hidden_features)` has no parameters or buffers
+
+    def forward(self, x, u, pos, variables, edge_index, batch, *, plan=None, segments=None):
+        n = x.shape[0]
+        if plan is None:
+            plan = MG.plan_for(edge_index, n)
+        if segments is None:
+            segments = MG.segments_for(batch, n)
+        m1, m2, u1, u2 = self.message_net_1[0], self.message_net_2[0], self.update_net_1[0], self.update_net_2[0]
+        return MF.GNNLayerFn.apply(x, u, pos, variables, m1.weight, m1.bias, m2.weight, m2.bias, u1.weight, u1.bias,
+                                   u2.weight, u2.bias, plan, segments)
+
+
+# temporal-bundling decoder shapes: time_window -> (kernel1, stride1, kernel2)   models/mpnn_2d.py:138-162
+_CONV = {10: (16, 6, 10), 16: (16, 5, 8), 20: (15, 4, 10), 25: (16, 3, 14), 50: (12, 2, 10)}
+
+
+class _MPNNBase(LightningModule):
+    """Shared body of MPNN (models/mpnn.py:93-333) and MPNN_2d (models/mpnn_2d.py:93-333)."""
+    _POS_DIM = 2
+
+    def __init__(self, hparams):
+        super().__init__()
+        self.save_hyperparameters()
+        self.lr = hparams.lr
+        self.weight_decay = hparams.weight_decay
+        self.factor = hparams.factor
+        self.step_size = hparams.step_size
+        self.loss = hparams.loss
+        self.out_features = hparams.time_window
+        self.hidden_features = hparams.hidden_features
+        self.hidden_layer = hparams.hidden_layer
+        self.time_window = hparams.time_window
+        self.teacher_forcing = hparams.teacher_forcing
+        self.n = hparams.neighbors
+        d = self._POS_DIM
+        self.gnn_layers = nn.ModuleList([
+            GNN_Layer(self.hidden_features, self.hidden_features, self.hidden_features, self.time_window, 1, pos_dim=d)
+            for _ in range(self.hidden_layer)])
+        self.embedding_mlp = nn.Sequential(
+            nn.Linear(self.time_window + d + 1, self.hidden_features), Swish(),
+            nn.Linear(self.hidden_features, self.hidden_features), Swish())
+        if self.time_window in _CONV:
+            k1, s1, k2 = _CONV[self.time_window]
+            layers = [nn.Conv1d(1, 8, k1, stride=s1)]
+            if not (d == 1 and self.time_window == 10):   # models/mpnn.py:139-142 has no Swish for tw=10
+                layers.append(Swish())
+            layers.append(nn.Conv1d(8, 1, k2, stride=1))
+            self.output_mlp = nn.Sequential(*layers)
+        self.criterion = {"l1": nn.L1Loss(), "l2": nn.MSELoss(), "smooth_l1": nn.SmoothL1Loss()}[self.loss]
+        self.mse_criterion = nn.MSELoss()
+        self.mae_criterion = nn.L1Loss()
+        self._graph_cache = {}
+
+    # ---- graph -------------------------------------------------------------------------
+    def _radius(self, x0: torch.Tensor, nx: int) -> float:
+        """models/mpnn_2d.py:240-243 / models/mpnn.py:243-244, evaluated in fp32 like the reference."""
+        if self._POS_DIM == 2:
+            pts = x0[[0, 1, int(nx ** 0.5)]].float().cpu()
+            dx, dy = pts[1] - pts[0], pts[2] - pts[0]
+            return float(self.n * torch.norm(dx - dy, p=2) + 0.0001)
+        pts = x0[[0, 1]].float().cpu()
+        return float(self.n * (pts[1] - pts[0]) + 0.0001)
+
+    def _mesh_graph(self, x: torch.Tensor, B: int, nx: int):
+        """edge_index / batch / positions for B copies of sample 0's mesh (models/mpnn_2d.py:235), cached."""
+        key = (x.data_ptr(), x._version, tuple(x.shape), B, self.n)
+        hit = self._graph_cache.get(key)
+        if hit is not None and hit[0]() is x:      # same tensor object, unmodified: same mesh
+            return hit[1]
+        x0 = x[0].reshape(nx, -1).float()
+        x_pos = x0.repeat(B, 1).contiguous()
+        radius = self._radius(x[0], nx)
+        seg = MG.uniform_segments(B, nx, x.device)
+        edge_index = MG.radius_graph(x_pos, radius, loop=False, ptr=seg.gptr)
+        batch = torch.arange(B, device=x.device).repeat_interleave(nx)
+        plan = MG.plan_for(edge_index, B * nx)
+        self._graph_cache.clear()
+        self._graph_cache[key] = (weakref.ref(x), (edge_index, batch, x_pos, plan, seg))
+        return self._graph_cache[key][1]
+
+    def _build_graph(self, data: torch.Tensor, t: torch.Tensor, x: torch.Tensor, steps: List[int]):
+        """data [B, tw, N], t [B, T], x [B, N(, 2)], steps [B] -> Data(x=u, edge_index, pos=[t, x(,y)], batch)."""
+        B, _, nx = data.shape
+        edge_index, batch, x_pos, plan, seg = self._mesh_graph(x, B, nx)
+        u = data.permute(0, 2, 1).reshape(B * nx, -1)
+        steps_t = torch.as_tensor(steps, device=t.device, dtype=torch.long)
+        t_pos = t[torch.arange(B, device=t.device), steps_t].to(data.dtype).repeat_interleave(nx)
+        graph = Data(x=u, edge_index=edge_index)
+        graph.pos = torch.cat((t_pos[:, None], x_pos), 1)
+        graph.batch = batch
+        graph.plan, graph.segments = plan, seg
+        return graph
+
+    # ---- model -------------------------------------------------------------------------
+    def forward(self, data, L, tmax, dt):
+        u, pos, edge_index, batch = data.x, data.pos, data.edge_index, data.batch
+        plan, seg = getattr(data, "plan", None), getattr(data, "segments", None)
+        pos_x = pos[:, 1][:, None] / L          # [N,2] in 2-D: both columns are x (quirk F6, models/mpnn_2d.py:178-180)
+        variables = pos[:, 0][:, None] / tmax
+        e0, e2 = self.embedding_mlp[0], self.embedding_mlp[2]
+        h = MF.linear_act(torch.cat((u, pos_x, variables), -1), e0.weight, e0.bias, "swish")
+        h = MF.linear_act(h, e2.weight, e2.bias, "swish")
+        for layer in self.gnn_layers:
+            h = layer(h, u, pos_x, variables, edge_index, batch, plan=plan, segments=seg)
+        dts = torch.cumsum(torch.ones(1, self.time_window, device=u.device, dtype=u.dtype) * dt, dim=1)
+        diff = self.output_mlp(h[:, None]).squeeze(1)
+        return u[:, -1:].expand(-1, self.time_window) + dts * diff
+
+    def configure_optimizers(self):
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=self.step_size, gamma=self.factor)
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler}}
+
+    # ---- rollout -----------------------------------------------------------------------
+    def _step_index(self, i: int) -> int:
+        # models/mpnn_2d.py:265,281 use the last time of the window; models/mpnn.py uses 0
+        return (i + 1) * self.time_window - 1 if self._POS_DIM == 2 else 0
+
+    def rollout(self, batch: dict, teacher_forcing: bool = False):
+        """Autoregressive unroll shared by training_step / validation_step
+        (models/mpnn_2d.py:254-297, 299-333).  Returns (u_hat [B, T_out, N], target)."""
+        u = batch["u"].float().permute(0, 2, 1)
+        x = batch["x"].float()
+        if self._POS_DIM == 1:
+            x = x.squeeze(-1)
+        t = batch["t"].float()
+        B, _, N = u.shape
+        dt = t[0][1] - t[0][0]
+        tw = self.time_window
+        graph = self._build_graph(u[:, :tw], t, x, [self._step_index(0)] * B)
+        target = u[:, tw:]
+        outs = []
+        n_iter = target.shape[1] // tw
+        for i in range(n_iter):
+            y = self.forward(graph, x[0, -1], t[0, -1], dt).reshape(B, N, -1).permute(0, 2, 1)
+            outs.append(y)
+            if i + 1 < n_iter:      # the reference also rebuilds after the last window; that graph is never used
+                nxt = u[:, (i + 1) * tw:(i + 2) * tw] if teacher_forcing else y
+                graph = self._build_graph(nxt, t, x, [self._step_index(i + 1)] * B)
+        return torch.cat(outs, dim=1), target
+
+    def training_step(self, train_batch, batch_idx):
+        u_hat, target = self.rollout(train_batch, teacher_forcing=self.teacher_forcing)
+        loss = self.criterion(u_hat, target)
+        self.log("train_loss", loss, prog_bar=True)
+        self.log("train_mae_loss", self.mae_criterion(u_hat, target), prog_bar=True)
+        return loss
+
+    def validation_step(self, val_batch, batch_idx):
+        u_hat, target = self.rollout(val_batch, teacher_forcing=False)
+        self.log("val_loss", self.criterion(u_hat, target), prog_bar=True)
+        self.log("val_mae_loss", self.mae_criterion(u_hat, target), prog_bar=True)
+
+
+class MPNN_2d(_MPNNBase):
+    """Drop-in for models/mpnn_2d.py:93 (FACTORY key 'mpnn_2d')."""
+    _POS_DIM = 2
+
+
+class MPNN(_MPNNBase):
+    """Drop-in for models/mpnn.py:93 (FACTORY key 'mpnn')."""
+    _POS_DIM = 1

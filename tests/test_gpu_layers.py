@@ -1,0 +1,179 @@
+"""GPU parity: dense stages, GNN_Layer forward/backward and the MPNN models vs the oracle.
+fp32 contract: max |a-b| / max |b| <= 1e-5 (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import graph as OG
+from oracle import restatement as R
+from oracle.reference_loader import HParams, mpnn_2d_hparams, mpnn_hparams
+from magnet_b200 import functional as MF, graph as MG, synthetic as S
+from magnet_b200.mpnn import GNN_Layer, MPNN, MPNN_2d
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+
+
+def _layer_shapes(tw, dp):
+    return {"message_net_1.0.weight": (128, 256 + tw + dp + 1), "message_net_1.0.bias": (128,),
+            "message_net_2.0.weight": (128, 128), "message_net_2.0.bias": (128,),
+            "update_net_1.0.weight": (128, 257), "update_net_1.0.bias": (128,),
+            "update_net_2.0.weight": (128, 128), "update_net_2.0.bias": (128,)}
+
+
+@pytest.mark.parametrize("rows,fin,fout,act", [(1000, 13, 128, "swish"), (777, 128, 128, "relu"), (300, 257, 128, "none"),
+                                               (129, 128, 10, "none"), (5, 132, 128, "relu"), (2048, 128, 1, "none")])
+def test_linear_act_fwd_bwd(rows, fin, fout, act):
+    g = S._gen(rows)
+    x = torch.randn(rows, fin, generator=g).to(DEV).requires_grad_()
+    W = (torch.randn(fout, fin, generator=g) / fin ** 0.5).to(DEV).requires_grad_()
+    b = torch.randn(fout, generator=g).to(DEV).requires_grad_()
+    res = torch.randn(rows, fout, generator=g).to(DEV).requires_grad_()
+    y = MF.linear_act(x, W, b, act, res)
+    gy = torch.randn(rows, fout, generator=g).to(DEV)
+    y.backward(gy)
+    xd, Wd, bd, rd = (t.detach().double().cpu().requires_grad_() for t in (x, W, b, res))
+    z = torch.nn.functional.linear(xd, Wd, bd)
+    z = {"swish": lambda v: v * torch.sigmoid(v), "relu": torch.relu, "none": lambda v: v}[act](z) + rd
+    z.backward(gy.double().cpu())
+    assert rel_err(y, z) < TOL
+    for got, want in ((x.grad, xd.grad), (W.grad, Wd.grad), (b.grad, bd.grad), (res.grad, rd.grad)):
+        assert rel_err(got, want) < TOL
+
+
+def test_layernorm_fwd_bwd():
+    g = S._gen(9)
+    x = (3 * torch.randn(1001, 128, generator=g) + 1).to(DEV).requires_grad_()
+    gm = (1 + 0.1 * torch.randn(128, generator=g)).to(DEV).requires_grad_()
+    bt = (0.1 * torch.randn(128, generator=g)).to(DEV).requires_grad_()
+    y = MF.layer_norm(x, gm, bt)
+    gy = torch.randn(1001, 128, generator=g).to(DEV)
+    y.backward(gy)
+    xd, gd, bd = (t.detach().double().cpu().requires_grad_() for t in (x, gm, bt))
+    z = torch.nn.functional.layer_norm(xd, (128,), gd, bd, 1e-5)
+    z.backward(gy.double().cpu())
+    assert rel_err(y, z) < TOL
+    for got, want in ((x.grad, xd.grad), (gm.grad, gd.grad), (bt.grad, bd.grad)):
+        assert rel_err(got, want) < TOL
+
+
+def test_instance_norm_ragged():
+    g = S._gen(10)
+    sizes = [300, 1, 0, 1000, 129]
+    x = torch.randn(sum(sizes), 128, generator=g)
+    batch = torch.cat([torch.full((n,), b) for b, n in enumerate(sizes)]).long()
+    gptr = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int64, device=DEV)
+    seg = MG.GraphSegments(gptr, len(sizes), max(sizes))
+    y = MF.instance_norm(x.to(DEV), seg)
+    assert rel_err(y, R.instance_norm(x.double(), batch)) < TOL
+
+
+def _run_layer(c, tw, dp, seed):
+    sd = S.seeded_state_dict(_layer_shapes(tw, dp), seed)
+    layer = GNN_Layer(128, 128, 128, tw, 1, pos_dim=dp).to(DEV)
+    layer.load_state_dict(sd, strict=True)
+    x = c["x"].to(DEV).requires_grad_()
+    u = c["u"].to(DEV).requires_grad_()
+    pos = c["pos"].to(DEV).requires_grad_()
+    y = layer(x, u, pos, c["variables"].to(DEV), c["edge_index"].to(DEV), c["batch"].to(DEV))
+    return layer, sd, x, u, pos, y
+
+
+def test_gnn_layer_golden(golden):
+    for name, c in golden("gnn_layer.pt").items():
+        tw, dp = c["time_window"], c["pos"].shape[1]
+        layer, sd, x, u, pos, y = _run_layer(c, tw, dp, c["seed"])
+        assert rel_err(y, c["y"]) < TOL, name
+        y.backward(c["grad_y"].to(DEV))
+        assert rel_err(x.grad, c["grad_x"]) < TOL, name
+        assert rel_err(u.grad, c["grad_u"]) < TOL, name
+        assert rel_err(pos.grad, c["grad_pos"]) < TOL, name
+        for k, p in layer.named_parameters():
+            assert rel_err(p.grad, c["grads"][k]) < TOL, (name, k)
+
+
+@pytest.mark.parametrize("B,N,r,trunc", [(4, 4096, 0.03, False), (2, 2048, 0.12, True)])
+def test_gnn_layer_vs_oracle_fp64(B, N, r, trunc):
+    """config-2 shaped layer (64x64 irregular-uniform mesh); fp64 oracle as the arbiter."""
+    g = S._gen(40 + B)
+    pos = torch.rand(B * N, 2, generator=g)
+    batch = torch.arange(B).repeat_interleave(N)
+    ei = OG.radius_graph(pos, r, batch, loop=False, threads=8)
+    if trunc:
+        assert int(torch.bincount(ei[1]).max()) >= 32
+    c = dict(x=torch.randn(B * N, 128, generator=g), u=torch.randn(B * N, 10, generator=g), pos=pos,
+             variables=torch.rand(B * N, 1, generator=g), edge_index=ei, batch=batch)
+    layer, sd, x, u, posd, y = _run_layer(c, 10, 2, 3)
+    sd64 = R.cast_sd(sd, torch.float64)
+    x64, u64, p64 = (t.double().requires_grad_() for t in (c["x"], c["u"], c["pos"]))
+    y64 = R.gnn_layer(sd64, "", x64, u64, p64, c["variables"].double(), ei, batch)
+    assert rel_err(y, y64) < TOL
+    gy = torch.randn(y64.shape, generator=g)
+    y.backward(gy.to(DEV))
+    y64.backward(gy.double())
+    assert rel_err(x.grad, x64.grad) < TOL
+    assert rel_err(u.grad, u64.grad) < TOL
+    assert rel_err(posd.grad, p64.grad) < TOL
+    # determinism: no atomics anywhere -> bit-identical reruns
+    layer2, _, x2, u2, pos2, y2 = _run_layer(c, 10, 2, 3)
+    assert torch.equal(y, y2)
+    y2.backward(gy.to(DEV))
+    assert torch.equal(x.grad, x2.grad)
+    for (k, p), (_, q) in zip(layer.named_parameters(), layer2.named_parameters()):
+        assert torch.equal(p.grad, q.grad), k
+
+
+def test_gnn_layer_isolated_nodes_and_arbitrary_edge_index():
+    """edge_index the layer did not build itself: unsorted, duplicated, with isolated nodes."""
+    g = S._gen(50)
+    N, E = 500, 3000
+    ei = torch.randint(0, N - 50, (2, E), generator=g)       # the last 50 nodes receive nothing
+    ei[1, :400] = 3                                          # one destination with 400 incoming edges
+    c = dict(x=torch.randn(N, 128, generator=g), u=torch.randn(N, 10, generator=g), pos=torch.rand(N, 2, generator=g),
+             variables=torch.rand(N, 1, generator=g), edge_index=ei, batch=torch.zeros(N, dtype=torch.long))
+    layer, sd, x, u, pos, y = _run_layer(c, 10, 2, 4)
+    y64 = R.gnn_layer(R.cast_sd(sd, torch.float64), "", c["x"].double(), c["u"].double(), c["pos"].double(),
+                      c["variables"].double(), ei, c["batch"])
+    assert rel_err(y, y64) < TOL
+
+
+def test_mpnn_2d_golden(golden):
+    c = golden("mpnn.pt")["mpnn_2d"]
+    m = MPNN_2d(HParams(c["hparams"])).to(DEV)
+    sd = S.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, c["seed"])
+    m.load_state_dict(sd, strict=True)
+    b = {k: v.to(DEV) for k, v in c["batch"].items()}
+    u = b["u"].permute(0, 2, 1)
+    graph = m._build_graph(u[:, :10], b["t"], b["x"], [9, 9])
+    assert torch.equal(graph.edge_index.cpu(), c["edge_index"])
+    assert torch.equal(graph.pos.cpu(), c["pos"])
+    with torch.no_grad():
+        y = m.forward(graph, b["x"][0, -1], b["t"][0, -1], b["t"][0][1] - b["t"][0][0])
+    assert rel_err(y, c["y"]) < TOL
+    m.eval()
+    with torch.no_grad():
+        m.validation_step(b, 0)
+    assert abs(float(m.logged["val_loss"]) - float(c["val_loss"])) <= 2e-5 * abs(float(c["val_loss"]))
+    m.train()
+    loss = m.training_step(b, 0)
+    loss.backward()
+    assert abs(float(loss) - float(c["train_loss"])) <= 2e-5 * abs(float(c["train_loss"]))
+    assert rel_err(m.embedding_mlp[0].weight.grad, c["grad_embedding0"]) < 5e-5
+    for k, p in m.named_parameters():
+        assert abs(float(p.grad.norm()) - float(c["grad_norms"][k])) <= 1e-4 * float(c["grad_norms"][k]) + 1e-9, k
+
+
+def test_mpnn_1d_golden(golden):
+    c = golden("mpnn.pt")["mpnn_1d"]
+    m = MPNN(HParams(c["hparams"])).to(DEV)
+    sd = S.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, c["seed"])
+    m.load_state_dict(sd, strict=True)
+    b = {k: v.to(DEV) for k, v in c["batch"].items()}
+    u = b["u"].permute(0, 2, 1)
+    x = b["x"].squeeze(-1)
+    graph = m._build_graph(u[:, :25], b["t"], x, [0] * 4)
+    assert torch.equal(graph.edge_index.cpu(), c["edge_index"])
+    with torch.no_grad():
+        y = m.forward(graph, x[0, -1], b["t"][0, -1], b["t"][0][1] - b["t"][0][0])
+    assert rel_err(y, c["y"]) < TOL
