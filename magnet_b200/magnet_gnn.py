@@ -152,7 +152,10 @@ class MAgNetGNN(LightningModule):
         self.teacher_forcing = hparams.teacher_forcing
         self.noise = hparams.noise
         self.interpolation = hparams.interpolation
-        self.dim = int(hparams["dim"]) if hasattr(hparams, "keys") and "dim" in hparams.keys() else int(getattr(hparams, "dim", 2))
+        try:
+            self.dim = int(hparams.dim)          # extension: 1-D meshes; absent in the reference config
+        except (AttributeError, KeyError):
+            self.dim = 2
         d, ts, ld = self.dim, self.time_slice, self.latent_dim
         self.criterion = {"l1": nn.L1Loss(), "l2": nn.MSELoss(), "smooth_l1": nn.SmoothL1Loss()}[self.loss]
         self.mse_criterion = nn.MSELoss()
