@@ -621,7 +621,10 @@ size_t gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp,
     b += align_up((size_t)2 * H * sh.Kc() * 4) + align_up(2 * H * 4);  // dwcat, dbcat
     size_t w = wgrad_workspace_bytes((int)n_nodes, 2 * H, sh.Kc());
     size_t w2 = wgrad_workspace_bytes((int)n_nodes, H, sh.K3());
-    b += (w > w2 ? w : w2) + inorm_workspace_bytes(n_graphs, max_nodes) + 8192;
+    size_t w3 = wgrad_workspace_bytes((int)n_nodes, H, H);
+    if (w2 > w) w = w2;
+    if (w3 > w) w = w3;
+    b += w + inorm_workspace_bytes(n_graphs, max_nodes) + 8192;
     return b;
 }
 
