@@ -88,6 +88,10 @@ int mgb_csr_plan(const int64_t* agg, const int64_t* other, int64_t n_edges, int6
  *   packed: mgb_gnn_layer_packed_floats() floats, filled by mgb_gnn_layer_pack (re-run when the
  *   parameters change).
  *   Saved for backward: pq [N,256], agg [N,128], y1_pre [N,128], y2_pre [N,128], rstd [G,128].
+ *   precision selects the arithmetic of the per-edge contraction (the 128x128 message_net_2 product and
+ *   its gradients):  0 = fp32 FFMA;  1 = tcgen05 tensor cores, bf16 hi/lo split of both operands with
+ *   fp32 accumulation in TMEM (error ~2^-17, meets the 1e-5 fp32 contract);  2 = tcgen05 plain bf16
+ *   operands + tanh.approx Swish (1e-2 contract).
  * ------------------------------------------------------------------------------------------- */
 size_t mgb_gnn_layer_packed_floats(int tw, int dp, int nv);
 int mgb_gnn_layer_pack(const float* W1, const float* b1, const float* W2, const float* W3, const float* W4, int tw,
@@ -97,8 +101,8 @@ int mgb_gnn_layer_fwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
                       const float* x, const float* u, const float* pos, const float* var, const int32_t* rowptr,
                       const int32_t* dst, const int32_t* src, const int64_t* gptr, const float* packed,
                       const float* b2, const float* b3, const float* b4, float* y, float* pq, float* agg,
-                      float* y1_pre, float* y2_pre, float* rstd, void* workspace, size_t workspace_bytes,
-                      void* stream);
+                      float* y1_pre, float* y2_pre, float* rstd, int precision, void* workspace,
+                      size_t workspace_bytes, void* stream);
 size_t mgb_gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs,
                                    int max_nodes_per_graph);
 /* du / dpos / dvar may be NULL.  accumulate_params != 0 adds into the d* parameter buffers. */
@@ -109,7 +113,7 @@ int mgb_gnn_layer_bwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
                       const int32_t* rowptr_t, const int32_t* pos_t, const int64_t* gptr, const float* packed,
                       const float* W2, const float* b2, const float* W3, const float* W4, float* dx, float* du,
                       float* dpos, float* dvar, float* dW1, float* db1, float* dW2, float* db2, float* dW3,
-                      float* db3, float* dW4, float* db4, int accumulate_params, void* workspace,
+                      float* db3, float* dW4, float* db4, int accumulate_params, int precision, void* workspace,
                       size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -137,6 +141,12 @@ int mgb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
 size_t mgb_instance_norm_workspace(int n_graphs, int max_nodes_per_graph);
 int mgb_instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes_per_graph, float* y,
                           float* rstd, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hook: one 128x128x128 bf16 tcgen05.mma tile, d[m][n] = sum_k A(m,k) B(n,k), through K-major
+ * (x_mn_major = 0: a[m][k] / b[n][k]) or MN-major (x_mn_major = 1: a[k][m] / b[k][n]) shared-memory
+ * descriptors over the same 128-byte-swizzled tile image.  lbo_mn / sbo_mn = 0 use the library defaults. */
+int mgb_umma_selftest(const float* a, const float* b, int a_mn_major, int b_mn_major, int lbo_mn, int sbo_mn, float* d,
+                      void* stream);
 
 /* Test hooks for the integer primitives (stable radix sort, exclusive scan). */
 size_t mgb_sort_workspace(int64_t n);

@@ -69,9 +69,9 @@ int mgb_gnn_layer_fwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
                       const float* x, const float* u, const float* pos, const float* var, const int32_t* rowptr,
                       const int32_t* dst, const int32_t* src, const int64_t* gptr, const float* packed,
                       const float* b2, const float* b3, const float* b4, float* y, float* pq, float* agg,
-                      float* y1_pre, float* y2_pre, float* rstd, void* workspace, size_t workspace_bytes,
+                      float* y1_pre, float* y2_pre, float* rstd, int precision, void* workspace, size_t workspace_bytes,
                       void* stream) {
-    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph};
+    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph, precision};
     GnnFwdIO io{x, u, pos, var, rowptr, dst, src, gptr, packed, b2, b3, b4, y, pq, agg, y1_pre, y2_pre, rstd};
     return gnn_layer_fwd(sh, io, workspace, workspace_bytes, STREAM(stream));
 }
@@ -88,9 +88,9 @@ int mgb_gnn_layer_bwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
                       const int32_t* rowptr_t, const int32_t* pos_t, const int64_t* gptr, const float* packed,
                       const float* W2, const float* b2, const float* W3, const float* W4, float* dx, float* du,
                       float* dpos, float* dvar, float* dW1, float* db1, float* dW2, float* db2, float* dW3,
-                      float* db3, float* dW4, float* db4, int accumulate_params, void* workspace,
+                      float* db3, float* dW4, float* db4, int accumulate_params, int precision, void* workspace,
                       size_t workspace_bytes, void* stream) {
-    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph};
+    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph, precision};
     GnnBwdIO io{dy, x, u, pos, var, y, pq, agg, y1_pre, y2_pre, rstd, rowptr, dst, src, rowptr_t, pos_t, gptr, packed,
                 W2, b2, W3, W4, dx, du, dpos, dvar, dW1, db1, dW2, db2, dW3, db3, dW4, db4, accumulate_params};
     return gnn_layer_bwd(sh, io, workspace, workspace_bytes, STREAM(stream));
@@ -162,6 +162,11 @@ size_t mgb_instance_norm_workspace(int n_graphs, int max_nodes_per_graph) {
 int mgb_instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes_per_graph, float* y,
                           float* rstd, void* workspace, size_t workspace_bytes, void* stream) {
     return instance_norm_fwd(x, gptr, n_graphs, max_nodes_per_graph, y, rstd, workspace, workspace_bytes, STREAM(stream));
+}
+
+int mgb_umma_selftest(const float* a, const float* b, int a_mn_major, int b_mn_major, int lbo_mn, int sbo_mn, float* d,
+                      void* stream) {
+    return umma_selftest(a, b, a_mn_major, b_mn_major, lbo_mn, sbo_mn, d, STREAM(stream));
 }
 
 size_t mgb_sort_workspace(int64_t n) { return sort_workspace_bytes(n); }

@@ -477,6 +477,7 @@ int instance_norm_bwd(const float* dy, const float* y, const float* rstd, const 
 // packed weight block (floats): wcat_t [Kc][2H] | wcat [2H][Kc] | bcat [2H] | w2t [H][H] | w3t [K3][H] | w4t [H][H]
 struct GnnPacked {
     float *wcat_t, *wcat, *bcat, *w2t, *w3t, *w4t;
+    float* w2img;   // two swizzled bf16 [128][128] images of W2 (hi | lo) for the tcgen05 edge kernels
 };
 static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) {
     size_t off = 0;
@@ -487,18 +488,19 @@ static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) 
     float* d = take((size_t)H * H);
     float* e = take((size_t)sh.K3() * H);
     float* f = take((size_t)H * H);
-    if (p) { p->wcat_t = a; p->wcat = b; p->bcat = c; p->w2t = d; p->w3t = e; p->w4t = f; }
+    float* g = take((size_t)H * H);      // 2 images x 128 x 128 bf16 = H*H floats
+    if (p) { p->wcat_t = a; p->wcat = b; p->bcat = c; p->w2t = d; p->w3t = e; p->w4t = f; p->w2img = g; }
     return off;
 }
 
 size_t gnn_layer_packed_floats(int tw, int dp, int nv) {
-    GnnLayerShape sh{0, 0, tw, dp, nv, 0, 0};
+    GnnLayerShape sh{0, 0, tw, dp, nv, 0, 0, 0};
     return packed_layout(sh, nullptr, nullptr);
 }
 
 int gnn_layer_pack(const float* W1, const float* b1, const float* W2, const float* W3, const float* W4, int tw, int dp,
                    int nv, float* packed, cudaStream_t s) {
-    GnnLayerShape sh{0, 0, tw, dp, nv, 0, 0};
+    GnnLayerShape sh{0, 0, tw, dp, nv, 0, 0, 0};
     GnnPacked p;
     packed_layout(sh, packed, &p);
     pack_w1_kernel<<<ceil_div(sh.Kc() * 2 * H, 256), 256, 0, s>>>(W1, b1, tw, dp, nv, p.wcat_t, p.wcat, p.bcat);
@@ -506,6 +508,7 @@ int gnn_layer_pack(const float* W1, const float* b1, const float* W2, const floa
     MGB_TRY(launch_transpose(W2, H, H, H, p.w2t, H, s));
     MGB_TRY(launch_transpose(W3, H, sh.K3(), sh.K3(), p.w3t, H, s));
     MGB_TRY(launch_transpose(W4, H, H, H, p.w4t, H, s));
+    MGB_TRY(pack_w2_image(W2, p.w2img, s));
     return MGB_OK;
 }
 
@@ -517,7 +520,7 @@ static int edge_grid(int64_t n_tiles, int ctas_per_sm) {
 size_t gnn_layer_fwd_workspace(int64_t n_nodes, int64_t n_edges, int n_graphs, int max_nodes) {
     int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TE);
     return 2 * align_up((size_t)tiles * H * sizeof(float)) + align_up((size_t)n_nodes * H * sizeof(float)) * 2 +
-           inorm_workspace_bytes(n_graphs, max_nodes) + 4096;
+           align_up(edge_fwd_tc_workspace(n_edges)) + inorm_workspace_bytes(n_graphs, max_nodes) + 4096;
 }
 
 int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, size_t ws_bytes, cudaStream_t s) {
@@ -531,7 +534,10 @@ int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, siz
     float* part_tail = ws.take<float>((size_t)tiles * H);
     float* y1 = ws.take<float>((size_t)N * H);
     float* out = ws.take<float>((size_t)N * H);
+    const size_t tc_bytes = edge_fwd_tc_workspace(sh.n_edges);
+    char* tc_ws = ws.take<char>(tc_bytes);
     MGB_WS_CHECK(ws);
+    MGB_REQUIRE(sh.precision >= 0 && sh.precision <= 2, "gnn_layer: unknown precision %d", sh.precision);
     if (N == 0) return MGB_OK;
     // 1. P | Q = [x,u,pos,var] Wcat^T + [b1 | 0]
     {
@@ -548,7 +554,10 @@ int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, siz
     }
     // 2. fused edge kernel + boundary fix-up
     MGB_CUDA(cudaMemsetAsync(io.agg, 0, (size_t)N * H * sizeof(float), s));
-    if (sh.n_edges > 0) {
+    if (sh.n_edges > 0 && sh.precision != 0) {
+        MGB_TRY(launch_edge_fwd_tc(sh.precision, io.pq, io.rowptr, io.dstv, io.srcv, sh.n_edges, p.w2img, io.b2, io.agg,
+                                   tc_ws, tc_bytes, s));
+    } else if (sh.n_edges > 0) {
         EdgeFwdArgs a{io.pq, io.rowptr, io.dstv, io.srcv, sh.n_edges, p.w2t, io.b2, io.agg, part_head, part_tail};
         MGB_CUDA(cudaFuncSetAttribute(gnn_edge_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_FWD_SMEM));
         {
@@ -607,7 +616,7 @@ gnn_combine_grads_kernel(const float* __restrict__ d0, const float* __restrict__
 static int ld4(int k) { return (k + 3) / 4 * 4; }
 
 size_t gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs, int max_nodes) {
-    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes};
+    GnnLayerShape sh{n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes, 0};
     const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TE);
     const int grid = edge_grid(tiles, 1);
     size_t b = 0;

@@ -27,6 +27,7 @@ struct GnnLayerShape {
     int64_t n_nodes, n_edges;
     int tw, dp, nv;
     int n_graphs, max_nodes_per_graph;
+    int precision;   // 0 fp32 FFMA, 1 tcgen05 bf16 hi/lo split (fp32 contract), 2 tcgen05 bf16
     int Kc() const { return 128 + tw + dp + nv; }
     int K1() const { return 256 + tw + dp + nv; }
     int K3() const { return 256 + nv; }
@@ -63,5 +64,14 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws, size_t 
 size_t inorm_workspace_bytes(int n_graphs, int max_nodes);
 int instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes, float* y, float* rstd_out, void* ws,
                       size_t ws_bytes, cudaStream_t s);
+
+// gnn_edge_tc.cu (tcgen05 edge kernels)
+int pack_w2_image(const float* W2, void* img, cudaStream_t s);
+size_t edge_fwd_tc_workspace(int64_t n_edges);
+int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv,
+                       int64_t n_edges, const void* w2img, const float* b2, float* agg, void* ws, size_t ws_bytes,
+                       cudaStream_t s);
+// umma_selftest.cu
+int umma_selftest(const float* a, const float* b, int a_mn, int b_mn, int lbo_mn, int sbo_mn, float* d, cudaStream_t s);
 
 }  // namespace mgb

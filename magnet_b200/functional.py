@@ -11,6 +11,26 @@ from .graph import AggregationPlan, GraphSegments
 
 ACT = {"none": 0, "relu": 1, "swish": 2}
 
+# Arithmetic of the per-edge contractions (include/magnet_b200.h, `precision`):
+#   "fp32"      0  fp32 FFMA
+#   "fp32_tc"   1  tcgen05 tensor cores, bf16 hi/lo split + fp32 accumulation (1e-5 contract)
+#   "bf16"      2  tcgen05 tensor cores, plain bf16 operands (1e-2 contract)
+PRECISIONS = {"fp32": 0, "fp32_tc": 1, "bf16": 2}
+_precision = "fp32_tc"
+
+
+def set_precision(name: str) -> str:
+    """Select the edge-kernel arithmetic; returns the previous setting."""
+    global _precision
+    if name not in PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+    old, _precision = _precision, name
+    return old
+
+
+def get_precision() -> str:
+    return _precision
+
 
 def _empty(shape, ref):
     return torch.empty(shape, dtype=torch.float32, device=ref.device)
@@ -44,6 +64,7 @@ class GNNLayerFn(torch.autograd.Function):
         if plan.n_nodes != N:
             raise RuntimeError("aggregation plan was built for a different node count")
         packed = pack_gnn_layer(W1, b1, W2, W3, W4, tw, dp, nv)
+        prec = PRECISIONS[_precision]
         y = _empty((N, H), x)
         pq = _empty((N, 2 * H), x)
         agg = _empty((N, H), x)
@@ -55,11 +76,12 @@ class GNNLayerFn(torch.autograd.Function):
                                        _lib.ptr(pos), _lib.ptr(var), _lib.ptr(plan.rowptr), _lib.ptr(plan.dst),
                                        _lib.ptr(plan.src), _lib.ptr(seg.gptr), _lib.ptr(packed), _lib.ptr(b2),
                                        _lib.ptr(b3), _lib.ptr(b4), _lib.ptr(y), _lib.ptr(pq), _lib.ptr(agg),
-                                       _lib.ptr(y1_pre), _lib.ptr(y2_pre), _lib.ptr(rstd), _lib.ptr(ws), ws.numel(),
+                                       _lib.ptr(y1_pre), _lib.ptr(y2_pre), _lib.ptr(rstd), prec, _lib.ptr(ws), ws.numel(),
                                        _lib.stream()), "gnn_layer_fwd")
         ctx.save_for_backward(x, u, pos, var, y, pq, agg, y1_pre, y2_pre, rstd, packed, W1, W2, b2, W3, W4)
         ctx.plan, ctx.seg = plan, seg
         ctx.dims = (N, tw, dp, nv)
+        ctx.prec = prec
         return y
 
     @staticmethod
@@ -88,7 +110,7 @@ class GNNLayerFn(torch.autograd.Function):
                 _lib.ptr(plan.rowptr_t), _lib.ptr(plan.pos_t), _lib.ptr(seg.gptr), _lib.ptr(packed), _lib.ptr(W2),
                 _lib.ptr(b2), _lib.ptr(W3), _lib.ptr(W4), _lib.ptr(dx), _lib.ptr(du), _lib.ptr(dpos), _lib.ptr(dvar),
                 _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2), _lib.ptr(dW3), _lib.ptr(db3),
-                _lib.ptr(dW4), _lib.ptr(db4), 0, _lib.ptr(ws), ws.numel(), _lib.stream()), "gnn_layer_bwd")
+                _lib.ptr(dW4), _lib.ptr(db4), 0, ctx.prec, _lib.ptr(ws), ws.numel(), _lib.stream()), "gnn_layer_bwd")
         return dx, du, dpos, dvar, dW1, db1, dW2, db2, dW3, db3, dW4, db4, None, None
 
 

@@ -80,7 +80,19 @@ def _run_layer(c, tw, dp, seed):
     return layer, sd, x, u, pos, y
 
 
-def test_gnn_layer_golden(golden):
+@pytest.fixture(params=["fp32", "fp32_tc", "bf16"])
+def precision(request):
+    old = MF.set_precision(request.param)
+    yield request.param
+    MF.set_precision(old)
+
+
+def _tol(precision):
+    return 1e-2 if precision == "bf16" else TOL
+
+
+def test_gnn_layer_golden(golden, precision):
+    TOL = _tol(precision)
     for name, c in golden("gnn_layer.pt").items():
         tw, dp = c["time_window"], c["pos"].shape[1]
         layer, sd, x, u, pos, y = _run_layer(c, tw, dp, c["seed"])
@@ -94,8 +106,9 @@ def test_gnn_layer_golden(golden):
 
 
 @pytest.mark.parametrize("B,N,r,trunc", [(4, 4096, 0.03, False), (2, 2048, 0.12, True)])
-def test_gnn_layer_vs_oracle_fp64(B, N, r, trunc):
+def test_gnn_layer_vs_oracle_fp64(B, N, r, trunc, precision):
     """config-2 shaped layer (64x64 irregular-uniform mesh); fp64 oracle as the arbiter."""
+    TOL = _tol(precision)
     g = S._gen(40 + B)
     pos = torch.rand(B * N, 2, generator=g)
     batch = torch.arange(B).repeat_interleave(N)
@@ -124,8 +137,9 @@ def test_gnn_layer_vs_oracle_fp64(B, N, r, trunc):
         assert torch.equal(p.grad, q.grad), k
 
 
-def test_gnn_layer_isolated_nodes_and_arbitrary_edge_index():
+def test_gnn_layer_isolated_nodes_and_arbitrary_edge_index(precision):
     """edge_index the layer did not build itself: unsorted, duplicated, with isolated nodes."""
+    TOL = _tol(precision)
     g = S._gen(50)
     N, E = 500, 3000
     ei = torch.randint(0, N - 50, (2, E), generator=g)       # the last 50 nodes receive nothing
