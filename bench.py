@@ -171,8 +171,9 @@ def workload_config(n_gpus, note=None):
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from magnet_b200 import _lib, graph as MG
+    from magnet_b200 import _lib, graph as MG, functional as MF
     from magnet_b200.mpnn import GNN_Layer
+    MF.set_precision(args.precision)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     L = _lib.lib()
@@ -266,12 +267,15 @@ def run_ours(args, rank, world, local_rank):
                     "executed_tflops": 3 * EXEC_FLOP_PER_EDGE_FWD * E / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0,
                     "edge_fwd_kernel_ms": fwd_ms,
                     "edge_fwd_algorithmic_tflops": FLOP_PER_EDGE_FWD * E / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0,
-                    "note": "fp32 FFMA path (1e-5 contract) measured against the bf16 tensor peak"}
+                    "note": {"fp32": "fp32 FFMA path (1e-5 contract) measured against the bf16 tensor peak",
+                             "fp32_tc": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (1e-5 contract)",
+                             "bf16": "tcgen05 bf16 operands, fp32 accumulate (1e-2 contract)"}[args.precision]}
         line = {
             "metric": "edges/s per MP layer fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks.summary(),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": dict(workload_config(world), precision=args.precision), "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline, "edges_per_gpu": E,
@@ -294,6 +298,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc", "bf16"],
+                    help="edge-kernel arithmetic: fp32 FFMA | tcgen05 bf16 hi/lo split (1e-5 contract) | tcgen05 bf16 (1e-2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

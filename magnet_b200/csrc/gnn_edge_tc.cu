@@ -78,6 +78,55 @@ segment_fixup_tc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __res
     out[(int64_t)node * ld_out + c] = mean ? acc / (float)(s1 - s0) : acc;
 }
 
+// Producer warp `pw` of TC_PROD_WARPS fills rows [pw*16, pw*16+16) of the edge tile:
+//   h1[e][:] = Swish(P[dst_e] + Q[src_e])  ->  bf16 (hi[/lo]) K-major swizzled image(s).
+// Coalesced 512-byte row reads (one float4 per lane); the P row is reused while dst stays the same.
+template <int NSPLIT, bool FAST>
+__device__ __forceinline__ void produce_h1_rows(const float* __restrict__ pq, const int32_t* __restrict__ dstv,
+                                                const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int pw,
+                                                int lane, uint64_t* empty_bar, uint32_t empty_parity, unsigned char* img) {
+    constexpr int ROWS = TCE / TC_PROD_WARPS;   // 16
+    const int64_t e0 = tile * TCE + pw * ROWS;
+    int my_d = -1, my_s = -1;
+    if (lane < ROWS && e0 + lane < n_edges) {
+        my_d = dstv[e0 + lane];
+        my_s = srcv[e0 + lane];
+    }
+    umma::mbar_wait(empty_bar, empty_parity);
+    int prev_d = -2;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < ROWS; ++r) {
+        const int d = __shfl_sync(0xffffffffu, my_d, r);
+        const int sidx = __shfl_sync(0xffffffffu, my_s, r);
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d >= 0) {
+            if (d != prev_d) {
+                p = *reinterpret_cast<const float4*>(pq + (int64_t)d * (2 * TCH) + lane * 4);
+                prev_d = d;
+            }
+            const float4 q = *reinterpret_cast<const float4*>(pq + (int64_t)sidx * (2 * TCH) + TCH + lane * 4);
+            float z;
+            z = p.x + q.x; h.x = z * sigmoid_tc<FAST>(z);
+            z = p.y + q.y; h.y = z * sigmoid_tc<FAST>(z);
+            z = p.z + q.z; h.z = z * sigmoid_tc<FAST>(z);
+            z = p.w + q.w; h.w = z * sigmoid_tc<FAST>(z);
+        }
+        const uint32_t off = umma::tile_off(128, pw * ROWS + r, lane * 4);
+        if (NSPLIT == 1) {
+            *reinterpret_cast<uint2*>(img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
+        } else {
+            __nv_bfloat16 hi[4], lo[4];
+            umma::split_bf16(h.x, hi[0], lo[0]);
+            umma::split_bf16(h.y, hi[1], lo[1]);
+            umma::split_bf16(h.z, hi[2], lo[2]);
+            umma::split_bf16(h.w, hi[3], lo[3]);
+            *reinterpret_cast<uint2*>(img + off) = *reinterpret_cast<uint2*>(hi);
+            *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = *reinterpret_cast<uint2*>(lo);
+        }
+    }
+}
+
 struct EdgeFwdTcArgs {
     const float* pq;         // [N][256]  P | Q  (fp32)
     const int32_t* rowptr;   // [N+1]
@@ -229,51 +278,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
     } else {
         // =========================== producers: 16 consecutive edge rows per warp ===================
         const int pw = warp - TC_EPI_WARPS - 1;
-        constexpr int ROWS = TCE / TC_PROD_WARPS;   // 16
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
-            const int64_t e0 = tile * TCE + pw * ROWS;
-            int my_d = -1, my_s = -1;
-            if (lane < ROWS && e0 + lane < a.n_edges) {
-                my_d = a.dstv[e0 + lane];
-                my_s = a.srcv[e0 + lane];
-            }
-            umma::mbar_wait(&empty[s], ph ^ 1);
-            unsigned char* img = b_img + (size_t)s * NSPLIT * TILE_BYTES;
-            int prev_d = -2;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int r = 0; r < ROWS; ++r) {
-                const int d = __shfl_sync(0xffffffffu, my_d, r);
-                const int sidx = __shfl_sync(0xffffffffu, my_s, r);
-                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (d >= 0) {
-                    if (d != prev_d) {
-                        p = *reinterpret_cast<const float4*>(a.pq + (int64_t)d * (2 * TCH) + lane * 4);
-                        prev_d = d;
-                    }
-                    const float4 q = *reinterpret_cast<const float4*>(a.pq + (int64_t)sidx * (2 * TCH) + TCH + lane * 4);
-                    float z;
-                    z = p.x + q.x; h.x = z * sigmoid_tc<FAST>(z);
-                    z = p.y + q.y; h.y = z * sigmoid_tc<FAST>(z);
-                    z = p.z + q.z; h.z = z * sigmoid_tc<FAST>(z);
-                    z = p.w + q.w; h.w = z * sigmoid_tc<FAST>(z);
-                }
-                const uint32_t off = umma::tile_off(128, pw * ROWS + r, lane * 4);
-                if (NSPLIT == 1) {
-                    *reinterpret_cast<uint2*>(img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
-                } else {
-                    __nv_bfloat16 hi[4], lo[4];
-                    umma::split_bf16(h.x, hi[0], lo[0]);
-                    umma::split_bf16(h.y, hi[1], lo[1]);
-                    umma::split_bf16(h.z, hi[2], lo[2]);
-                    umma::split_bf16(h.w, hi[3], lo[3]);
-                    *reinterpret_cast<uint2*>(img + off) = *reinterpret_cast<uint2*>(hi);
-                    *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = *reinterpret_cast<uint2*>(lo);
-                }
-            }
+            produce_h1_rows<NSPLIT, FAST>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], ph ^ 1,
+                                          b_img + (size_t)s * NSPLIT * TILE_BYTES);
             umma::fence_async_smem();
             umma::mbar_arrive(&full[s]);
         }
@@ -317,6 +327,376 @@ int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, co
         segment_fixup_tc_kernel<<<(unsigned)(tiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, TCE, part_head, part_tail, agg, TCH, 1);
         MGB_LAUNCH_CHECK();
     }
+    return MGB_OK;
+}
+
+// ==================================================================================================
+// Backward (recompute).  Per 128-edge tile, all contractions on the tensor core, transposed so that an
+// epilogue thread owns one channel:
+//   MMA1  D1[n][e] = sum_k W2[n][k] h1[e][k]          A = W2 image (K-major),  B = h1 tile (K-major)
+//   epi1  dz2[e][n] = dagg[dst_e][n]/deg * Swish'(D1 + b2[n])  -> DZt tile [n][e] (bf16 hi[/lo]);  db2[n] += dz2
+//   MMA2  D2[k][e] = sum_n W2[n][k] dz2[e][n]         A = W2 image (MN-major), B = DZt tile (MN-major)
+//   MMA3  D3[n][k] += sum_e dz2[e][n] h1[e][k]        A = DZt tile (K-major),  B = h1 tile (MN-major)
+//         D3 = dW2 stays in TMEM for the whole persistent CTA (one [128][128] partial per CTA at the end)
+//   epi2  dz1[e][k] = D2 * Swish'(P[dst_e][k] + Q[src_e][k])  -> global dz1 (by-source reduction later)
+//         and the segmented SUM over the dst-sorted positions -> dP[dst]      (no atomics)
+// ==================================================================================================
+struct EdgeBwdTcArgs {
+    const float* pq;
+    const int32_t* rowptr;
+    const int32_t* dstv;
+    const int32_t* srcv;
+    int64_t n_edges;
+    const unsigned char* w2img;
+    const float* b2;
+    const float* dagg;       // [N][ld_dagg]
+    int ld_dagg;
+    float* dz1;              // [E][128]
+    float* dpq;              // [N][256]: columns [0,128) = dP written here (pre-zeroed)
+    float* part_head;
+    float* part_tail;
+    float* dw2_partial;      // [grid][128][128]
+    float* db2_partial;      // [grid][128]
+};
+
+template <int NSPLIT>
+constexpr int edge_bwd_tc_stages() { return NSPLIT == 1 ? 2 : 1; }
+template <int NSPLIT>
+constexpr size_t edge_bwd_tc_smem() {
+    return 1024 + (size_t)NSPLIT * TILE_BYTES * (2 + edge_bwd_tc_stages<NSPLIT>()) + 4 * TCE * sizeof(int) + 256;
+}
+
+template <int NSPLIT, bool FAST>
+__global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const EdgeBwdTcArgs a) {
+    constexpr int STAGES = edge_bwd_tc_stages<NSPLIT>();
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = umma::smem_u32(smem_raw);
+    unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* w_img = base;
+    unsigned char* h_img = w_img + (size_t)NSPLIT * TILE_BYTES;                 // [stage][split]
+    unsigned char* dz_img = h_img + (size_t)STAGES * NSPLIT * TILE_BYTES;       // [split]   DZt[n][e]
+    int* epi_dst = reinterpret_cast<int*>(dz_img + (size_t)NSPLIT * TILE_BYTES);   // [2][128]
+    int* epi_src = epi_dst + 2 * TCE;                                              // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_src + 2 * TCE);
+    uint64_t* full = bars;               // [2] producers -> MMA (h1 tile ready)
+    uint64_t* empty = bars + 2;          // [2] MMA3 done -> producers
+    uint64_t* d1_full = bars + 4;        // MMA1 done -> epilogue
+    uint64_t* dz_full = bars + 5;        // epilogue wrote DZt -> MMA
+    uint64_t* dz_empty = bars + 6;       // MMA2+MMA3 done reading DZt -> epilogue
+    uint64_t* d2_full = bars + 7;        // MMA2 done -> epilogue
+    uint64_t* d2_empty = bars + 8;       // epilogue drained D2 -> MMA
+    uint64_t* d3_full = bars + 9;        // all MMA3 done -> epilogue (final dW2 read-out)
+    uint64_t* wbar = bars + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = ceil_div<int64_t>(a.n_edges, TCE);
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            umma::mbar_init(&full[s], TC_PROD_WARPS * 32);
+            umma::mbar_init(&empty[s], 1);
+        }
+        umma::mbar_init(d1_full, 1);
+        umma::mbar_init(dz_full, TC_EPI_WARPS * 32);
+        umma::mbar_init(dz_empty, 1);
+        umma::mbar_init(d2_full, 1);
+        umma::mbar_init(d2_empty, TC_EPI_WARPS * 32);
+        umma::mbar_init(d3_full, 1);
+        umma::mbar_init(wbar, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == TC_EPI_WARPS) umma::tmem_alloc(tmem_slot, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;
+
+    if (warp < TC_EPI_WARPS) {
+        // =========================== epilogue: thread = channel ===================================
+        const int n = tid;
+        const float bias = a.b2[n];
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        float db = 0.f;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            const int64_t e0 = tile * TCE;
+            const int ne = (int)((a.n_edges - e0) < (int64_t)TCE ? (a.n_edges - e0) : (int64_t)TCE);
+            const int64_t e1 = e0 + ne;
+            int* dsts = epi_dst + (it & 1) * TCE;
+            int* srcs = epi_src + (it & 1) * TCE;
+            dsts[tid] = tid < ne ? a.dstv[e0 + tid] : -1;
+            srcs[tid] = tid < ne ? a.srcv[e0 + tid] : -1;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // ---- epi1: dz2 = dagg[dst]/deg * Swish'(z2) -> DZt (rows = channel, cols = edge) ----
+            umma::mbar_wait(d1_full, ph);
+            umma::mbar_wait(dz_empty, ph ^ 1);
+            umma::tc_fence_after();
+            {
+                int cur = -1;
+                float g = 0.f;
+#pragma unroll 1
+                for (int c0 = 0; c0 < TCE; c0 += 32) {
+                    float v[32];
+                    umma::tmem_ld32(tm_d1 + lane_base + c0, v);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int e = c0 + i;
+                        const int d = dsts[e];
+                        float o = 0.f;
+                        if (d >= 0) {
+                            if (d != cur) {
+                                cur = d;
+                                const float deg = (float)(a.rowptr[d + 1] - a.rowptr[d]);
+                                g = a.dagg[(int64_t)d * a.ld_dagg + n] / deg;
+                            }
+                            const float z = v[i] + bias;
+                            const float sg = sigmoid_tc<FAST>(z);
+                            o = g * (sg * fmaf(z, 1.0f - sg, 1.0f));
+                        }
+                        v[i] = o;
+                        db += o;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t off = umma::tile_off(128, n, c0 + 8 * j);
+                        if (NSPLIT == 1) {
+                            uint4 w;
+                            w.x = umma::pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                            w.y = umma::pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                            w.z = umma::pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                            w.w = umma::pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                            *reinterpret_cast<uint4*>(dz_img + off) = w;
+                        } else {
+                            __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) umma::split_bf16(v[8 * j + q], hi[q], lo[q]);
+                            *reinterpret_cast<uint4*>(dz_img + off) = *reinterpret_cast<uint4*>(hi);
+                            *reinterpret_cast<uint4*>(dz_img + TILE_BYTES + off) = *reinterpret_cast<uint4*>(lo);
+                        }
+                    }
+                }
+            }
+            umma::fence_async_smem();
+            umma::tc_fence_before();
+            umma::mbar_arrive(dz_full);
+            // ---- epi2: dz1 = dh1 * Swish'(z1) -> global + segmented sum by destination -> dP ----
+            umma::mbar_wait(d2_full, ph);
+            umma::tc_fence_after();
+            {
+                int cur = dsts[0];
+                float sum = 0.f;
+                float pk = a.pq[(int64_t)cur * (2 * TCH) + n];
+                auto flush = [&](int node, float v) {
+                    const int64_t s0 = a.rowptr[node], s1 = a.rowptr[node + 1];
+                    if (s0 >= e0 && s1 <= e1) a.dpq[(int64_t)node * (2 * TCH) + n] = v;
+                    else if (s0 < e0) a.part_head[tile * TCH + n] = v;
+                    else a.part_tail[tile * TCH + n] = v;
+                };
+#pragma unroll 1
+                for (int c0 = 0; c0 < TCE; c0 += 32) {
+                    float v[32];
+                    umma::tmem_ld32(tm_d2 + lane_base + c0, v);
+                    if (c0 + 32 >= TCE) {
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(d2_empty);
+                    }
+                    if (c0 < ne) {
+                        float q[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int sidx = srcs[c0 + i];
+                            q[i] = sidx >= 0 ? a.pq[(int64_t)sidx * (2 * TCH) + TCH + n] : 0.f;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int e = c0 + i;
+                            if (e < ne) {
+                                const int d = dsts[e];
+                                if (d != cur) {
+                                    flush(cur, sum);
+                                    cur = d;
+                                    sum = 0.f;
+                                    pk = a.pq[(int64_t)d * (2 * TCH) + n];
+                                }
+                                const float z = pk + q[i];
+                                const float sg = sigmoid_tc<FAST>(z);
+                                const float o = v[i] * (sg * fmaf(z, 1.0f - sg, 1.0f));
+                                a.dz1[(e0 + e) * TCH + n] = o;
+                                sum += o;
+                            }
+                        }
+                    }
+                }
+                flush(cur, sum);
+            }
+        }
+        // ---- final: dW2 partial of this CTA (D3) and db2 partial ----
+        if (it > 0) {
+            umma::mbar_wait(d3_full, 0);
+            umma::tc_fence_after();
+            float* out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH;
+#pragma unroll 1
+            for (int c0 = 0; c0 < TCH; c0 += 32) {
+                float v[32];
+                umma::tmem_ld32(tm_d3 + lane_base + c0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(out + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        } else {
+            float* out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH;
+            for (int c = 0; c < TCH; ++c) out[c] = 0.f;
+        }
+        a.db2_partial[(int64_t)blockIdx.x * TCH + n] = db;
+    } else if (warp == TC_EPI_WARPS) {
+        // =========================== MMA issue ====================================================
+        if (lane == 0) {
+            const uint32_t bytes = NSPLIT * TILE_BYTES;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(wbar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             umma::smem_u32(w_img)),
+                         "l"(a.w2img), "r"(bytes), "r"(umma::smem_u32(wbar))
+                         : "memory");
+        }
+        umma::mbar_wait(wbar, 0);
+        const uint32_t id_kk = umma::idesc_bf16(128, 128, 0, 0);     // A K-major,  B K-major   (MMA1)
+        const uint32_t id_mm = umma::idesc_bf16(128, 128, 1, 1);     // A MN-major, B MN-major  (MMA2)
+        const uint32_t id_km = umma::idesc_bf16(128, 128, 0, 1);     // A K-major,  B MN-major  (MMA3)
+        const uint32_t w_s = umma::smem_u32(w_img), dz_s = umma::smem_u32(dz_img);
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % STAGES;
+            const uint32_t sph = (it / STAGES) & 1;
+            const uint32_t ph = it & 1;
+            const uint32_t h_s = umma::smem_u32(h_img + (size_t)s * NSPLIT * TILE_BYTES);
+            umma::mbar_wait(&full[s], sph);
+            umma::tc_fence_after();
+            if (lane == 0) {
+                uint32_t accum = 0;
+#pragma unroll
+                for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
+                    const int wa = term == 2 ? 1 : 0, hb = term == 1 ? 1 : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        umma::mma_bf16(tm_d1, umma::desc_kmajor(w_s + wa * TILE_BYTES, k), umma::desc_kmajor(h_s + hb * TILE_BYTES, k),
+                                       id_kk, accum);
+                        accum = 1;
+                    }
+                }
+                umma::mma_commit(d1_full);
+            }
+            __syncwarp();
+            umma::mbar_wait(dz_full, ph);
+            umma::mbar_wait(d2_empty, ph ^ 1);
+            umma::tc_fence_after();
+            if (lane == 0) {
+                uint32_t accum = 0;
+#pragma unroll
+                for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
+                    const int wa = term == 2 ? 1 : 0, zb = term == 1 ? 1 : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {     // K = n
+                        umma::mma_bf16(tm_d2, umma::desc_mnmajor(w_s + wa * TILE_BYTES, k), umma::desc_mnmajor(dz_s + zb * TILE_BYTES, k),
+                                       id_mm, accum);
+                        accum = 1;
+                    }
+                }
+                umma::mma_commit(d2_full);
+                accum = it > 0 ? 1u : 0u;
+#pragma unroll
+                for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
+                    const int za = term == 2 ? 1 : 0, hb = term == 1 ? 1 : 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {     // K = e
+                        umma::mma_bf16(tm_d3, umma::desc_kmajor(dz_s + za * TILE_BYTES, k), umma::desc_mnmajor(h_s + hb * TILE_BYTES, k),
+                                       id_km, accum);
+                        accum = 1;
+                    }
+                }
+                umma::mma_commit(&empty[s]);
+                umma::mma_commit(dz_empty);
+            }
+            __syncwarp();
+        }
+        if (lane == 0 && it > 0) umma::mma_commit(d3_full);
+        __syncwarp();
+    } else {
+        // =========================== producers ====================================================
+        const int pw = warp - TC_EPI_WARPS - 1;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % STAGES;
+            const uint32_t sph = (it / STAGES) & 1;
+            produce_h1_rows<NSPLIT, FAST>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], sph ^ 1,
+                                          h_img + (size_t)s * NSPLIT * TILE_BYTES);
+            umma::fence_async_smem();
+            umma::mbar_arrive(&full[s]);
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == TC_EPI_WARPS) umma::tmem_dealloc(tmem, 512);
+}
+
+int edge_bwd_tc_grid(int64_t n_edges) {
+    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TCE);
+    return (int)(tiles < sm_count() ? tiles : sm_count());
+}
+
+size_t edge_bwd_tc_workspace(int64_t n_edges) {
+    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TCE);
+    const int grid = edge_bwd_tc_grid(n_edges);
+    return 2 * align_up((size_t)tiles * TCH * sizeof(float)) + align_up((size_t)grid * TCH * TCH * sizeof(float)) +
+           align_up((size_t)grid * TCH * sizeof(float)) + 1024;
+}
+
+__global__ void __launch_bounds__(256)
+sum_partials_tc_kernel(const float* __restrict__ partial, int n_parts, int64_t count, float* __restrict__ out, int accumulate) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.f;
+    for (int p = 0; p < n_parts; ++p) s += partial[(int64_t)p * count + i];
+    out[i] = accumulate ? out[i] + s : s;
+}
+
+int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv,
+                       int64_t n_edges, const void* w2img, const float* b2, const float* dagg, int ld_dagg, float* dz1,
+                       float* dpq, float* dW2, float* db2, int accumulate, void* ws_ptr, size_t ws_bytes, cudaStream_t s) {
+    if (n_edges <= 0) return MGB_OK;
+    const int64_t tiles = ceil_div<int64_t>(n_edges, TCE);
+    const int grid = edge_bwd_tc_grid(n_edges);
+    Workspace ws(ws_ptr, ws_bytes);
+    float* part_head = ws.take<float>((size_t)tiles * TCH);
+    float* part_tail = ws.take<float>((size_t)tiles * TCH);
+    float* dw2_part = ws.take<float>((size_t)grid * TCH * TCH);
+    float* db2_part = ws.take<float>((size_t)grid * TCH);
+    MGB_WS_CHECK(ws);
+    EdgeBwdTcArgs a{pq, rowptr, dstv, srcv, n_edges, (const unsigned char*)w2img, b2, dagg, ld_dagg, dz1, dpq,
+                    part_head, part_tail, dw2_part, db2_part};
+    {
+        ProfScope prof(PROF_EDGE_BWD, s);
+        if (precision == 2) {
+            constexpr size_t smem = edge_bwd_tc_smem<1>();
+            MGB_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gnn_edge_bwd_tc_kernel<1, true><<<grid, TC_THREADS, smem, s>>>(a);
+        } else {
+            constexpr size_t smem = edge_bwd_tc_smem<2>();
+            MGB_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            gnn_edge_bwd_tc_kernel<2, false><<<grid, TC_THREADS, smem, s>>>(a);
+        }
+    }
+    MGB_LAUNCH_CHECK();
+    if (tiles > 1) {
+        segment_fixup_tc_kernel<<<(unsigned)(tiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, TCE, part_head, part_tail, dpq, 2 * TCH, 0);
+        MGB_LAUNCH_CHECK();
+    }
+    sum_partials_tc_kernel<<<ceil_div(TCH * TCH, 256), 256, 0, s>>>(dw2_part, grid, (int64_t)TCH * TCH, dW2, accumulate);
+    MGB_LAUNCH_CHECK();
+    sum_partials_tc_kernel<<<1, 256, 0, s>>>(db2_part, grid, TCH, db2, accumulate);
+    MGB_LAUNCH_CHECK();
     return MGB_OK;
 }
 

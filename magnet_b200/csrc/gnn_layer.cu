@@ -634,6 +634,7 @@ size_t gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp,
     if (w2 > w) w = w2;
     if (w3 > w) w = w3;
     b += w + inorm_workspace_bytes(n_graphs, max_nodes) + 8192;
+    b += align_up(edge_bwd_tc_workspace(n_edges));
     return b;
 }
 
@@ -659,7 +660,10 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     float* db2_part = ws.take<float>((size_t)grid * H);
     float* dwcat = ws.take<float>((size_t)2 * H * sh.Kc());
     float* dbcat = ws.take<float>(2 * H);
+    const size_t tc_bytes = edge_bwd_tc_workspace(sh.n_edges);
+    char* tc_ws = ws.take<char>(tc_bytes);
     MGB_WS_CHECK(ws);
+    MGB_REQUIRE(sh.precision >= 0 && sh.precision <= 2, "gnn_layer: unknown precision %d", sh.precision);
     void* sub_ws = ws.base + ws.off;
     size_t sub_bytes = ws.cap - ws.off;
     const int acc = io.accumulate_params;
@@ -694,7 +698,12 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     }
     // B4. fused edge backward (dagg = dc[:, H:2H])
     MGB_CUDA(cudaMemsetAsync(dpq, 0, (size_t)N * 2 * H * sizeof(float), s));
-    if (sh.n_edges > 0) {
+    if (sh.n_edges > 0 && sh.precision != 0) {
+        MGB_TRY(launch_edge_bwd_tc(sh.precision, io.pq, io.rowptr, io.dstv, io.srcv, sh.n_edges, p.w2img, io.b2, dc + H, ldc,
+                                   dz1, dpq, io.dW2, io.db2, acc, tc_ws, tc_bytes, s));
+        gather_sum_rows_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)N * 32, 256), 256, 0, s>>>(dz1, io.rowptr_t, io.pos_t, N, dpq + H, 2 * H);
+        MGB_LAUNCH_CHECK();
+    } else if (sh.n_edges > 0) {
         EdgeBwdArgs a{io.pq, io.rowptr, io.dstv, io.srcv, sh.n_edges, p.w2t, io.W2, io.b2, dc + H, ldc,
                       dz1, dpq, part_head, part_tail, dw2_part, db2_part};
         MGB_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_BWD_SMEM));

@@ -71,6 +71,10 @@ size_t edge_fwd_tc_workspace(int64_t n_edges);
 int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv,
                        int64_t n_edges, const void* w2img, const float* b2, float* agg, void* ws, size_t ws_bytes,
                        cudaStream_t s);
+size_t edge_bwd_tc_workspace(int64_t n_edges);
+int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv,
+                       int64_t n_edges, const void* w2img, const float* b2, const float* dagg, int ld_dagg, float* dz1,
+                       float* dpq, float* dW2, float* db2, int accumulate, void* ws, size_t ws_bytes, cudaStream_t s);
 // umma_selftest.cu
 int umma_selftest(const float* a, const float* b, int a_mn, int b_mn, int lbo_mn, int sbo_mn, float* d, cudaStream_t s);
 
