@@ -31,16 +31,44 @@ constexpr int TCE = 128;            // edge positions per tile (MMA N)
 constexpr int TILE_BYTES = 128 * 256;   // one [128][128] bf16 image
 constexpr int TC_STAGES = 2;
 constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 1 + TC_PROD_WARPS) * 32;
+constexpr int TC_MMA_WARP = TC_EPI_WARPS, TC_META_WARP = TC_EPI_WARPS + 1, TC_PROD_WARP0 = TC_EPI_WARPS + 2;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
+constexpr int META_STAGES = 4;
 
+// ---- activations ------------------------------------------------------------------------------------
+// FAST (bf16 contract): sigmoid through one MUFU.TANH; precise: ex2.approx + rcp.approx (2 MUFU, ~2 ulp).
 template <bool FAST>
-__device__ __forceinline__ float sigmoid_tc(float x) {
+__device__ __forceinline__ float sigmoid_tc(float z) {
     if (FAST) {
         float t;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
         return fmaf(0.5f, t, 0.5f);
     }
-    return sigmoid_f(x);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+template <bool FAST>
+__device__ __forceinline__ float swish_tc(float z) {
+    if (FAST) {
+        float t;
+        const float h = 0.5f * z;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        return fmaf(h, t, h);
+    }
+    return z * sigmoid_tc<false>(z);
+}
+template <bool FAST>
+__device__ __forceinline__ float swish_grad_tc(float z) {
+    const float s = sigmoid_tc<FAST>(z);
+    return s * fmaf(z, 1.0f - s, 1.0f);
+}
+
+// two floats -> bf16x2 (hi) and the bf16x2 of the residuals (lo); ~3 instructions per element
+__device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = umma::pack_bf16(a, b);
+    lo = umma::pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
 // ---- W2 -> swizzled bf16 images (hi, lo) ----------------------------------------------------------
@@ -78,9 +106,64 @@ segment_fixup_tc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __res
     out[(int64_t)node * ld_out + c] = mean ? acc / (float)(s1 - s0) : acc;
 }
 
+// ---- per-tile segment metadata, produced ahead of time by the meta warp ----------------------------------
+struct TileMeta {
+    int dst[TCE];          // destination node of every position (-1 past the end of the edge list)
+    int src[TCE];
+    float scale[TCE];      // at segment-END positions: 1 / in-degree of the destination
+    int kind[TCE];         // at segment-END positions: 1 = segment lies inside the tile, 2 = began in an earlier
+                           // tile (head partial), 3 = continues into a later tile (tail partial)
+    int segdst[TCE];       // the tile's segments in order: destination node, 1 / in-degree
+    float seginv[TCE];
+    uint32_t endmask[4];   // bit p of the 128-bit mask: position p is the last of its segment within the tile
+    int nseg;
+    int pad[3];
+};
+
+// one warp; positions p = j*32 + lane
+__device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dstv,
+                                                const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int lane) {
+    const int64_t e0 = tile * TCE;
+    const int64_t e1 = (e0 + TCE < n_edges) ? e0 + TCE : n_edges;
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = j * 32 + lane;
+        const int64_t e = e0 + p;
+        const bool valid = e < e1;
+        const int d = valid ? dstv[e] : -1;
+        const int sidx = valid ? srcv[e] : -1;
+        const int nxt = (valid && e + 1 < e1) ? dstv[e + 1] : -2;
+        const int prv = (valid && p > 0) ? dstv[e - 1] : -2;
+        const bool is_end = valid && nxt != d;
+        const bool is_start = valid && prv != d;
+        int s0 = 0, s1 = 1;
+        if (is_end || is_start) {
+            s0 = rowptr[d];
+            s1 = rowptr[d + 1];
+        }
+        const float inv = 1.0f / (float)(s1 - s0);
+        M->dst[p] = d;
+        M->src[p] = sidx;
+        M->scale[p] = inv;
+        M->kind[p] = !is_end ? 0 : ((int64_t)s0 >= e0 && (int64_t)s1 <= e1) ? 1 : ((int64_t)s0 < e0 ? 2 : 3);
+        const uint32_t em = __ballot_sync(0xffffffffu, is_end);
+        const uint32_t sm = __ballot_sync(0xffffffffu, is_start);
+        if (lane == 0) M->endmask[j] = em;
+        if (is_start) {
+            const int idx = base + __popc(sm & ((1u << lane) - 1u));
+            M->segdst[idx] = d;
+            M->seginv[idx] = inv;
+        }
+        base += __popc(sm);
+    }
+    if (lane == 0) M->nseg = base;
+}
+
 // Producer warp `pw` of TC_PROD_WARPS fills rows [pw*16, pw*16+16) of the edge tile:
 //   h1[e][:] = Swish(P[dst_e] + Q[src_e])  ->  bf16 (hi[/lo]) K-major swizzled image(s).
-// Coalesced 512-byte row reads (one float4 per lane); the P row is reused while dst stays the same.
+// All 16 Q-row gathers of the warp are issued before the first use (one 512-byte coalesced row per
+// load instruction, float4 per lane); the P row is reused while dst stays the same.
 template <int NSPLIT, bool FAST>
 __device__ __forceinline__ void produce_h1_rows(const float* __restrict__ pq, const int32_t* __restrict__ dstv,
                                                 const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int pw,
@@ -92,41 +175,56 @@ __device__ __forceinline__ void produce_h1_rows(const float* __restrict__ pq, co
         my_d = dstv[e0 + lane];
         my_s = srcv[e0 + lane];
     }
+    float4 q[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int sidx = __shfl_sync(0xffffffffu, my_s, r);
+        q[r] = *reinterpret_cast<const float4*>(pq + (int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + lane * 4);
+    }
+    int prev_d = __shfl_sync(0xffffffffu, my_d, 0);
+    float4 p = *reinterpret_cast<const float4*>(pq + (int64_t)(prev_d < 0 ? 0 : prev_d) * (2 * TCH) + lane * 4);
+    // byte offset of this lane's 4 channels inside a row of the swizzled image (row & 7 == r & 7 as pw*16 % 8 == 0)
+    const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
+    const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
     umma::mbar_wait(empty_bar, empty_parity);
-    int prev_d = -2;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll
     for (int r = 0; r < ROWS; ++r) {
         const int d = __shfl_sync(0xffffffffu, my_d, r);
-        const int sidx = __shfl_sync(0xffffffffu, my_s, r);
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d >= 0) {
-            if (d != prev_d) {
-                p = *reinterpret_cast<const float4*>(pq + (int64_t)d * (2 * TCH) + lane * 4);
-                prev_d = d;
-            }
-            const float4 q = *reinterpret_cast<const float4*>(pq + (int64_t)sidx * (2 * TCH) + TCH + lane * 4);
-            float z;
-            z = p.x + q.x; h.x = z * sigmoid_tc<FAST>(z);
-            z = p.y + q.y; h.y = z * sigmoid_tc<FAST>(z);
-            z = p.z + q.z; h.z = z * sigmoid_tc<FAST>(z);
-            z = p.w + q.w; h.w = z * sigmoid_tc<FAST>(z);
+        if (d != prev_d) {
+            if (d >= 0) p = *reinterpret_cast<const float4*>(pq + (int64_t)d * (2 * TCH) + lane * 4);
+            prev_d = d;
         }
-        const uint32_t off = umma::tile_off(128, pw * ROWS + r, lane * 4);
+        float4 h;
+        h.x = swish_tc<FAST>(p.x + q[r].x);
+        h.y = swish_tc<FAST>(p.y + q[r].y);
+        h.z = swish_tc<FAST>(p.z + q[r].z);
+        h.w = swish_tc<FAST>(p.w + q[r].w);
+        if (d < 0) h = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t off = lane_blk + (uint32_t)(pw * ROWS + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
         if (NSPLIT == 1) {
             *reinterpret_cast<uint2*>(img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
         } else {
-            __nv_bfloat16 hi[4], lo[4];
-            umma::split_bf16(h.x, hi[0], lo[0]);
-            umma::split_bf16(h.y, hi[1], lo[1]);
-            umma::split_bf16(h.z, hi[2], lo[2]);
-            umma::split_bf16(h.w, hi[3], lo[3]);
-            *reinterpret_cast<uint2*>(img + off) = *reinterpret_cast<uint2*>(hi);
-            *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = *reinterpret_cast<uint2*>(lo);
+            uint2 hi, lo;
+            split2_bf16(h.x, h.y, hi.x, lo.x);
+            split2_bf16(h.z, h.w, hi.y, lo.y);
+            *reinterpret_cast<uint2*>(img + off) = hi;
+            *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = lo;
         }
     }
 }
 
+__device__ __forceinline__ void load_w2_image(unsigned char* w_img, const unsigned char* src, uint32_t bytes, uint64_t* wbar) {
+    // one bulk async copy (TMA engine; no tensor map is needed for a pre-swizzled image)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(wbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     umma::smem_u32(w_img)),
+                 "l"(src), "r"(bytes), "r"(umma::smem_u32(wbar))
+                 : "memory");
+}
+
+// ==================================================================================================
+// Forward
+// ==================================================================================================
 struct EdgeFwdTcArgs {
     const float* pq;         // [N][256]  P | Q  (fp32)
     const int32_t* rowptr;   // [N+1]
@@ -142,7 +240,7 @@ struct EdgeFwdTcArgs {
 
 template <int NSPLIT>
 constexpr size_t edge_fwd_tc_smem() {
-    return 1024 + (size_t)NSPLIT * TILE_BYTES * (1 + TC_STAGES) + 2 * TCE * sizeof(int) + 256;
+    return 1024 + (size_t)NSPLIT * TILE_BYTES * (1 + TC_STAGES) + META_STAGES * sizeof(TileMeta) + 256;
 }
 
 template <int NSPLIT, bool FAST>
@@ -152,31 +250,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     unsigned char* w_img = base;                                         // NSPLIT images
     unsigned char* b_img = base + (size_t)NSPLIT * TILE_BYTES;            // [stage][split]
-    int* epi_dst = reinterpret_cast<int*>(b_img + (size_t)TC_STAGES * NSPLIT * TILE_BYTES);   // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_dst + 2 * TCE);
-    uint64_t* full = bars;                    // [stages] producers -> MMA
-    uint64_t* empty = bars + TC_STAGES;       // [stages] MMA -> producers
-    uint64_t* tfull = bars + 2 * TC_STAGES;   // [2] MMA -> epilogue
-    uint64_t* tempty = bars + 2 * TC_STAGES + 2;   // [2] epilogue -> MMA
-    uint64_t* wbar = bars + 2 * TC_STAGES + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 5);
+    TileMeta* metas = reinterpret_cast<TileMeta*>(b_img + (size_t)TC_STAGES * NSPLIT * TILE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(metas + META_STAGES);
+    uint64_t* full = bars;                    // [2] producers -> MMA
+    uint64_t* empty = bars + 2;               // [2] MMA -> producers
+    uint64_t* tfull = bars + 4;               // [2] MMA -> epilogue
+    uint64_t* tempty = bars + 6;              // [2] epilogue -> MMA
+    uint64_t* mfull = bars + 8;               // [META_STAGES] meta warp -> epilogue
+    uint64_t* mempty = bars + 8 + META_STAGES;   // [META_STAGES] epilogue -> meta warp
+    uint64_t* wbar = bars + 8 + 2 * META_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * META_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = ceil_div<int64_t>(a.n_edges, TCE);
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < 2; ++s) {
             umma::mbar_init(&full[s], TC_PROD_WARPS * 32);
             umma::mbar_init(&empty[s], 1);
-        }
-        for (int s = 0; s < 2; ++s) {
             umma::mbar_init(&tfull[s], 1);
             umma::mbar_init(&tempty[s], TC_EPI_WARPS * 32);
+        }
+        for (int s = 0; s < META_STAGES; ++s) {
+            umma::mbar_init(&mfull[s], 32);
+            umma::mbar_init(&mempty[s], TC_EPI_WARPS * 32);
         }
         umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == TC_EPI_WARPS) umma::tmem_alloc(tmem_slot, 256);
+    if (warp == TC_MMA_WARP) umma::tmem_alloc(tmem_slot, 256);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -190,22 +292,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int64_t e0 = tile * TCE;
-            const int ne = (int)((a.n_edges - e0) < (int64_t)TCE ? (a.n_edges - e0) : (int64_t)TCE);
-            int* dsts = epi_dst + acc * TCE;
-            dsts[tid] = tid < ne ? a.dstv[e0 + tid] : -1;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int ms = it % META_STAGES;
+            const TileMeta* M = metas + ms;
+            umma::mbar_wait(&mfull[ms], (it / META_STAGES) & 1);
             umma::mbar_wait(&tfull[acc], aph);
             umma::tc_fence_after();
-            const int64_t e1 = e0 + ne;
-            int cur = dsts[0];
             float sum = 0.f;
-            auto flush = [&](int node, float v) {
-                const int64_t s0 = a.rowptr[node], s1 = a.rowptr[node + 1];
-                if (s0 >= e0 && s1 <= e1) a.agg[(int64_t)node * TCH + n] = v / (float)(s1 - s0);
-                else if (s0 < e0) a.part_head[tile * TCH + n] = v;
-                else a.part_tail[tile * TCH + n] = v;
-            };
 #pragma unroll 1
             for (int c0 = 0; c0 < TCE; c0 += 32) {
                 float v[32];
@@ -214,36 +306,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
                     umma::tc_fence_before();
                     umma::mbar_arrive(&tempty[acc]);
                 }
-                if (c0 < ne) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int e = c0 + i;
-                        if (e < ne) {
-                            const int d = dsts[e];
-                            if (d != cur) {
-                                flush(cur, sum);
-                                cur = d;
-                                sum = 0.f;
-                            }
-                            const float z = v[i] + bias;
-                            sum += z * sigmoid_tc<FAST>(z);
-                        }
+                for (int i = 0; i < 32; ++i) v[i] = swish_tc<FAST>(v[i] + bias);
+                const uint32_t em = M->endmask[c0 >> 5];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    sum += v[i];
+                    if (em & (1u << i)) {
+                        const int pos = c0 + i, kind = M->kind[pos];
+                        if (kind == 1) a.agg[(int64_t)M->dst[pos] * TCH + n] = sum * M->scale[pos];
+                        else if (kind == 2) a.part_head[tile * TCH + n] = sum;
+                        else a.part_tail[tile * TCH + n] = sum;
+                        sum = 0.f;
                     }
                 }
             }
-            flush(cur, sum);
+            umma::mbar_arrive(&mempty[ms]);
         }
-    } else if (warp == TC_EPI_WARPS) {
+    } else if (warp == TC_MMA_WARP) {
         // =========================== MMA issue ====================================================
-        if (lane == 0) {
-            // W2 image(s): one bulk async copy (TMA engine, no tensor map needed for a pre-swizzled image)
-            const uint32_t bytes = NSPLIT * TILE_BYTES;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(wbar)), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             umma::smem_u32(w_img)),
-                         "l"(a.w2img), "r"(bytes), "r"(umma::smem_u32(wbar))
-                         : "memory");
-        }
+        if (lane == 0) load_w2_image(w_img, a.w2img, NSPLIT * TILE_BYTES, wbar);
         umma::mbar_wait(wbar, 0);
         const uint32_t idesc = umma::idesc_bf16(128, 128, 0, 0);
         const uint32_t w_s = umma::smem_u32(w_img);
@@ -275,9 +357,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
             }
             __syncwarp();
         }
+    } else if (warp == TC_META_WARP) {
+        // =========================== segment metadata, META_STAGES tiles ahead =====================
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int ms = it % META_STAGES;
+            umma::mbar_wait(&mempty[ms], ((it / META_STAGES) & 1) ^ 1);
+            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane);
+            umma::mbar_arrive(&mfull[ms]);
+        }
     } else {
         // =========================== producers: 16 consecutive edge rows per warp ===================
-        const int pw = warp - TC_EPI_WARPS - 1;
+        const int pw = warp - TC_PROD_WARP0;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
@@ -290,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == TC_EPI_WARPS) umma::tmem_dealloc(tmem, 256);
+    if (warp == TC_MMA_WARP) umma::tmem_dealloc(tmem, 256);
 }
 
 size_t edge_fwd_tc_workspace(int64_t n_edges) {
@@ -337,7 +428,9 @@ int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, co
 //   epi1  dz2[e][n] = dagg[dst_e][n]/deg * Swish'(D1 + b2[n])  -> DZt tile [n][e] (bf16 hi[/lo]);  db2[n] += dz2
 //   MMA2  D2[k][e] = sum_n W2[n][k] dz2[e][n]         A = W2 image (MN-major), B = DZt tile (MN-major)
 //   MMA3  D3[n][k] += sum_e dz2[e][n] h1[e][k]        A = DZt tile (K-major),  B = h1 tile (MN-major)
-//         D3 = dW2 stays in TMEM for the whole persistent CTA (one [128][128] partial per CTA at the end)
+//         D3 = dW2 accumulates in TMEM; two D3 buffers alternate every D3_GROUP tiles and are drained into
+//         the CTA's fp32 partial with round-to-nearest adds (the tensor core's own accumulation truncates,
+//         which would bias a sum over thousands of K-steps past the 1e-5 contract)
 //   epi2  dz1[e][k] = D2 * Swish'(P[dst_e][k] + Q[src_e][k])  -> global dz1 (by-source reduction later)
 //         and the segmented SUM over the dst-sorted positions -> dP[dst]      (no atomics)
 // ==================================================================================================
@@ -359,25 +452,32 @@ struct EdgeBwdTcArgs {
     float* db2_partial;      // [grid][128]
 };
 
+constexpr int BWD_NPRE = 8;      // segments per tile whose dagg / P rows are prefetched into shared memory
 template <int NSPLIT>
 constexpr int edge_bwd_tc_stages() { return NSPLIT == 1 ? 2 : 1; }
 template <int NSPLIT>
+constexpr int edge_bwd_meta_stages() { return NSPLIT == 1 ? 4 : 2; }
+template <int NSPLIT>
 constexpr size_t edge_bwd_tc_smem() {
-    return 1024 + (size_t)NSPLIT * TILE_BYTES * (2 + edge_bwd_tc_stages<NSPLIT>()) + 4 * TCE * sizeof(int) + 256;
+    return 1024 + (size_t)NSPLIT * TILE_BYTES * (2 + edge_bwd_tc_stages<NSPLIT>()) +
+           edge_bwd_meta_stages<NSPLIT>() * sizeof(TileMeta) + 2 * BWD_NPRE * TCH * sizeof(float) + 256;
 }
 
 template <int NSPLIT, bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const EdgeBwdTcArgs a) {
     constexpr int STAGES = edge_bwd_tc_stages<NSPLIT>();
+    constexpr int MSTAGES = edge_bwd_meta_stages<NSPLIT>();
+    constexpr int D3_GROUP = FAST ? (1 << 30) : 4;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = umma::smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     unsigned char* w_img = base;
     unsigned char* h_img = w_img + (size_t)NSPLIT * TILE_BYTES;                 // [stage][split]
     unsigned char* dz_img = h_img + (size_t)STAGES * NSPLIT * TILE_BYTES;       // [split]   DZt[n][e]
-    int* epi_dst = reinterpret_cast<int*>(dz_img + (size_t)NSPLIT * TILE_BYTES);   // [2][128]
-    int* epi_src = epi_dst + 2 * TCE;                                              // [2][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_src + 2 * TCE);
+    TileMeta* metas = reinterpret_cast<TileMeta*>(dz_img + (size_t)NSPLIT * TILE_BYTES);
+    float* gtab = reinterpret_cast<float*>(metas + MSTAGES);       // [BWD_NPRE][128]  dagg[segdst]/deg
+    float* ptab = gtab + BWD_NPRE * TCH;                           // [BWD_NPRE][128]  P[segdst]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ptab + BWD_NPRE * TCH);
     uint64_t* full = bars;               // [2] producers -> MMA (h1 tile ready)
     uint64_t* empty = bars + 2;          // [2] MMA3 done -> producers
     uint64_t* d1_full = bars + 4;        // MMA1 done -> epilogue
@@ -385,9 +485,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
     uint64_t* dz_empty = bars + 6;       // MMA2+MMA3 done reading DZt -> epilogue
     uint64_t* d2_full = bars + 7;        // MMA2 done -> epilogue
     uint64_t* d2_empty = bars + 8;       // epilogue drained D2 -> MMA
-    uint64_t* d3_full = bars + 9;        // all MMA3 done -> epilogue (final dW2 read-out)
-    uint64_t* wbar = bars + 10;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* d3_full = bars + 9;        // [2] a D3 group is complete -> epilogue
+    uint64_t* d3_empty = bars + 11;      // [2] epilogue drained D3 buffer -> MMA
+    uint64_t* mfull = bars + 13;         // [MSTAGES]
+    uint64_t* mempty = bars + 13 + MSTAGES;
+    uint64_t* wbar = bars + 13 + 2 * MSTAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * MSTAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = ceil_div<int64_t>(a.n_edges, TCE);
@@ -396,85 +499,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         for (int s = 0; s < 2; ++s) {
             umma::mbar_init(&full[s], TC_PROD_WARPS * 32);
             umma::mbar_init(&empty[s], 1);
+            umma::mbar_init(&d3_full[s], 1);
+            umma::mbar_init(&d3_empty[s], TC_EPI_WARPS * 32);
+        }
+        for (int s = 0; s < MSTAGES; ++s) {
+            umma::mbar_init(&mfull[s], 32);
+            umma::mbar_init(&mempty[s], TC_EPI_WARPS * 32);
         }
         umma::mbar_init(d1_full, 1);
         umma::mbar_init(dz_full, TC_EPI_WARPS * 32);
         umma::mbar_init(dz_empty, 1);
         umma::mbar_init(d2_full, 1);
         umma::mbar_init(d2_empty, TC_EPI_WARPS * 32);
-        umma::mbar_init(d3_full, 1);
         umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == TC_EPI_WARPS) umma::tmem_alloc(tmem_slot, 512);
+    if (warp == TC_MMA_WARP) umma::tmem_alloc(tmem_slot, 512);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;
+    const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;   // D3 buffers at +256, +384
 
     if (warp < TC_EPI_WARPS) {
         // =========================== epilogue: thread = channel ===================================
         const int n = tid;
         const float bias = a.b2[n];
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        float* dw_out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH;
         float db = 0.f;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t ph = it & 1;
             const int64_t e0 = tile * TCE;
             const int ne = (int)((a.n_edges - e0) < (int64_t)TCE ? (a.n_edges - e0) : (int64_t)TCE);
-            const int64_t e1 = e0 + ne;
-            int* dsts = epi_dst + (it & 1) * TCE;
-            int* srcs = epi_src + (it & 1) * TCE;
-            dsts[tid] = tid < ne ? a.dstv[e0 + tid] : -1;
-            srcs[tid] = tid < ne ? a.srcv[e0 + tid] : -1;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int ms = it % MSTAGES;
+            const TileMeta* M = metas + ms;
+            umma::mbar_wait(&mfull[ms], (it / MSTAGES) & 1);
+            const int nseg = M->nseg;
+            // prefetch the per-segment rows this thread needs (independent loads; own column of the tables)
+            {
+                const int npre = nseg < BWD_NPRE ? nseg : BWD_NPRE;
+                for (int j = 0; j < npre; ++j) {
+                    const int d = M->segdst[j];
+                    gtab[j * TCH + n] = a.dagg[(int64_t)d * a.ld_dagg + n] * M->seginv[j];
+                    ptab[j * TCH + n] = a.pq[(int64_t)d * (2 * TCH) + n];
+                }
+            }
+            auto seg_g = [&](int j) -> float {
+                if (j >= nseg) return 0.f;
+                if (j < BWD_NPRE) return gtab[j * TCH + n];
+                return a.dagg[(int64_t)M->segdst[j] * a.ld_dagg + n] * M->seginv[j];
+            };
+            auto seg_p = [&](int j) -> float {
+                if (j >= nseg) return 0.f;
+                if (j < BWD_NPRE) return ptab[j * TCH + n];
+                return a.pq[(int64_t)M->segdst[j] * (2 * TCH) + n];
+            };
             // ---- epi1: dz2 = dagg[dst]/deg * Swish'(z2) -> DZt (rows = channel, cols = edge) ----
             umma::mbar_wait(d1_full, ph);
             umma::mbar_wait(dz_empty, ph ^ 1);
             umma::tc_fence_after();
             {
-                int cur = -1;
-                float g = 0.f;
+                int j = 0;
+                float g = seg_g(0);
 #pragma unroll 1
                 for (int c0 = 0; c0 < TCE; c0 += 32) {
                     float v[32];
                     umma::tmem_ld32(tm_d1 + lane_base + c0, v);
 #pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = swish_grad_tc<FAST>(v[i] + bias);
+                    const uint32_t em = M->endmask[c0 >> 5];
+#pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const int e = c0 + i;
-                        const int d = dsts[e];
-                        float o = 0.f;
-                        if (d >= 0) {
-                            if (d != cur) {
-                                cur = d;
-                                const float deg = (float)(a.rowptr[d + 1] - a.rowptr[d]);
-                                g = a.dagg[(int64_t)d * a.ld_dagg + n] / deg;
-                            }
-                            const float z = v[i] + bias;
-                            const float sg = sigmoid_tc<FAST>(z);
-                            o = g * (sg * fmaf(z, 1.0f - sg, 1.0f));
-                        }
-                        v[i] = o;
-                        db += o;
+                        v[i] *= g;
+                        db += v[i];
+                        if (em & (1u << i)) g = seg_g(++j);
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint32_t off = umma::tile_off(128, n, c0 + 8 * j);
+                    for (int q8 = 0; q8 < 4; ++q8) {
+                        const uint32_t off = umma::tile_off(128, n, c0 + 8 * q8);
+                        uint4 hi, lo;
                         if (NSPLIT == 1) {
-                            uint4 w;
-                            w.x = umma::pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-                            w.y = umma::pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                            w.z = umma::pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                            w.w = umma::pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-                            *reinterpret_cast<uint4*>(dz_img + off) = w;
+                            hi.x = umma::pack_bf16(v[8 * q8 + 0], v[8 * q8 + 1]);
+                            hi.y = umma::pack_bf16(v[8 * q8 + 2], v[8 * q8 + 3]);
+                            hi.z = umma::pack_bf16(v[8 * q8 + 4], v[8 * q8 + 5]);
+                            hi.w = umma::pack_bf16(v[8 * q8 + 6], v[8 * q8 + 7]);
+                            *reinterpret_cast<uint4*>(dz_img + off) = hi;
                         } else {
-                            __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) umma::split_bf16(v[8 * j + q], hi[q], lo[q]);
-                            *reinterpret_cast<uint4*>(dz_img + off) = *reinterpret_cast<uint4*>(hi);
-                            *reinterpret_cast<uint4*>(dz_img + TILE_BYTES + off) = *reinterpret_cast<uint4*>(lo);
+                            split2_bf16(v[8 * q8 + 0], v[8 * q8 + 1], hi.x, lo.x);
+                            split2_bf16(v[8 * q8 + 2], v[8 * q8 + 3], hi.y, lo.y);
+                            split2_bf16(v[8 * q8 + 4], v[8 * q8 + 5], hi.z, lo.z);
+                            split2_bf16(v[8 * q8 + 6], v[8 * q8 + 7], hi.w, lo.w);
+                            *reinterpret_cast<uint4*>(dz_img + off) = hi;
+                            *reinterpret_cast<uint4*>(dz_img + TILE_BYTES + off) = lo;
                         }
                     }
                 }
@@ -486,81 +604,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             umma::mbar_wait(d2_full, ph);
             umma::tc_fence_after();
             {
-                int cur = dsts[0];
+                int j = 0;
+                float pk = seg_p(0);
                 float sum = 0.f;
-                float pk = a.pq[(int64_t)cur * (2 * TCH) + n];
-                auto flush = [&](int node, float v) {
-                    const int64_t s0 = a.rowptr[node], s1 = a.rowptr[node + 1];
-                    if (s0 >= e0 && s1 <= e1) a.dpq[(int64_t)node * (2 * TCH) + n] = v;
-                    else if (s0 < e0) a.part_head[tile * TCH + n] = v;
-                    else a.part_tail[tile * TCH + n] = v;
-                };
 #pragma unroll 1
-                for (int c0 = 0; c0 < TCE; c0 += 32) {
-                    float v[32];
-                    umma::tmem_ld32(tm_d2 + lane_base + c0, v);
-                    if (c0 + 32 >= TCE) {
+                for (int c0 = 0; c0 < TCE; c0 += 16) {
+                    float v[16];
+                    umma::tmem_ld16(tm_d2 + lane_base + c0, v);
+                    if (c0 + 16 >= TCE) {
                         umma::tc_fence_before();
                         umma::mbar_arrive(d2_empty);
                     }
-                    if (c0 < ne) {
-                        float q[32];
+                    if (c0 >= ne) continue;
+                    float q[16];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int sidx = srcs[c0 + i];
-                            q[i] = sidx >= 0 ? a.pq[(int64_t)sidx * (2 * TCH) + TCH + n] : 0.f;
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        const int sidx = M->src[c0 + i];
+                        q[i] = a.pq[(int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + n];
+                    }
+                    const uint32_t em = (M->endmask[c0 >> 5] >> (c0 & 16)) & 0xffffu;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int e = c0 + i;
-                            if (e < ne) {
-                                const int d = dsts[e];
-                                if (d != cur) {
-                                    flush(cur, sum);
-                                    cur = d;
-                                    sum = 0.f;
-                                    pk = a.pq[(int64_t)d * (2 * TCH) + n];
-                                }
-                                const float z = pk + q[i];
-                                const float sg = sigmoid_tc<FAST>(z);
-                                const float o = v[i] * (sg * fmaf(z, 1.0f - sg, 1.0f));
-                                a.dz1[(e0 + e) * TCH + n] = o;
-                                sum += o;
-                            }
+                    for (int i = 0; i < 16; ++i) {
+                        q[i] += pk;
+                        if (em & (1u << i)) pk = seg_p(++j);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] *= swish_grad_tc<FAST>(q[i]);
+                    float* dzrow = a.dz1 + (e0 + c0) * TCH + n;
+                    const int nvalid = ne - c0;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (i < nvalid) dzrow[(int64_t)i * TCH] = v[i];
+                        sum += v[i];
+                        if (em & (1u << i)) {
+                            const int pos = c0 + i, kind = M->kind[pos];
+                            if (kind == 1) a.dpq[(int64_t)M->dst[pos] * (2 * TCH) + n] = sum;
+                            else if (kind == 2) a.part_head[tile * TCH + n] = sum;
+                            else a.part_tail[tile * TCH + n] = sum;
+                            sum = 0.f;
                         }
                     }
                 }
-                flush(cur, sum);
             }
-        }
-        // ---- final: dW2 partial of this CTA (D3) and db2 partial ----
-        if (it > 0) {
-            umma::mbar_wait(d3_full, 0);
-            umma::tc_fence_after();
-            float* out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH;
+            umma::mbar_arrive(&mempty[ms]);
+            // ---- drain a finished D3 group into this CTA's fp32 partial (round-to-nearest adds) ----
+            const bool last = tile + gridDim.x >= n_tiles;
+            if ((it % D3_GROUP) == D3_GROUP - 1 || last) {
+                const int grp = it / D3_GROUP, buf = grp & 1;
+                umma::mbar_wait(&d3_full[buf], (grp >> 1) & 1);
+                umma::tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < TCH; c0 += 32) {
-                float v[32];
-                umma::tmem_ld32(tm_d3 + lane_base + c0, v);
+                for (int c0 = 0; c0 < TCH; c0 += 32) {
+                    float v[32];
+                    umma::tmem_ld32(tm_d3 + (uint32_t)(buf * 128) + lane_base + c0, v);
+                    if (c0 + 32 >= TCH) {
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(&d3_empty[buf]);
+                    }
+                    float4* o = reinterpret_cast<float4*>(dw_out + c0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(out + c0 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        if (grp > 0) {
+                            const float4 old = o[q4];
+                            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                        }
+                        o[q4] = w;
+                    }
+                }
             }
-        } else {
-            float* out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH;
-            for (int c = 0; c < TCH; ++c) out[c] = 0.f;
         }
         a.db2_partial[(int64_t)blockIdx.x * TCH + n] = db;
-    } else if (warp == TC_EPI_WARPS) {
+    } else if (warp == TC_MMA_WARP) {
         // =========================== MMA issue ====================================================
-        if (lane == 0) {
-            const uint32_t bytes = NSPLIT * TILE_BYTES;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(wbar)), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             umma::smem_u32(w_img)),
-                         "l"(a.w2img), "r"(bytes), "r"(umma::smem_u32(wbar))
-                         : "memory");
-        }
+        if (lane == 0) load_w2_image(w_img, a.w2img, NSPLIT * TILE_BYTES, wbar);
         umma::mbar_wait(wbar, 0);
         const uint32_t id_kk = umma::idesc_bf16(128, 128, 0, 0);     // A K-major,  B K-major   (MMA1)
         const uint32_t id_mm = umma::idesc_bf16(128, 128, 1, 1);     // A MN-major, B MN-major  (MMA2)
@@ -572,6 +689,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             const uint32_t sph = (it / STAGES) & 1;
             const uint32_t ph = it & 1;
             const uint32_t h_s = umma::smem_u32(h_img + (size_t)s * NSPLIT * TILE_BYTES);
+            const int grp = it / D3_GROUP, buf = grp & 1;
+            const bool first_in_group = (it % D3_GROUP) == 0;
+            const bool last = tile + gridDim.x >= n_tiles;
             umma::mbar_wait(&full[s], sph);
             umma::tc_fence_after();
             if (lane == 0) {
@@ -591,6 +711,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             __syncwarp();
             umma::mbar_wait(dz_full, ph);
             umma::mbar_wait(d2_empty, ph ^ 1);
+            if (first_in_group) umma::mbar_wait(&d3_empty[buf], ((grp >> 1) & 1) ^ 1);
             umma::tc_fence_after();
             if (lane == 0) {
                 uint32_t accum = 0;
@@ -605,27 +726,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                     }
                 }
                 umma::mma_commit(d2_full);
-                accum = it > 0 ? 1u : 0u;
+                accum = first_in_group ? 0u : 1u;
 #pragma unroll
                 for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
                     const int za = term == 2 ? 1 : 0, hb = term == 1 ? 1 : 0;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {     // K = e
-                        umma::mma_bf16(tm_d3, umma::desc_kmajor(dz_s + za * TILE_BYTES, k), umma::desc_mnmajor(h_s + hb * TILE_BYTES, k),
-                                       id_km, accum);
+                        umma::mma_bf16(tm_d3 + (uint32_t)(buf * 128), umma::desc_kmajor(dz_s + za * TILE_BYTES, k),
+                                       umma::desc_mnmajor(h_s + hb * TILE_BYTES, k), id_km, accum);
                         accum = 1;
                     }
                 }
                 umma::mma_commit(&empty[s]);
                 umma::mma_commit(dz_empty);
+                if ((it % D3_GROUP) == D3_GROUP - 1 || last) umma::mma_commit(&d3_full[buf]);
             }
             __syncwarp();
         }
-        if (lane == 0 && it > 0) umma::mma_commit(d3_full);
-        __syncwarp();
+    } else if (warp == TC_META_WARP) {
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int ms = it % MSTAGES;
+            umma::mbar_wait(&mempty[ms], ((it / MSTAGES) & 1) ^ 1);
+            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane);
+            umma::mbar_arrive(&mfull[ms]);
+        }
     } else {
         // =========================== producers ====================================================
-        const int pw = warp - TC_EPI_WARPS - 1;
+        const int pw = warp - TC_PROD_WARP0;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % STAGES;
@@ -638,7 +766,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == TC_EPI_WARPS) umma::tmem_dealloc(tmem, 512);
+    if (warp == TC_MMA_WARP) umma::tmem_dealloc(tmem, 512);
 }
 
 int edge_bwd_tc_grid(int64_t n_edges) {
