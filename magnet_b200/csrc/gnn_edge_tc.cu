@@ -110,9 +110,10 @@ segment_fixup_tc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __res
 struct TileMeta {
     int dst[TCE];          // destination node of every position (-1 past the end of the edge list)
     int src[TCE];
-    float scale[TCE];      // at segment-END positions: 1 / in-degree of the destination
-    int kind[TCE];         // at segment-END positions: 1 = segment lies inside the tile, 2 = began in an earlier
-                           // tile (head partial), 3 = continues into a later tile (tail partial)
+    float scale[TCE];      // at segment-END positions: factor applied to the segment sum before it is stored
+                           // (1/in-degree for a mean over a segment that lies inside the tile, else 1)
+    float* out[TCE];       // at segment-END positions: row (channel 0) the segment sum goes to — the destination's
+                           // output row, or this tile's head / tail partial row when the segment crosses a tile boundary
     int segdst[TCE];       // the tile's segments in order: destination node, 1 / in-degree
     float seginv[TCE];
     uint32_t endmask[4];   // bit p of the 128-bit mask: position p is the last of its segment within the tile
@@ -122,7 +123,8 @@ struct TileMeta {
 
 // one warp; positions p = j*32 + lane
 __device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dstv,
-                                                const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int lane) {
+                                                const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int lane,
+                                                float* out_base, int ld_out, bool mean, float* part_head, float* part_tail) {
     const int64_t e0 = tile * TCE;
     const int64_t e1 = (e0 + TCE < n_edges) ? e0 + TCE : n_edges;
     int base = 0;
@@ -145,8 +147,10 @@ __device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __re
         const float inv = 1.0f / (float)(s1 - s0);
         M->dst[p] = d;
         M->src[p] = sidx;
-        M->scale[p] = inv;
-        M->kind[p] = !is_end ? 0 : ((int64_t)s0 >= e0 && (int64_t)s1 <= e1) ? 1 : ((int64_t)s0 < e0 ? 2 : 3);
+        const bool inside = (int64_t)s0 >= e0 && (int64_t)s1 <= e1;
+        M->scale[p] = (inside && mean) ? inv : 1.0f;
+        if (is_end)
+            M->out[p] = inside ? out_base + (int64_t)d * ld_out : ((int64_t)s0 < e0 ? part_head : part_tail) + tile * TCH;
         const uint32_t em = __ballot_sync(0xffffffffu, is_end);
         const uint32_t sm = __ballot_sync(0xffffffffu, is_start);
         if (lane == 0) M->endmask[j] = em;
@@ -310,14 +314,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
                 for (int i = 0; i < 32; ++i) v[i] = swish_tc<FAST>(v[i] + bias);
                 const uint32_t em = M->endmask[c0 >> 5];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    sum += v[i];
-                    if (em & (1u << i)) {
-                        const int pos = c0 + i, kind = M->kind[pos];
-                        if (kind == 1) a.agg[(int64_t)M->dst[pos] * TCH + n] = sum * M->scale[pos];
-                        else if (kind == 2) a.part_head[tile * TCH + n] = sum;
-                        else a.part_tail[tile * TCH + n] = sum;
-                        sum = 0.f;
+                for (int qd = 0; qd < 4; ++qd) {
+                    const uint32_t eq = (em >> (8 * qd)) & 0xffu;
+                    const float* w = v + 8 * qd;
+                    if (eq == 0) {      // no segment ends among these 8 positions (the common case)
+                        sum += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            sum += w[i];
+                            if (eq & (1u << i)) {
+                                const int pos = c0 + 8 * qd + i;
+                                M->out[pos][n] = sum * M->scale[pos];
+                                sum = 0.f;
+                            }
+                        }
                     }
                 }
             }
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ms = it % META_STAGES;
             umma::mbar_wait(&mempty[ms], ((it / META_STAGES) & 1) ^ 1);
-            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane);
+            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.agg, TCH, true, a.part_head, a.part_tail);
             umma::mbar_arrive(&mfull[ms]);
         }
     } else {
@@ -539,11 +550,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             const int nseg = M->nseg;
             // prefetch the per-segment rows this thread needs (independent loads; own column of the tables)
             {
-                const int npre = nseg < BWD_NPRE ? nseg : BWD_NPRE;
-                for (int j = 0; j < npre; ++j) {
-                    const int d = M->segdst[j];
-                    gtab[j * TCH + n] = a.dagg[(int64_t)d * a.ld_dagg + n] * M->seginv[j];
-                    ptab[j * TCH + n] = a.pq[(int64_t)d * (2 * TCH) + n];
+                float gv[BWD_NPRE], pv[BWD_NPRE];
+#pragma unroll
+                for (int j = 0; j < BWD_NPRE; ++j) {          // all loads issued before the first use
+                    const int jj = j < nseg ? j : nseg - 1;
+                    const int d = M->segdst[jj];
+                    gv[j] = a.dagg[(int64_t)d * a.ld_dagg + n] * M->seginv[jj];
+                    pv[j] = a.pq[(int64_t)d * (2 * TCH) + n];
+                }
+#pragma unroll
+                for (int j = 0; j < BWD_NPRE; ++j) {
+                    gtab[j * TCH + n] = gv[j];
+                    ptab[j * TCH + n] = pv[j];
                 }
             }
             auto seg_g = [&](int j) -> float {
@@ -571,10 +589,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                     for (int i = 0; i < 32; ++i) v[i] = swish_grad_tc<FAST>(v[i] + bias);
                     const uint32_t em = M->endmask[c0 >> 5];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        v[i] *= g;
-                        db += v[i];
-                        if (em & (1u << i)) g = seg_g(++j);
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const uint32_t eq = (em >> (8 * qd)) & 0xffu;
+                        float* w = v + 8 * qd;
+                        if (eq == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] *= g;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                w[i] *= g;
+                                if (eq & (1u << i)) g = seg_g(++j);
+                            }
+                        }
+                        db += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
                     }
 #pragma unroll
                     for (int q8 = 0; q8 < 4; ++q8) {
@@ -601,49 +629,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             umma::tc_fence_before();
             umma::mbar_arrive(dz_full);
             // ---- epi2: dz1 = dh1 * Swish'(z1) -> global + segmented sum by destination -> dP ----
-            umma::mbar_wait(d2_full, ph);
-            umma::tc_fence_after();
             {
                 int j = 0;
                 float pk = seg_p(0);
                 float sum = 0.f;
-#pragma unroll 1
-                for (int c0 = 0; c0 < TCE; c0 += 16) {
+                const bool full_tile = ne == TCE;
+                auto load_q = [&](float (&q)[16], int c0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int sidx = M->src[c0 + i];
+                        q[i] = a.pq[(int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + n];
+                    }
+                };
+                auto process = [&](float (&q)[16], int c0) {
                     float v[16];
                     umma::tmem_ld16(tm_d2 + lane_base + c0, v);
                     if (c0 + 16 >= TCE) {
                         umma::tc_fence_before();
                         umma::mbar_arrive(d2_empty);
                     }
-                    if (c0 >= ne) continue;
-                    float q[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int sidx = M->src[c0 + i];
-                        q[i] = a.pq[(int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + n];
-                    }
+                    if (c0 >= ne) return;
                     const uint32_t em = (M->endmask[c0 >> 5] >> (c0 & 16)) & 0xffffu;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        q[i] += pk;
-                        if (em & (1u << i)) pk = seg_p(++j);
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        const uint32_t eq = (em >> (8 * h8)) & 0xffu;
+                        float* w = q + 8 * h8;
+                        if (eq == 0) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w[i] += pk;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                w[i] += pk;
+                                if (eq & (1u << i)) pk = seg_p(++j);
+                            }
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] *= swish_grad_tc<FAST>(q[i]);
                     float* dzrow = a.dz1 + (e0 + c0) * TCH + n;
-                    const int nvalid = ne - c0;
+                    if (full_tile) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (i < nvalid) dzrow[(int64_t)i * TCH] = v[i];
-                        sum += v[i];
-                        if (em & (1u << i)) {
-                            const int pos = c0 + i, kind = M->kind[pos];
-                            if (kind == 1) a.dpq[(int64_t)M->dst[pos] * (2 * TCH) + n] = sum;
-                            else if (kind == 2) a.part_head[tile * TCH + n] = sum;
-                            else a.part_tail[tile * TCH + n] = sum;
-                            sum = 0.f;
+                        for (int i = 0; i < 16; ++i) dzrow[(int64_t)i * TCH] = v[i];
+                    } else {
+                        const int nvalid = ne - c0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < nvalid) dzrow[(int64_t)i * TCH] = v[i];
+                    }
+#pragma unroll
+                    for (int h8 = 0; h8 < 2; ++h8) {
+                        const uint32_t eq = (em >> (8 * h8)) & 0xffu;
+                        const float* w = v + 8 * h8;
+                        if (eq == 0) {
+                            sum += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                sum += w[i];
+                                if (eq & (1u << i)) {
+                                    const int pos = c0 + 8 * h8 + i;
+                                    M->out[pos][n] = sum;
+                                    sum = 0.f;
+                                }
+                            }
                         }
                     }
+                };
+                // the Q re-gather of the next 16 positions is in flight while the current 16 are processed;
+                // the first batch is issued before waiting for MMA2
+                float qa[16], qb[16];
+                load_q(qa, 0);
+                umma::mbar_wait(d2_full, ph);
+                umma::tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < TCE; c0 += 32) {
+                    load_q(qb, c0 + 16);
+                    process(qa, c0);
+                    if (c0 + 32 < TCE) load_q(qa, c0 + 32);
+                    process(qb, c0 + 16);
                 }
             }
             umma::mbar_arrive(&mempty[ms]);
@@ -748,7 +812,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ms = it % MSTAGES;
             umma::mbar_wait(&mempty[ms], ((it / MSTAGES) & 1) ^ 1);
-            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane);
+            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.dpq, 2 * TCH, false, a.part_head, a.part_tail);
             umma::mbar_arrive(&mfull[ms]);
         }
     } else {
