@@ -137,6 +137,43 @@ int mgb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
                       float* dx, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MAgNet[GNN] InteractionNetwork glue (models/magnet_gnn.py:70-90).  The first Linear of edge_fn is
+ * factorised, W [x_i, x_j, e] = P[i] + Q[j] + R[e] with i = edge_index[1] (the aggregation endpoint),
+ * j = edge_index[0]; per-edge tensors are [E,128] in the caller's COO order.
+ *   mgb_edge_combine_fwd:  out[e] = act(p[i_e] + q[j_e] + r[e]), act 0 none / 1 ReLU; edge_index int64 [2,E].
+ *   mgb_relu_mask:         dz = dout * (out > 0).
+ *   mgb_segment_sum_rows:  out[n] = scale * sum_{q in [rowptr[n], rowptr[n+1])} rows[idx ? idx[q] : q]; scale = 1/max(count,1)
+ *                          when mean != 0 (scatter(reduce='mean'), aggr='mean' :54), fixed order, no atomics.
+ *   mgb_gather_rows:       out[e] = rows[index[e]] * (rowptr ? 1/max(count(index[e]),1) : 1)  (backward of the mean).
+ * ------------------------------------------------------------------------------------------- */
+int mgb_edge_combine_fwd(const float* p, const float* q, const float* r, const int64_t* edge_index, int64_t n_edges, int act,
+                         float* out, void* stream);
+int mgb_relu_mask(const float* dout, const float* out, int64_t n, float* dz, void* stream);
+int mgb_segment_sum_rows(const float* rows, int cols, const int32_t* rowptr, const int32_t* idx, int64_t n_nodes, int mean,
+                         float* out, int ld_out, void* stream);
+int mgb_gather_rows(const float* rows, const int64_t* index, const int32_t* rowptr, int64_t n_edges, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * INR decoder.  Replaces the body of MAgNetGNN.continuous_decoder (models/magnet_gnn.py:254-280) given the
+ * neighbour table of mgb_knn (:247).  a [B*L,128] = lr_encoded proj_head.weight[:, :128]^T + proj_head.bias
+ * (the latent part of proj_head, factorised per low-resolution node); xlr [B,T,L]; lr_coords [B*L,d];
+ * hr_coords [Q,d]; t [B,ldt] (first T columns used); wsmall = proj_head.weight + 128 with row stride ldw
+ * (columns: input value, relative coordinates, time); idx [Q,k] global low-res row ids, ascending distance —
+ * only neighbours 0 and 1 enter the blend.  mode: 0 'area', 1 'knn', 2 'sph'.
+ *   fwd: z [Q,T,128].
+ *   bwd: g [2Q,128] and sx [2Q,T] (per-neighbour contributions to d a / d xlr, to be summed per low-res node with
+ *        mgb_segment_sum_rows), dwsmall [128, ldw-strided, d+2 columns] (+)= .
+ * ------------------------------------------------------------------------------------------- */
+int mgb_inr_decode_fwd(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
+                       const float* wsmall, int ldw, const int64_t* idx, int k, int64_t n_query, int nq_per_sample, int L, int T,
+                       int d, int mode, float* z, void* stream);
+size_t mgb_inr_decode_bwd_workspace(int64_t n_query);
+int mgb_inr_decode_bwd(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
+                       const float* wsmall, int ldw, const int64_t* idx, int k, int64_t n_query, int nq_per_sample, int L, int T,
+                       int d, int mode, const float* dz, float* g, float* sx, float* dwsmall, int accumulate, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* InstanceNorm alone (PyG InstanceNorm, models/mpnn_2d.py:63,70) — exposed for tests. */
 size_t mgb_instance_norm_workspace(int n_graphs, int max_nodes_per_graph);
 int mgb_instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes_per_graph, float* y,

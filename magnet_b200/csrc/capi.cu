@@ -164,6 +164,44 @@ int mgb_instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int
     return instance_norm_fwd(x, gptr, n_graphs, max_nodes_per_graph, y, rstd, workspace, workspace_bytes, STREAM(stream));
 }
 
+int mgb_edge_combine_fwd(const float* p, const float* q, const float* r, const int64_t* edge_index, int64_t n_edges, int act,
+                         float* out, void* stream) {
+    return edge_combine_fwd(p, q, r, edge_index, n_edges, act, out, STREAM(stream));
+}
+int mgb_relu_mask(const float* dout, const float* out, int64_t n, float* dz, void* stream) {
+    return relu_mask(dout, out, n, dz, STREAM(stream));
+}
+int mgb_segment_sum_rows(const float* rows, int cols, const int32_t* rowptr, const int32_t* idx, int64_t n_nodes, int mean,
+                         float* out, int ld_out, void* stream) {
+    return segment_sum_rows(rows, cols, rowptr, idx, n_nodes, mean, out, ld_out, STREAM(stream));
+}
+int mgb_gather_rows(const float* rows, const int64_t* index, const int32_t* rowptr, int64_t n_edges, float* out, void* stream) {
+    return gather_rows(rows, index, rowptr, n_edges, out, STREAM(stream));
+}
+
+static InrArgs inr_args(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
+                        const float* wsmall, int ldw, const int64_t* idx, int k, int64_t n_query, int nq_per_sample, int L, int T,
+                        int d, int mode) {
+    InrArgs r;
+    r.A = a; r.xlr = xlr; r.lr_coords = lr_coords; r.hr_coords = hr_coords; r.t = t; r.ldt = ldt; r.wsmall = wsmall; r.ldw = ldw;
+    r.idx = idx; r.k = k; r.n_query = n_query; r.nq_per_sample = nq_per_sample; r.L = L; r.T = T; r.d = d; r.mode = mode;
+    return r;
+}
+int mgb_inr_decode_fwd(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
+                       const float* wsmall, int ldw, const int64_t* idx, int k, int64_t n_query, int nq_per_sample, int L, int T,
+                       int d, int mode, float* z, void* stream) {
+    return inr_decode_fwd(inr_args(a, xlr, lr_coords, hr_coords, t, ldt, wsmall, ldw, idx, k, n_query, nq_per_sample, L, T, d, mode),
+                          z, STREAM(stream));
+}
+size_t mgb_inr_decode_bwd_workspace(int64_t n_query) { return inr_decode_bwd_workspace(n_query); }
+int mgb_inr_decode_bwd(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
+                       const float* wsmall, int ldw, const int64_t* idx, int k, int64_t n_query, int nq_per_sample, int L, int T,
+                       int d, int mode, const float* dz, float* g, float* sx, float* dwsmall, int accumulate, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    return inr_decode_bwd(inr_args(a, xlr, lr_coords, hr_coords, t, ldt, wsmall, ldw, idx, k, n_query, nq_per_sample, L, T, d, mode),
+                          dz, g, sx, dwsmall, ldw, accumulate, workspace, workspace_bytes, STREAM(stream));
+}
+
 int mgb_umma_selftest(const float* a, const float* b, int a_mn_major, int b_mn_major, int lbo_mn, int sbo_mn, float* d,
                       void* stream) {
     return umma_selftest(a, b, a_mn_major, b_mn_major, lbo_mn, sbo_mn, d, STREAM(stream));

@@ -65,6 +65,32 @@ size_t inorm_workspace_bytes(int n_graphs, int max_nodes);
 int instance_norm_fwd(const float* x, const int64_t* gptr, int n_graphs, int max_nodes, float* y, float* rstd_out, void* ws,
                       size_t ws_bytes, cudaStream_t s);
 
+// interaction.cu
+int edge_combine_fwd(const float* P, const float* Q, const float* R, const int64_t* edge_index, int64_t n_edges, int act,
+                     float* out, cudaStream_t s);
+int relu_mask(const float* dout, const float* out, int64_t n, float* dz, cudaStream_t s);
+int segment_sum_rows(const float* rows, int cols, const int32_t* rowptr, const int32_t* idx, int64_t n_nodes, int mean,
+                     float* out, int ld_out, cudaStream_t s);
+int gather_rows(const float* rows, const int64_t* index, const int32_t* rowptr, int64_t n_edges, float* out, cudaStream_t s);
+struct InrArgs {
+    const float* A;          // [B*L][128]
+    const float* xlr;        // [B][T][L]
+    const float* lr_coords;  // [B*L][d]
+    const float* hr_coords;  // [Q][d]
+    const float* t;          // [B][ldt]  (first T entries of each row are used)
+    int ldt;
+    const float* wsmall;     // proj_head.weight + C, row stride ldw
+    int ldw;
+    const int64_t* idx;      // [Q][k]  nearest low-res nodes (global row ids), ascending distance
+    int k;
+    int64_t n_query;
+    int nq_per_sample, L, T, d, mode;    // mode 0 area, 1 knn, 2 sph
+};
+int inr_decode_fwd(const InrArgs& a, float* z, cudaStream_t s);
+size_t inr_decode_bwd_workspace(int64_t n_query);
+int inr_decode_bwd(const InrArgs& a, const float* dz, float* G, float* Sx, float* dwsmall, int ldw, int accumulate, void* ws,
+                   size_t ws_bytes, cudaStream_t s);
+
 // gnn_edge_tc.cu (tcgen05 edge kernels)
 int pack_w2_image(const float* W2, void* img, cudaStream_t s);
 size_t edge_fwd_tc_workspace(int64_t n_edges);

@@ -211,3 +211,156 @@ def instance_norm(x: torch.Tensor, seg: GraphSegments) -> torch.Tensor:
     _lib.check(L.mgb_instance_norm_fwd(_lib.ptr(x), _lib.ptr(seg.gptr), seg.n_graphs, seg.max_nodes, _lib.ptr(y),
                                        _lib.ptr(rstd), _lib.ptr(ws), ws.numel(), _lib.stream()), "instance_norm_fwd")
     return y
+
+
+# --------------------------------------------------------------------------------------------
+# InteractionNetwork glue (models/magnet_gnn.py:70-90) and the INR decoder (:224-283)
+# --------------------------------------------------------------------------------------------
+def _segment_sum(rows, cols, rowptr, idx, n_nodes, mean, out=None, ld_out=None):
+    L = _lib.lib()
+    if out is None:
+        out = _empty((n_nodes, cols), rows)
+        ld_out = cols
+    _lib.check(L.mgb_segment_sum_rows(_lib.ptr(rows), cols, _lib.ptr(rowptr), _lib.ptr(idx), n_nodes, int(mean),
+                                      _lib.ptr(out), ld_out, _lib.stream()), "segment_sum_rows")
+    return out
+
+
+class EdgeCombineFn(torch.autograd.Function):
+    """out[e] = act(p[edge_index[1][e]] + q[edge_index[0][e]] + r[e]) — the factorised first Linear of edge_fn
+    applied to cat([x_i, x_j, e_features]) (models/magnet_gnn.py:79-82)."""
+
+    @staticmethod
+    def forward(ctx, p, q, r, edge_index, plan: AggregationPlan, act: int):
+        _lib.require_cuda(p, q, r, edge_index)
+        L = _lib.lib()
+        p, q, r = _lib.f32c(p), _lib.f32c(q), _lib.f32c(r)
+        ei = edge_index.contiguous()
+        E = ei.shape[1]
+        out = _empty((E, 128), p)
+        _lib.check(L.mgb_edge_combine_fwd(_lib.ptr(p), _lib.ptr(q), _lib.ptr(r), _lib.ptr(ei), E, act, _lib.ptr(out),
+                                          _lib.stream()), "edge_combine_fwd")
+        ctx.save_for_backward(out)
+        ctx.plan, ctx.act, ctx.n = plan, act, p.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        (out,) = ctx.saved_tensors
+        plan = ctx.plan
+        dout = _lib.f32c(dout)
+        with torch.cuda.device(out.device):
+            if ctx.act:
+                dz = torch.empty_like(dout)
+                _lib.check(L.mgb_relu_mask(_lib.ptr(dout), _lib.ptr(out), dout.numel(), _lib.ptr(dz), _lib.stream()), "relu_mask")
+            else:
+                dz = dout
+            dp = _segment_sum(dz, 128, plan.rowptr, plan.perm, ctx.n, False)
+            dq = _segment_sum(dz, 128, plan.rowptr_t, plan.perm_src(), ctx.n, False)
+        return dp, dq, dz, None, None, None
+
+
+def edge_combine(p, q, r, edge_index, plan, act: str = "none"):
+    return EdgeCombineFn.apply(p, q, r, edge_index, plan, ACT[act])
+
+
+class ScatterMeanFn(torch.autograd.Function):
+    """scatter(m, edge_index[1], reduce='mean') through the destination-sorted plan (aggr='mean', models/magnet_gnn.py:54)."""
+
+    @staticmethod
+    def forward(ctx, m, edge_index, plan: AggregationPlan):
+        m = _lib.f32c(m)
+        ctx.plan = plan
+        ctx.save_for_backward(edge_index)
+        return _segment_sum(m, 128, plan.rowptr, plan.perm, plan.n_nodes, True)
+
+    @staticmethod
+    def backward(ctx, dagg):
+        L = _lib.lib()
+        (edge_index,) = ctx.saved_tensors
+        plan = ctx.plan
+        dagg = _lib.f32c(dagg)
+        E = plan.n_edges
+        dm = _empty((E, 128), dagg)
+        with torch.cuda.device(dagg.device):
+            ei1 = edge_index[1].contiguous()
+            _lib.check(L.mgb_gather_rows(_lib.ptr(dagg), _lib.ptr(ei1), _lib.ptr(plan.rowptr), E, _lib.ptr(dm), _lib.stream()),
+                       "gather_rows")
+        return dm, None, None
+
+
+def scatter_mean(m, edge_index, plan):
+    return ScatterMeanFn.apply(m, edge_index, plan)
+
+
+INTERP = {"area": 0, "knn": 1, "sph": 2}
+
+
+class InrBlendFn(torch.autograd.Function):
+    """z[q, i, :] = blend of the two nearest low-res nodes' proj_head outputs (models/magnet_gnn.py:254-279) given
+    a = lr_encoded Wp[:, :C]^T + b (per node).  Differentiable in a, xlr and proj_head.weight[:, C:]."""
+
+    @staticmethod
+    def forward(ctx, a, xlr, wp, lr_coords, hr_coords, t, idx, geom):
+        nq, L_, T, d, mode = geom
+        _lib.require_cuda(a, xlr, wp, lr_coords, hr_coords, t, idx)
+        L = _lib.lib()
+        a, xlr, lr_coords, hr_coords, t = (_lib.f32c(v) for v in (a, xlr, lr_coords, hr_coords, t))
+        wpc = _lib.f32c(wp.detach())
+        Q, k = idx.shape
+        z = _empty((Q, T, 128), a)
+        ldw = wpc.shape[1]
+        wsmall = ctypes_offset(wpc, 128)
+        _lib.check(L.mgb_inr_decode_fwd(_lib.ptr(a), _lib.ptr(xlr), _lib.ptr(lr_coords), _lib.ptr(hr_coords), _lib.ptr(t),
+                                        t.shape[1], wsmall, ldw, _lib.ptr(idx), k, Q, nq, L_, T, d, mode, _lib.ptr(z),
+                                        _lib.stream()), "inr_decode_fwd")
+        ctx.save_for_backward(a, xlr, wpc, lr_coords, hr_coords, t, idx)
+        ctx.geom = geom
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        from .graph import build_plan
+        L = _lib.lib()
+        a, xlr, wpc, lr_coords, hr_coords, t, idx = ctx.saved_tensors
+        nq, L_, T, d, mode = ctx.geom
+        dz = _lib.f32c(dz)
+        Q, k = idx.shape
+        n_lr = a.shape[0]
+        with torch.cuda.device(a.device):
+            g = _empty((2 * Q, 128), a)
+            sx = _empty((2 * Q, T), a)
+            dwp = torch.zeros_like(wpc)
+            ws = _lib.workspace(L.mgb_inr_decode_bwd_workspace(Q), a.device)
+            _lib.check(L.mgb_inr_decode_bwd(_lib.ptr(a), _lib.ptr(xlr), _lib.ptr(lr_coords), _lib.ptr(hr_coords), _lib.ptr(t),
+                                            t.shape[1], ctypes_offset(wpc, 128), wpc.shape[1], _lib.ptr(idx), k, Q, nq, L_, T, d,
+                                            mode, _lib.ptr(dz), _lib.ptr(g), _lib.ptr(sx), ctypes_offset(dwp, 128), 0,
+                                            _lib.ptr(ws), ws.numel(), _lib.stream()), "inr_decode_bwd")
+            # per-low-res-node sums of the two per-query contribution rows (deterministic, via a sorted plan)
+            sel = idx[:, :2].reshape(-1).contiguous()
+            plan = build_plan(torch.stack([sel, sel]), n_lr)
+            da = _segment_sum(g, 128, plan.rowptr, plan.perm, n_lr, False)
+            dx_flat = _segment_sum(sx, T, plan.rowptr, plan.perm, n_lr, False)      # [B*L, T]
+            B = xlr.shape[0]
+            dxlr = dx_flat.reshape(B, L_, T).permute(0, 2, 1).contiguous()
+        return da, dxlr, dwp, None, None, None, None, None
+
+
+def ctypes_offset(t: torch.Tensor, n_elems: int):
+    import ctypes
+    return ctypes.c_void_p(t.data_ptr() + n_elems * t.element_size())
+
+
+def inr_decode(xlr, lr_encoded, lr_coords, hr_coords, t, wp, bp, B, L_, nq, k, interpolation, *, idx=None):
+    """continuous_decoder (models/magnet_gnn.py:224-283): xlr [B,T,L], lr_encoded [B*L,C], lr_coords [B*L,d],
+    hr_coords [B*nq,d], t [B,>=T] -> z [B*nq, T, n_chan]."""
+    from . import graph as MG
+    T = xlr.shape[1]
+    d = lr_coords.shape[1]
+    if idx is None:
+        ptr_x = MG.uniform_ptr(B, L_, xlr.device)
+        ptr_y = MG.uniform_ptr(B, nq, xlr.device)
+        idx = MG.knn_indices(lr_coords, hr_coords, k, ptr_x, ptr_y)
+    a = linear_act(lr_encoded, wp[:, :128], bp, "none")
+    return InrBlendFn.apply(a, xlr, wp, lr_coords, hr_coords, t, idx, (nq, L_, T, d, INTERP[interpolation]))

@@ -130,6 +130,13 @@ class AggregationPlan:
     src: torch.Tensor        # int32 [E]           edge_index[0] in aggregation order
     rowptr_t: torch.Tensor   # int32 [n_nodes+1]   segments of edge_index[0]
     pos_t: torch.Tensor      # int32 [E]           aggregation-order positions grouped by edge_index[0]
+    _perm_src: Optional[torch.Tensor] = None
+
+    def perm_src(self) -> torch.Tensor:
+        """int32 [E]: COO edge ids grouped by edge_index[0] (segments rowptr_t) = perm[pos_t]."""
+        if self._perm_src is None:
+            self._perm_src = self.perm[self.pos_t.long()].contiguous()
+        return self._perm_src
 
 
 _PLAN_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()

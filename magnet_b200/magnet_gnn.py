@@ -48,8 +48,8 @@ class MLP(nn.Module):
         out = x
         for n, l in enumerate(lin):
             last = n + 1 == len(lin)
-            if n == 0 and first_preact is not None:
-                out = MF.relu(first_preact) if not last else first_preact
+            if n == 0 and first_preact is not None:      # already activated by the caller (fused into the gather)
+                out = first_preact
                 continue
             out = MF.linear_act(out, l.weight, l.bias, "none" if last else "relu")
         return out
@@ -95,9 +95,9 @@ class InteractionNetwork(nn.Module):
         p = MF.linear_act(x, W[:, :h], b, "none")
         q = MF.linear_act(x, W[:, h:2 * h], torch.zeros_like(b), "none")
         r = MF.linear_act(e_features, W[:, 2 * h:], torch.zeros_like(b), "none")
-        z0 = MF.edge_gather_add(p, q, r, edge_index, plan)
-        m = _mlp_ln(self.edge_fn, None, first_preact=z0)
-        agg = MF.scatter_mean(m, plan)
+        h0 = MF.edge_combine(p, q, r, edge_index, plan, "relu")      # ReLU of the first Linear, fused into the gather
+        m = _mlp_ln(self.edge_fn, None, first_preact=h0)
+        agg = MF.scatter_mean(m, edge_index, plan)
         x_new = _mlp_ln(self.node_fn, torch.cat([agg, x], dim=-1))
         return x_new + x, e_features + e_features
 
