@@ -23,53 +23,17 @@
 // operands, three MMAs (hi*hi + hi*lo + lo*hi), fp32 accumulation: error ~2^-17, inside the 1e-5 contract.
 #include "internal.cuh"
 #include "umma.cuh"
+#include "tc_common.cuh"
 
 namespace mgb {
 
 constexpr int TCH = 128;            // hidden width
 constexpr int TCE = 128;            // edge positions per tile (MMA N)
-constexpr int TILE_BYTES = 128 * 256;   // one [128][128] bf16 image
 constexpr int TC_STAGES = 2;
 constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
 constexpr int TC_MMA_WARP = TC_EPI_WARPS, TC_META_WARP = TC_EPI_WARPS + 1, TC_PROD_WARP0 = TC_EPI_WARPS + 2;
 constexpr int TC_THREADS = (TC_EPI_WARPS + 2 + TC_PROD_WARPS) * 32;   // 448
 constexpr int META_STAGES = 4;
-
-// ---- activations ------------------------------------------------------------------------------------
-// FAST (bf16 contract): sigmoid through one MUFU.TANH; precise: ex2.approx + rcp.approx (2 MUFU, ~2 ulp).
-template <bool FAST>
-__device__ __forceinline__ float sigmoid_tc(float z) {
-    if (FAST) {
-        float t;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
-        return fmaf(0.5f, t, 0.5f);
-    }
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-    return r;
-}
-template <bool FAST>
-__device__ __forceinline__ float swish_tc(float z) {
-    if (FAST) {
-        float t;
-        const float h = 0.5f * z;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-        return fmaf(h, t, h);
-    }
-    return z * sigmoid_tc<false>(z);
-}
-template <bool FAST>
-__device__ __forceinline__ float swish_grad_tc(float z) {
-    const float s = sigmoid_tc<FAST>(z);
-    return s * fmaf(z, 1.0f - s, 1.0f);
-}
-
-// two floats -> bf16x2 (hi) and the bf16x2 of the residuals (lo); ~3 instructions per element
-__device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
-    hi = umma::pack_bf16(a, b);
-    lo = umma::pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
-}
 
 // ---- W2 -> swizzled bf16 images (hi, lo) ----------------------------------------------------------
 __global__ void pack_w2_image_kernel(const float* __restrict__ W2, unsigned char* __restrict__ img) {
@@ -164,66 +128,61 @@ __device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __re
     if (lane == 0) M->nseg = base;
 }
 
-// Producer warp `pw` of TC_PROD_WARPS fills rows [pw*16, pw*16+16) of the edge tile:
+// Producer warp `pw` of PROD_WARPS fills rows [pw*ROWS, (pw+1)*ROWS) of the edge tile (ROWS = 128 / PROD_WARPS):
 //   h1[e][:] = Swish(P[dst_e] + Q[src_e])  ->  bf16 (hi[/lo]) K-major swizzled image(s).
-// All 16 Q-row gathers of the warp are issued before the first use (one 512-byte coalesced row per
+// The Q-row gathers are issued 16 rows at a time before their first use (one 512-byte coalesced row per
 // load instruction, float4 per lane); the P row is reused while dst stays the same.
-template <int NSPLIT, bool FAST>
+template <int NSPLIT, bool FAST, int PROD_WARPS>
 __device__ __forceinline__ void produce_h1_rows(const float* __restrict__ pq, const int32_t* __restrict__ dstv,
                                                 const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int pw,
                                                 int lane, uint64_t* empty_bar, uint32_t empty_parity, unsigned char* img) {
-    constexpr int ROWS = TCE / TC_PROD_WARPS;   // 16
+    constexpr int ROWS = TCE / PROD_WARPS;   // 16 or 32
+    static_assert(ROWS == 16 || ROWS == 32, "16 or 32 rows per producer warp");
     const int64_t e0 = tile * TCE + pw * ROWS;
     int my_d = -1, my_s = -1;
     if (lane < ROWS && e0 + lane < n_edges) {
         my_d = dstv[e0 + lane];
         my_s = srcv[e0 + lane];
     }
-    float4 q[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int sidx = __shfl_sync(0xffffffffu, my_s, r);
-        q[r] = *reinterpret_cast<const float4*>(pq + (int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + lane * 4);
-    }
-    int prev_d = __shfl_sync(0xffffffffu, my_d, 0);
-    float4 p = *reinterpret_cast<const float4*>(pq + (int64_t)(prev_d < 0 ? 0 : prev_d) * (2 * TCH) + lane * 4);
-    // byte offset of this lane's 4 channels inside a row of the swizzled image (row & 7 == r & 7 as pw*16 % 8 == 0)
+    // byte offset of this lane's 4 channels inside a row of the swizzled image (row & 7 == r & 7 as pw*ROWS % 8 == 0)
     const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
     const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
-    umma::mbar_wait(empty_bar, empty_parity);
+    int prev_d = __shfl_sync(0xffffffffu, my_d, 0);
+    float4 p = *reinterpret_cast<const float4*>(pq + (int64_t)(prev_d < 0 ? 0 : prev_d) * (2 * TCH) + lane * 4);
+#pragma unroll 1
+    for (int r0 = 0; r0 < ROWS; r0 += 16) {
+        float4 q[16];
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-        const int d = __shfl_sync(0xffffffffu, my_d, r);
-        if (d != prev_d) {
-            if (d >= 0) p = *reinterpret_cast<const float4*>(pq + (int64_t)d * (2 * TCH) + lane * 4);
-            prev_d = d;
+        for (int r = 0; r < 16; ++r) {
+            const int sidx = __shfl_sync(0xffffffffu, my_s, r0 + r);
+            q[r] = *reinterpret_cast<const float4*>(pq + (int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + lane * 4);
         }
-        float4 h;
-        h.x = swish_tc<FAST>(p.x + q[r].x);
-        h.y = swish_tc<FAST>(p.y + q[r].y);
-        h.z = swish_tc<FAST>(p.z + q[r].z);
-        h.w = swish_tc<FAST>(p.w + q[r].w);
-        if (d < 0) h = make_float4(0.f, 0.f, 0.f, 0.f);
-        const uint32_t off = lane_blk + (uint32_t)(pw * ROWS + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
-        if (NSPLIT == 1) {
-            *reinterpret_cast<uint2*>(img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
-        } else {
-            uint2 hi, lo;
-            split2_bf16(h.x, h.y, hi.x, lo.x);
-            split2_bf16(h.z, h.w, hi.y, lo.y);
-            *reinterpret_cast<uint2*>(img + off) = hi;
-            *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = lo;
+        if (r0 == 0) umma::mbar_wait(empty_bar, empty_parity);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int d = __shfl_sync(0xffffffffu, my_d, r0 + r);
+            if (d != prev_d) {
+                if (d >= 0) p = *reinterpret_cast<const float4*>(pq + (int64_t)d * (2 * TCH) + lane * 4);
+                prev_d = d;
+            }
+            float4 h;
+            h.x = swish_tc<FAST>(p.x + q[r].x);
+            h.y = swish_tc<FAST>(p.y + q[r].y);
+            h.z = swish_tc<FAST>(p.z + q[r].z);
+            h.w = swish_tc<FAST>(p.w + q[r].w);
+            if (d < 0) h = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t off = lane_blk + (uint32_t)(pw * ROWS + r0 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
+            if (NSPLIT == 1) {
+                *reinterpret_cast<uint2*>(img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
+            } else {
+                uint2 hi, lo;
+                split2_bf16(h.x, h.y, hi.x, lo.x);
+                split2_bf16(h.z, h.w, hi.y, lo.y);
+                *reinterpret_cast<uint2*>(img + off) = hi;
+                *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = lo;
+            }
         }
     }
-}
-
-__device__ __forceinline__ void load_w2_image(unsigned char* w_img, const unsigned char* src, uint32_t bytes, uint64_t* wbar) {
-    // one bulk async copy (TMA engine; no tensor map is needed for a pre-swizzled image)
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(wbar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     umma::smem_u32(w_img)),
-                 "l"(src), "r"(bytes), "r"(umma::smem_u32(wbar))
-                 : "memory");
 }
 
 // ==================================================================================================
@@ -384,7 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
-            produce_h1_rows<NSPLIT, FAST>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], ph ^ 1,
+            produce_h1_rows<NSPLIT, FAST, TC_PROD_WARPS>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], ph ^ 1,
                                           b_img + (size_t)s * NSPLIT * TILE_BYTES);
             umma::fence_async_smem();
             umma::mbar_arrive(&full[s]);
@@ -474,6 +433,10 @@ constexpr size_t edge_bwd_tc_smem() {
            edge_bwd_meta_stages<NSPLIT>() * sizeof(TileMeta) + 2 * BWD_NPRE * TCH * sizeof(float) + 256;
 }
 
+// warp roles of the backward kernel: 0-3 epilogue 1 (dz2, dW2 drain), 4-7 epilogue 2 (dz1, dP), 8 MMA, 9 metadata, 10-13 producers
+constexpr int BW_MMA_WARP = 8, BW_META_WARP = 9, BW_PROD_WARP0 = 10, BW_PROD_WARPS = 4;
+static_assert((BW_PROD_WARP0 + BW_PROD_WARPS) * 32 == TC_THREADS, "backward role layout");
+
 template <int NSPLIT, bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const EdgeBwdTcArgs a) {
     constexpr int STAGES = edge_bwd_tc_stages<NSPLIT>();
@@ -508,14 +471,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            umma::mbar_init(&full[s], TC_PROD_WARPS * 32);
+            umma::mbar_init(&full[s], BW_PROD_WARPS * 32);
             umma::mbar_init(&empty[s], 1);
             umma::mbar_init(&d3_full[s], 1);
             umma::mbar_init(&d3_empty[s], TC_EPI_WARPS * 32);
         }
         for (int s = 0; s < MSTAGES; ++s) {
             umma::mbar_init(&mfull[s], 32);
-            umma::mbar_init(&mempty[s], TC_EPI_WARPS * 32);
+            umma::mbar_init(&mempty[s], 2 * TC_EPI_WARPS * 32);
         }
         umma::mbar_init(d1_full, 1);
         umma::mbar_init(dz_full, TC_EPI_WARPS * 32);
@@ -525,18 +488,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == TC_MMA_WARP) umma::tmem_alloc(tmem_slot, 512);
+    if (warp == BW_MMA_WARP) umma::tmem_alloc(tmem_slot, 512);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;   // D3 buffers at +256, +384
 
-    if (warp < TC_EPI_WARPS) {
-        // =========================== epilogue: thread = channel ===================================
-        const int n = tid;
+    if (warp < 2 * TC_EPI_WARPS) {
+        // =========================== epilogues: thread = channel; group 0 (warps 0-3) runs epi1 of every tile,
+        // group 1 (warps 4-7) runs epi2, so epi1 of tile t+1 overlaps epi2 of tile t ==============================
+        const int grp_id = warp >> 2;
+        const int n = tid & 127;
         const float bias = a.b2[n];
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         float* dw_out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH;
         float db = 0.f;
         int it = 0;
@@ -548,21 +513,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             const TileMeta* M = metas + ms;
             umma::mbar_wait(&mfull[ms], (it / MSTAGES) & 1);
             const int nseg = M->nseg;
-            // prefetch the per-segment rows this thread needs (independent loads; own column of the tables)
+            // prefetch the per-segment rows this thread needs (independent loads; own column of the group's table)
             {
-                float gv[BWD_NPRE], pv[BWD_NPRE];
+                float tv[BWD_NPRE];
 #pragma unroll
                 for (int j = 0; j < BWD_NPRE; ++j) {          // all loads issued before the first use
                     const int jj = j < nseg ? j : nseg - 1;
                     const int d = M->segdst[jj];
-                    gv[j] = a.dagg[(int64_t)d * a.ld_dagg + n] * M->seginv[jj];
-                    pv[j] = a.pq[(int64_t)d * (2 * TCH) + n];
+                    tv[j] = grp_id == 0 ? a.dagg[(int64_t)d * a.ld_dagg + n] * M->seginv[jj] : a.pq[(int64_t)d * (2 * TCH) + n];
                 }
+                float* tab = grp_id == 0 ? gtab : ptab;
 #pragma unroll
-                for (int j = 0; j < BWD_NPRE; ++j) {
-                    gtab[j * TCH + n] = gv[j];
-                    ptab[j * TCH + n] = pv[j];
-                }
+                for (int j = 0; j < BWD_NPRE; ++j) tab[j * TCH + n] = tv[j];
             }
             auto seg_g = [&](int j) -> float {
                 if (j >= nseg) return 0.f;
@@ -574,6 +536,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 if (j < BWD_NPRE) return ptab[j * TCH + n];
                 return a.pq[(int64_t)M->segdst[j] * (2 * TCH) + n];
             };
+            if (grp_id == 0) {
             // ---- epi1: dz2 = dagg[dst]/deg * Swish'(z2) -> DZt (rows = channel, cols = edge) ----
             umma::mbar_wait(d1_full, ph);
             umma::mbar_wait(dz_empty, ph ^ 1);
@@ -628,6 +591,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             umma::fence_async_smem();
             umma::tc_fence_before();
             umma::mbar_arrive(dz_full);
+            // ---- drain a finished D3 group into this CTA's fp32 partial (round-to-nearest adds) ----
+            umma::mbar_arrive(&mempty[ms]);
+            const bool last = tile + gridDim.x >= n_tiles;
+            if ((it % D3_GROUP) == D3_GROUP - 1 || last) {
+                const int grp = it / D3_GROUP, buf = grp & 1;
+                umma::mbar_wait(&d3_full[buf], (grp >> 1) & 1);
+                umma::tc_fence_after();
+#pragma unroll 1
+                for (int c0 = 0; c0 < TCH; c0 += 32) {
+                    float v[32];
+                    umma::tmem_ld32(tm_d3 + (uint32_t)(buf * 128) + lane_base + c0, v);
+                    if (c0 + 32 >= TCH) {
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(&d3_empty[buf]);
+                    }
+                    float4* o = reinterpret_cast<float4*>(dw_out + c0);
+#pragma unroll
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        if (grp > 0) {
+                            const float4 old = o[q4];
+                            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                        }
+                        o[q4] = w;
+                    }
+                }
+            }
+            } else {
             // ---- epi2: dz1 = dh1 * Swish'(z1) -> global + segmented sum by destination -> dP ----
             {
                 int j = 0;
@@ -711,35 +702,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 }
             }
             umma::mbar_arrive(&mempty[ms]);
-            // ---- drain a finished D3 group into this CTA's fp32 partial (round-to-nearest adds) ----
-            const bool last = tile + gridDim.x >= n_tiles;
-            if ((it % D3_GROUP) == D3_GROUP - 1 || last) {
-                const int grp = it / D3_GROUP, buf = grp & 1;
-                umma::mbar_wait(&d3_full[buf], (grp >> 1) & 1);
-                umma::tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < TCH; c0 += 32) {
-                    float v[32];
-                    umma::tmem_ld32(tm_d3 + (uint32_t)(buf * 128) + lane_base + c0, v);
-                    if (c0 + 32 >= TCH) {
-                        umma::tc_fence_before();
-                        umma::mbar_arrive(&d3_empty[buf]);
-                    }
-                    float4* o = reinterpret_cast<float4*>(dw_out + c0);
-#pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-                        if (grp > 0) {
-                            const float4 old = o[q4];
-                            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-                        }
-                        o[q4] = w;
-                    }
-                }
             }
         }
-        a.db2_partial[(int64_t)blockIdx.x * TCH + n] = db;
-    } else if (warp == TC_MMA_WARP) {
+        if (grp_id == 0) a.db2_partial[(int64_t)blockIdx.x * TCH + n] = db;
+    } else if (warp == BW_MMA_WARP) {
         // =========================== MMA issue ====================================================
         if (lane == 0) load_w2_image(w_img, a.w2img, NSPLIT * TILE_BYTES, wbar);
         umma::mbar_wait(wbar, 0);
@@ -807,7 +773,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             }
             __syncwarp();
         }
-    } else if (warp == TC_META_WARP) {
+    } else if (warp == BW_META_WARP) {
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ms = it % MSTAGES;
@@ -817,12 +783,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         }
     } else {
         // =========================== producers ====================================================
-        const int pw = warp - TC_PROD_WARP0;
+        const int pw = warp - BW_PROD_WARP0;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % STAGES;
             const uint32_t sph = (it / STAGES) & 1;
-            produce_h1_rows<NSPLIT, FAST>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], sph ^ 1,
+            produce_h1_rows<NSPLIT, FAST, BW_PROD_WARPS>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], sph ^ 1,
                                           h_img + (size_t)s * NSPLIT * TILE_BYTES);
             umma::fence_async_smem();
             umma::mbar_arrive(&full[s]);
@@ -830,7 +796,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == TC_MMA_WARP) umma::tmem_dealloc(tmem, 512);
+    if (warp == BW_MMA_WARP) umma::tmem_dealloc(tmem, 512);
 }
 
 int edge_bwd_tc_grid(int64_t n_edges) {

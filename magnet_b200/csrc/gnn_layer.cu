@@ -478,6 +478,9 @@ int instance_norm_bwd(const float* dy, const float* y, const float* rstd, const 
 struct GnnPacked {
     float *wcat_t, *wcat, *bcat, *w2t, *w3t, *w4t;
     float* w2img;   // two swizzled bf16 [128][128] images of W2 (hi | lo) for the tcgen05 edge kernels
+    float* img_pq;  // weight tiles (hi|lo images, H*H floats each) of the node-level Linears for linear_tc.cu:
+    float* img_w3;  //   Wcat rows P / Q x columns [0,128);  W3 columns [0,128) / [128,256);  W4
+    float* img_w4;
 };
 static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) {
     size_t off = 0;
@@ -489,7 +492,11 @@ static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) 
     float* e = take((size_t)sh.K3() * H);
     float* f = take((size_t)H * H);
     float* g = take((size_t)H * H);      // 2 images x 128 x 128 bf16 = H*H floats
-    if (p) { p->wcat_t = a; p->wcat = b; p->bcat = c; p->w2t = d; p->w3t = e; p->w4t = f; p->w2img = g; }
+    float* i1 = take((size_t)2 * H * H);
+    float* i2 = take((size_t)2 * H * H);
+    float* i3 = take((size_t)H * H);
+    if (p) { p->wcat_t = a; p->wcat = b; p->bcat = c; p->w2t = d; p->w3t = e; p->w4t = f; p->w2img = g;
+             p->img_pq = i1; p->img_w3 = i2; p->img_w4 = i3; }
     return off;
 }
 
@@ -509,6 +516,11 @@ int gnn_layer_pack(const float* W1, const float* b1, const float* W2, const floa
     MGB_TRY(launch_transpose(W3, H, sh.K3(), sh.K3(), p.w3t, H, s));
     MGB_TRY(launch_transpose(W4, H, H, H, p.w4t, H, s));
     MGB_TRY(pack_w2_image(W2, p.w2img, s));
+    MGB_TRY(pack_weight_tile(p.wcat, sh.Kc(), 2 * H, sh.Kc(), 0, 0, p.img_pq, s));
+    MGB_TRY(pack_weight_tile(p.wcat, sh.Kc(), 2 * H, sh.Kc(), H, 0, p.img_pq + H * H, s));
+    MGB_TRY(pack_weight_tile(W3, sh.K3(), H, sh.K3(), 0, 0, p.img_w3, s));
+    MGB_TRY(pack_weight_tile(W3, sh.K3(), H, sh.K3(), 0, H, p.img_w3 + H * H, s));
+    MGB_TRY(pack_weight_tile(W4, H, H, H, 0, 0, p.img_w4, s));
     return MGB_OK;
 }
 
@@ -539,8 +551,20 @@ int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, siz
     MGB_WS_CHECK(ws);
     MGB_REQUIRE(sh.precision >= 0 && sh.precision <= 2, "gnn_layer: unknown precision %d", sh.precision);
     if (N == 0) return MGB_OK;
+    const int kt_pq = sh.tw + sh.dp + sh.nv;
+    const bool tc_nodes = sh.precision != 0 && kt_pq <= 16 && sh.nv <= 16;
     // 1. P | Q = [x,u,pos,var] Wcat^T + [b1 | 0]
-    {
+    if (tc_nodes) {
+        LinTcArgs a{};
+        a.src[0] = io.x; a.ld[0] = H; a.nk = 1;
+        a.tsrc[0] = io.u; a.tld[0] = sh.tw; a.tk[0] = sh.tw;
+        a.tsrc[1] = io.pos; a.tld[1] = sh.dp; a.tk[1] = sh.dp;
+        a.tsrc[2] = io.var; a.tld[2] = sh.nv; a.tk[2] = sh.nv;
+        a.kt = kt_pq; a.wtail = p.wcat + H; a.wt_sn = sh.Kc(); a.wt_st = 1;
+        a.wimg = p.img_pq; a.nm = 2; a.tile_of[0][0] = 0; a.tile_of[1][0] = 1;
+        a.bias = p.bcat; a.act = ACT_NONE; a.y = io.pq; a.ldy = 2 * H; a.rows = N;
+        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+    } else {
         GemmArgs g{};
         g.a.p[0] = io.x; g.a.ld[0] = H; g.a.k[0] = H;
         g.a.p[1] = io.u; g.a.ld[1] = sh.tw; g.a.k[1] = sh.tw;
@@ -571,6 +595,21 @@ int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, siz
         }
     }
     // 3. update net
+    if (tc_nodes) {
+        LinTcArgs a{};
+        a.src[0] = io.x; a.ld[0] = H; a.src[1] = io.agg; a.ld[1] = H; a.nk = 2;
+        a.tsrc[0] = io.var; a.tld[0] = sh.nv; a.tk[0] = sh.nv; a.kt = sh.nv;
+        a.wtail = p.w3t + (size_t)2 * H * H; a.wt_sn = 1; a.wt_st = H;
+        a.wimg = p.img_w3; a.nm = 1; a.tile_of[0][0] = 0; a.tile_of[0][1] = 1;
+        a.bias = io.b3; a.act = ACT_SWISH; a.y = y1; a.ldy = H; a.y_pre = io.y1_pre; a.ldyp = H; a.rows = N;
+        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+        LinTcArgs b{};
+        b.src[0] = y1; b.ld[0] = H; b.nk = 1;
+        b.wimg = p.img_w4; b.nm = 1; b.tile_of[0][0] = 0;
+        b.bias = io.b4; b.act = ACT_SWISH; b.residual = io.x; b.ldr = H;
+        b.y = out; b.ldy = H; b.y_pre = io.y2_pre; b.ldyp = H; b.rows = N;
+        MGB_TRY(launch_linear_tc(sh.precision, b, s));
+    } else {
     {
         GemmArgs g{};
         g.a.p[0] = io.x; g.a.ld[0] = H; g.a.k[0] = H;
@@ -590,6 +629,7 @@ int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, siz
         g.c = out; g.ldc = H; g.c_pre = io.y2_pre; g.ldcp = H; g.act = ACT_SWISH;
         g.M = N; g.N = H; g.K = H;
         MGB_TRY(launch_gemm(g, s));
+    }
     }
     // 4. InstanceNorm per graph
     MGB_TRY(instance_norm_fwd(out, io.gptr, sh.n_graphs, sh.max_nodes_per_graph, io.y, io.rstd, ws.base + ws.off,
@@ -634,7 +674,7 @@ size_t gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp,
     if (w2 > w) w = w2;
     if (w3 > w) w = w3;
     b += w + inorm_workspace_bytes(n_graphs, max_nodes) + 8192;
-    b += align_up(edge_bwd_tc_workspace(n_edges));
+    b += align_up(edge_bwd_tc_workspace(n_edges)) + align_up(wgrad_tc_workspace(n_nodes));
     return b;
 }
 
@@ -662,8 +702,12 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     float* dbcat = ws.take<float>(2 * H);
     const size_t tc_bytes = edge_bwd_tc_workspace(sh.n_edges);
     char* tc_ws = ws.take<char>(tc_bytes);
+    const size_t wg_bytes = wgrad_tc_workspace(N);
+    char* wg_ws = ws.take<char>(wg_bytes);
     MGB_WS_CHECK(ws);
     MGB_REQUIRE(sh.precision >= 0 && sh.precision <= 2, "gnn_layer: unknown precision %d", sh.precision);
+    const int kt_pq = sh.tw + sh.dp + sh.nv;
+    const bool tc_nodes = sh.precision != 0 && kt_pq <= 16 && sh.nv <= 16;
     void* sub_ws = ws.base + ws.off;
     size_t sub_bytes = ws.cap - ws.off;
     const int acc = io.accumulate_params;
@@ -671,7 +715,18 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     // B1. InstanceNorm backward -> d0 = d(out)
     MGB_TRY(instance_norm_bwd(io.dy, io.y, io.rstd, io.gptr, sh.n_graphs, sh.max_nodes_per_graph, d0, sub_ws, sub_bytes, s));
     // B2. update_net_2:  dW4 = (d0*Swish'(y2_pre))^T Swish(y1_pre);  d1 = (d0*Swish'(y2_pre)) W4
-    {
+    if (tc_nodes) {
+        WgradTcArgs w{};
+        w.dy = d0; w.lddy = H; w.y_pre = io.y2_pre; w.ldyp = H; w.y_act = ACT_SWISH;
+        w.x = io.y1_pre; w.ldx = H; w.x_act = ACT_SWISH; w.rows = N;
+        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW4, H, H, H, acc, wg_ws, wg_bytes, s));
+        MGB_TRY(launch_colsum(d0, H, io.y2_pre, ACT_SWISH, N, H, io.db4, acc, sub_ws, sub_bytes, s));
+        LinTcArgs a{};
+        a.src[0] = d0; a.ld[0] = H; a.nk = 1; a.pre = io.y2_pre; a.ldpre = H; a.pre_act = ACT_SWISH;
+        a.wimg = p.img_w4; a.nm = 1; a.a_trans = 1; a.tile_of[0][0] = 0;
+        a.act = ACT_NONE; a.y = d1; a.ldy = H; a.rows = N;
+        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+    } else {
         WgradArgs w{};
         w.dy = d0; w.lddy = H; w.y_pre = io.y2_pre; w.y_act = ACT_SWISH;
         w.a.p[0] = io.y1_pre; w.a.ld[0] = H; w.a.k[0] = H; w.a.nseg = 1; w.a.self_act = ACT_SWISH;
@@ -683,7 +738,23 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         MGB_TRY(launch_gemm(g, s));
     }
     // B3. update_net_1:  dW3 = (d1*Swish'(y1_pre))^T [x,agg,var];  dc = (d1*Swish'(y1_pre)) W3
-    {
+    if (tc_nodes) {
+        WgradTcArgs w{};
+        w.dy = d1; w.lddy = H; w.y_pre = io.y1_pre; w.ldyp = H; w.y_act = ACT_SWISH; w.rows = N;
+        w.x = io.x; w.ldx = H;
+        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW3, sh.K3(), H, H, acc, wg_ws, wg_bytes, s));
+        w.x = io.agg;
+        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW3 + H, sh.K3(), H, H, acc, wg_ws, wg_bytes, s));
+        w.x = nullptr; w.tsrc[0] = io.var; w.tld[0] = sh.nv; w.tk[0] = sh.nv; w.kt = sh.nv;
+        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW3 + 2 * H, sh.K3(), H, sh.nv, acc, wg_ws, wg_bytes, s));
+        MGB_TRY(launch_colsum(d1, H, io.y1_pre, ACT_SWISH, N, H, io.db3, acc, sub_ws, sub_bytes, s));
+        LinTcArgs a{};
+        a.src[0] = d1; a.ld[0] = H; a.nk = 1; a.pre = io.y1_pre; a.ldpre = H; a.pre_act = ACT_SWISH;
+        a.wimg = p.img_w3; a.nm = 2; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[1][0] = 1;
+        a.act = ACT_NONE; a.y = dc; a.ldy = ldc; a.rows = N;
+        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+        MGB_TRY(launch_tail_dgrad(d1, H, H, io.y1_pre, H, ACT_SWISH, io.W3 + 2 * H, sh.K3(), 1, sh.nv, N, dc + 2 * H, ldc, s));
+    } else {
         WgradArgs w{};
         w.dy = d1; w.lddy = H; w.y_pre = io.y1_pre; w.y_act = ACT_SWISH;
         w.a.p[0] = io.x; w.a.ld[0] = H; w.a.k[0] = H;
@@ -728,7 +799,30 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         MGB_CUDA(cudaMemsetAsync(io.db2, 0, (size_t)H * sizeof(float), s));
     }
     // B6. first Linear (factorised): dWcat = dPQ^T [x,u,pos,var];  dxc = dPQ Wcat
-    {
+    if (tc_nodes) {
+        for (int half = 0; half < 2; ++half) {       // rows of dWcat: P outputs, Q outputs
+            WgradTcArgs w{};
+            w.dy = dpq + half * H; w.lddy = 2 * H; w.rows = N;
+            w.x = io.x; w.ldx = H;
+            MGB_TRY(launch_wgrad_tc(sh.precision, w, dwcat + (size_t)half * H * sh.Kc(), sh.Kc(), H, H, 0, wg_ws, wg_bytes, s));
+            w.x = nullptr;
+            w.tsrc[0] = io.u; w.tld[0] = sh.tw; w.tk[0] = sh.tw;
+            w.tsrc[1] = io.pos; w.tld[1] = sh.dp; w.tk[1] = sh.dp;
+            w.tsrc[2] = io.var; w.tld[2] = sh.nv; w.tk[2] = sh.nv; w.kt = kt_pq;
+            MGB_TRY(launch_wgrad_tc(sh.precision, w, dwcat + (size_t)half * H * sh.Kc() + H, sh.Kc(), H, kt_pq, 0, wg_ws, wg_bytes, s));
+        }
+        MGB_TRY(launch_colsum(dpq, 2 * H, nullptr, ACT_NONE, N, 2 * H, dbcat, 0, sub_ws, sub_bytes, s));
+        unpack_dw1_kernel<<<ceil_div(H * sh.K1(), 256), 256, 0, s>>>(dwcat, sh.tw, sh.dp, sh.nv, io.dW1, acc);
+        MGB_LAUNCH_CHECK();
+        sum_partials_kernel<<<1, 256, 0, s>>>(dbcat, 1, H, io.db1, acc);
+        MGB_LAUNCH_CHECK();
+        LinTcArgs a{};
+        a.src[0] = dpq; a.ld[0] = 2 * H; a.src[1] = dpq + H; a.ld[1] = 2 * H; a.nk = 2;
+        a.wimg = p.img_pq; a.nm = 1; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[0][1] = 1;
+        a.act = ACT_NONE; a.y = dxc; a.ldy = ldx; a.rows = N;
+        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+        MGB_TRY(launch_tail_dgrad(dpq, 2 * H, 2 * H, nullptr, 0, ACT_NONE, p.wcat + H, sh.Kc(), 1, kt_pq, N, dxc + H, ldx, s));
+    } else {
         WgradArgs w{};
         w.dy = dpq; w.lddy = 2 * H;
         w.a.p[0] = io.x; w.a.ld[0] = H; w.a.k[0] = H;

@@ -101,6 +101,34 @@ size_t edge_bwd_tc_workspace(int64_t n_edges);
 int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv,
                        int64_t n_edges, const void* w2img, const float* b2, const float* dagg, int ld_dagg, float* dz1,
                        float* dpq, float* dW2, float* db2, int accumulate, void* ws, size_t ws_bytes, cudaStream_t s);
+// linear_tc.cu (tcgen05 row-wise Linear, data and weight gradients)
+struct LinTcArgs {
+    const float* src[2]; int ld[2]; int nk;         // activation chunks of 128 columns
+    const float* pre; int ldpre; int pre_act;       // chunk 0: x *= act'(pre)
+    int self_act;                                   // chunk 0: x = act(x)
+    const float* tsrc[3]; int tld[3]; int tk[3]; int kt;   // small-K tail (forward only), sum tk = kt <= 16
+    const float* wtail; int wt_sn, wt_st;           // tail weight (n, t) at wtail[n*wt_sn + t*wt_st]
+    const void* wimg;                               // weight tiles (hi|lo images), 64 KB each
+    int nm, a_trans; int tile_of[2][2];             // tile index used by (output block m, chunk kc)
+    const float* bias; int act;
+    const float* residual; int ldr;
+    float* y; int ldy; float* y_pre; int ldyp;
+    int64_t rows;
+};
+struct WgradTcArgs {
+    const float* dy; int lddy; const float* y_pre; int ldyp; int y_act;   // Y' = dy * act'(y_pre)
+    const float* x; int ldx; int x_act;                                   // X (128 columns) or null -> tail columns
+    const float* tsrc[3]; int tld[3]; int tk[3]; int kt;
+    int64_t rows;
+    float* partial;                                                       // filled by the launcher
+};
+int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s);
+int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s);
+size_t wgrad_tc_workspace(int64_t rows);
+int launch_wgrad_tc(int precision, WgradTcArgs a, float* dw, int lddw, int n_valid, int k_valid, int accumulate, void* ws,
+                    size_t ws_bytes, cudaStream_t s);
+int launch_tail_dgrad(const float* dy, int lddy, int ny, const float* pre, int ldpre, int act, const float* wtail, int wt_sn,
+                      int wt_st, int kt, int64_t rows, float* out, int ldo, cudaStream_t s);
 // umma_selftest.cu
 int umma_selftest(const float* a, const float* b, int a_mn, int b_mn, int lbo_mn, int sbo_mn, float* d, cudaStream_t s);
 
