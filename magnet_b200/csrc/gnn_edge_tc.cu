@@ -81,6 +81,7 @@ struct TileMeta {
     int segdst[TCE];       // the tile's segments in order: destination node, 1 / in-degree
     float seginv[TCE];
     uint32_t endmask[4];   // bit p of the 128-bit mask: position p is the last of its segment within the tile
+    uint32_t flushmask[4]; // bit p: a running segment sum is stored after position p (segment ends + sub-tile ends)
     int nseg;
     int pad[3];
 };
@@ -88,7 +89,10 @@ struct TileMeta {
 // one warp; positions p = j*32 + lane
 __device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dstv,
                                                 const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int lane,
-                                                float* out_base, int ld_out, bool mean, float* part_head, float* part_tail) {
+                                                float* out_base, int ld_out, bool mean, float* part_head, float* part_tail,
+                                                int flush_te) {
+    // flush_te (128 or 64): granularity at which running segment sums are cut and stored; sums cut by a sub-tile
+    // boundary go to that sub-tile's head / tail partial row (sub-tile id = e / flush_te) and are merged by the fix-up kernel
     const int64_t e0 = tile * TCE;
     const int64_t e1 = (e0 + TCE < n_edges) ? e0 + TCE : n_edges;
     int base = 0;
@@ -103,21 +107,25 @@ __device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __re
         const int prv = (valid && p > 0) ? dstv[e - 1] : -2;
         const bool is_end = valid && nxt != d;
         const bool is_start = valid && prv != d;
+        const bool is_flush = is_end || (valid && (p % flush_te) == flush_te - 1);
         int s0 = 0, s1 = 1;
-        if (is_end || is_start) {
+        if (is_flush || is_start) {
             s0 = rowptr[d];
             s1 = rowptr[d + 1];
         }
         const float inv = 1.0f / (float)(s1 - s0);
         M->dst[p] = d;
         M->src[p] = sidx;
-        const bool inside = (int64_t)s0 >= e0 && (int64_t)s1 <= e1;
+        const int64_t f0 = e0 + (p / flush_te) * flush_te;                 // bounds of this position's sub-tile
+        const int64_t f1 = (f0 + flush_te < e1) ? f0 + flush_te : e1;
+        const bool inside = (int64_t)s0 >= f0 && (int64_t)s1 <= f1;
         M->scale[p] = (inside && mean) ? inv : 1.0f;
-        if (is_end)
-            M->out[p] = inside ? out_base + (int64_t)d * ld_out : ((int64_t)s0 < e0 ? part_head : part_tail) + tile * TCH;
+        if (is_flush)
+            M->out[p] = inside ? out_base + (int64_t)d * ld_out : ((int64_t)s0 < f0 ? part_head : part_tail) + (f0 / flush_te) * TCH;
         const uint32_t em = __ballot_sync(0xffffffffu, is_end);
+        const uint32_t fm = __ballot_sync(0xffffffffu, is_flush);
         const uint32_t sm = __ballot_sync(0xffffffffu, is_start);
-        if (lane == 0) M->endmask[j] = em;
+        if (lane == 0) { M->endmask[j] = em; M->flushmask[j] = fm; }
         if (is_start) {
             const int idx = base + __popc(sm & ((1u << lane) - 1u));
             M->segdst[idx] = d;
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ms = it % META_STAGES;
             umma::mbar_wait(&mempty[ms], ((it / META_STAGES) & 1) ^ 1);
-            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.agg, TCH, true, a.part_head, a.part_tail);
+            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.agg, TCH, true, a.part_head, a.part_tail, TCE);
             umma::mbar_arrive(&mfull[ms]);
         }
     } else {
@@ -430,15 +438,17 @@ constexpr int edge_bwd_meta_stages() { return NSPLIT == 1 ? 4 : 2; }
 template <int NSPLIT>
 constexpr size_t edge_bwd_tc_smem() {
     return 1024 + (size_t)NSPLIT * TILE_BYTES * (2 + edge_bwd_tc_stages<NSPLIT>()) +
-           edge_bwd_meta_stages<NSPLIT>() * sizeof(TileMeta) + 2 * BWD_NPRE * TCH * sizeof(float) + 256;
+           edge_bwd_meta_stages<NSPLIT>() * sizeof(TileMeta) + 3 * BWD_NPRE * TCH * sizeof(float) + 256;
 }
 
-// warp roles of the backward kernel: 0-3 epilogue 1 (dz2, dW2 drain), 4-7 epilogue 2 (dz1, dP), 8 MMA, 9 metadata, 10-13 producers
-constexpr int BW_MMA_WARP = 8, BW_META_WARP = 9, BW_PROD_WARP0 = 10, BW_PROD_WARPS = 4;
-static_assert((BW_PROD_WARP0 + BW_PROD_WARPS) * 32 == TC_THREADS, "backward role layout");
+// warp roles of the backward kernel: 0-3 epilogue 1 (dz2, dW2 drain); 4-11 epilogue 2 (dz1, dP; warps 4-7 own edge
+// positions 0-63 of the tile, warps 8-11 positions 64-127); 12 MMA; 13 metadata; 14-17 producers
+constexpr int BW_MMA_WARP = 12, BW_META_WARP = 13, BW_PROD_WARP0 = 14, BW_PROD_WARPS = 4;
+constexpr int BW_THREADS = (BW_PROD_WARP0 + BW_PROD_WARPS) * 32;     // 576
+constexpr int BW_FLUSH_TE = 64;
 
 template <int NSPLIT, bool FAST>
-__global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const EdgeBwdTcArgs a) {
+__global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const EdgeBwdTcArgs a) {
     constexpr int STAGES = edge_bwd_tc_stages<NSPLIT>();
     constexpr int MSTAGES = edge_bwd_meta_stages<NSPLIT>();
     constexpr int D3_GROUP = FAST ? (1 << 30) : 4;
@@ -450,8 +460,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
     unsigned char* dz_img = h_img + (size_t)STAGES * NSPLIT * TILE_BYTES;       // [split]   DZt[n][e]
     TileMeta* metas = reinterpret_cast<TileMeta*>(dz_img + (size_t)NSPLIT * TILE_BYTES);
     float* gtab = reinterpret_cast<float*>(metas + MSTAGES);       // [BWD_NPRE][128]  dagg[segdst]/deg
-    float* ptab = gtab + BWD_NPRE * TCH;                           // [BWD_NPRE][128]  P[segdst]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ptab + BWD_NPRE * TCH);
+    float* ptab_all = gtab + BWD_NPRE * TCH;                       // [2 halves][BWD_NPRE][128]  P[segdst]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ptab_all + 2 * BWD_NPRE * TCH);
     uint64_t* full = bars;               // [2] producers -> MMA (h1 tile ready)
     uint64_t* empty = bars + 2;          // [2] MMA3 done -> producers
     uint64_t* d1_full = bars + 4;        // MMA1 done -> epilogue
@@ -478,13 +488,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         }
         for (int s = 0; s < MSTAGES; ++s) {
             umma::mbar_init(&mfull[s], 32);
-            umma::mbar_init(&mempty[s], 2 * TC_EPI_WARPS * 32);
+            umma::mbar_init(&mempty[s], 3 * TC_EPI_WARPS * 32);
         }
         umma::mbar_init(d1_full, 1);
         umma::mbar_init(dz_full, TC_EPI_WARPS * 32);
         umma::mbar_init(dz_empty, 1);
         umma::mbar_init(d2_full, 1);
-        umma::mbar_init(d2_empty, TC_EPI_WARPS * 32);
+        umma::mbar_init(d2_empty, 2 * TC_EPI_WARPS * 32);
         umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
@@ -495,10 +505,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
     const uint32_t tmem = *tmem_slot;
     const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;   // D3 buffers at +256, +384
 
-    if (warp < 2 * TC_EPI_WARPS) {
+    if (warp < 3 * TC_EPI_WARPS) {
         // =========================== epilogues: thread = channel; group 0 (warps 0-3) runs epi1 of every tile,
         // group 1 (warps 4-7) runs epi2, so epi1 of tile t+1 overlaps epi2 of tile t ==============================
-        const int grp_id = warp >> 2;
+        const int grp_id = warp < TC_EPI_WARPS ? 0 : 1;
+        const int half = warp < 2 * TC_EPI_WARPS ? 0 : 1;       // epilogue 2: which 64 positions of the tile
+        float* ptab = ptab_all + half * BWD_NPRE * TCH;         // the two halves run independently: own table each
         const int n = tid & 127;
         const float bias = a.b2[n];
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -621,8 +633,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             } else {
             // ---- epi2: dz1 = dh1 * Swish'(z1) -> global + segmented sum by destination -> dP ----
             {
-                int j = 0;
-                float pk = seg_p(0);
+                const int pos0 = half * 64;
+                int j = half ? __popc(M->endmask[0]) + __popc(M->endmask[1]) : 0;     // segment that contains position pos0
+                float pk = seg_p(j);
                 float sum = 0.f;
                 const bool full_tile = ne == TCE;
                 auto load_q = [&](float (&q)[16], int c0) {
@@ -635,12 +648,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 auto process = [&](float (&q)[16], int c0) {
                     float v[16];
                     umma::tmem_ld16(tm_d2 + lane_base + c0, v);
-                    if (c0 + 16 >= TCE) {
+                    if (c0 + 16 >= pos0 + 64) {
                         umma::tc_fence_before();
                         umma::mbar_arrive(d2_empty);
                     }
                     if (c0 >= ne) return;
                     const uint32_t em = (M->endmask[c0 >> 5] >> (c0 & 16)) & 0xffffu;
+                    const uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 16)) & 0xffffu;
 #pragma unroll
                     for (int h8 = 0; h8 < 2; ++h8) {
                         const uint32_t eq = (em >> (8 * h8)) & 0xffu;
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                     }
 #pragma unroll
                     for (int h8 = 0; h8 < 2; ++h8) {
-                        const uint32_t eq = (em >> (8 * h8)) & 0xffu;
+                        const uint32_t eq = (fm >> (8 * h8)) & 0xffu;
                         const float* w = v + 8 * h8;
                         if (eq == 0) {
                             sum += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
@@ -690,14 +704,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 // the Q re-gather of the next 16 positions is in flight while the current 16 are processed;
                 // the first batch is issued before waiting for MMA2
                 float qa[16], qb[16];
-                load_q(qa, 0);
+                load_q(qa, pos0);
                 umma::mbar_wait(d2_full, ph);
                 umma::tc_fence_after();
 #pragma unroll 1
-                for (int c0 = 0; c0 < TCE; c0 += 32) {
+                for (int c0 = pos0; c0 < pos0 + 64; c0 += 32) {
                     load_q(qb, c0 + 16);
                     process(qa, c0);
-                    if (c0 + 32 < TCE) load_q(qa, c0 + 32);
+                    if (c0 + 32 < pos0 + 64) load_q(qa, c0 + 32);
                     process(qb, c0 + 16);
                 }
             }
@@ -778,7 +792,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ms = it % MSTAGES;
             umma::mbar_wait(&mempty[ms], ((it / MSTAGES) & 1) ^ 1);
-            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.dpq, 2 * TCH, false, a.part_head, a.part_tail);
+            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.dpq, 2 * TCH, false, a.part_head, a.part_tail, BW_FLUSH_TE);
             umma::mbar_arrive(&mfull[ms]);
         }
     } else {
@@ -805,7 +819,7 @@ int edge_bwd_tc_grid(int64_t n_edges) {
 }
 
 size_t edge_bwd_tc_workspace(int64_t n_edges) {
-    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TCE);
+    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, BW_FLUSH_TE);
     const int grid = edge_bwd_tc_grid(n_edges);
     return 2 * align_up((size_t)tiles * TCH * sizeof(float)) + align_up((size_t)grid * TCH * TCH * sizeof(float)) +
            align_up((size_t)grid * TCH * sizeof(float)) + 1024;
@@ -824,11 +838,11 @@ int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, co
                        int64_t n_edges, const void* w2img, const float* b2, const float* dagg, int ld_dagg, float* dz1,
                        float* dpq, float* dW2, float* db2, int accumulate, void* ws_ptr, size_t ws_bytes, cudaStream_t s) {
     if (n_edges <= 0) return MGB_OK;
-    const int64_t tiles = ceil_div<int64_t>(n_edges, TCE);
+    const int64_t subtiles = ceil_div<int64_t>(n_edges, BW_FLUSH_TE);
     const int grid = edge_bwd_tc_grid(n_edges);
     Workspace ws(ws_ptr, ws_bytes);
-    float* part_head = ws.take<float>((size_t)tiles * TCH);
-    float* part_tail = ws.take<float>((size_t)tiles * TCH);
+    float* part_head = ws.take<float>((size_t)subtiles * TCH);
+    float* part_tail = ws.take<float>((size_t)subtiles * TCH);
     float* dw2_part = ws.take<float>((size_t)grid * TCH * TCH);
     float* db2_part = ws.take<float>((size_t)grid * TCH);
     MGB_WS_CHECK(ws);
@@ -839,16 +853,16 @@ int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, co
         if (precision == 2) {
             constexpr size_t smem = edge_bwd_tc_smem<1>();
             MGB_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gnn_edge_bwd_tc_kernel<1, true><<<grid, TC_THREADS, smem, s>>>(a);
+            gnn_edge_bwd_tc_kernel<1, true><<<grid, BW_THREADS, smem, s>>>(a);
         } else {
             constexpr size_t smem = edge_bwd_tc_smem<2>();
             MGB_CUDA(cudaFuncSetAttribute(gnn_edge_bwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gnn_edge_bwd_tc_kernel<2, false><<<grid, TC_THREADS, smem, s>>>(a);
+            gnn_edge_bwd_tc_kernel<2, false><<<grid, BW_THREADS, smem, s>>>(a);
         }
     }
     MGB_LAUNCH_CHECK();
-    if (tiles > 1) {
-        segment_fixup_tc_kernel<<<(unsigned)(tiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, TCE, part_head, part_tail, dpq, 2 * TCH, 0);
+    if (subtiles > 1) {
+        segment_fixup_tc_kernel<<<(unsigned)(subtiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, BW_FLUSH_TE, part_head, part_tail, dpq, 2 * TCH, 0);
         MGB_LAUNCH_CHECK();
     }
     sum_partials_tc_kernel<<<ceil_div(TCH * TCH, 256), 256, 0, s>>>(dw2_part, grid, (int64_t)TCH * TCH, dW2, accumulate);
