@@ -169,6 +169,77 @@ def workload_config(n_gpus, note=None):
     return c
 
 
+def extra_metrics(dev, rank):
+    """The two other metrics BASELINE.json names, measured in the same run on this rank's GPU (reported per GPU;
+    both shard by independent samples with no collective, so N GPUs give N times these figures):
+      * INR decode: queries/s of continuous_decoder + projector (kNN search, gather, head, blend, 5-layer MLP) on
+        2^18 query points over a 2^18-node low-res mesh, k = 4, T = 10 (BASELINE configs[4] shape, one sample);
+      * rollout: MAgNet[GNN] validation rollout steps/s at the reference's training shape (B = 32, L = Nq = 256,
+        time_slice 10, 4 autoregressive steps; BASELINE configs[2])."""
+    from magnet_b200 import synthetic as S
+    from magnet_b200.magnet_gnn import MAgNetGNN
+
+    class HP(dict):
+        __getattr__ = dict.__getitem__
+    hp = HP(time_slice=10, latent_dim=128, num_message_passing_steps=5, mlp_layers=4, mlp_hidden=128, radius=0.08, n_chan=128,
+            teacher_forcing=True, codec_neighbors=4, noise=0, interpolation="area", factor=0.3, step_size=50, loss="l1",
+            lr=1e-3, weight_decay=0)
+    m = MAgNetGNN(hp).to(dev).eval()
+    sd = S.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 7)
+    m.load_state_dict(sd)
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        # ---- INR decode ----
+        g = S._gen(500 + rank)
+        Lr, Q, T = 1 << 18, 1 << 18, 10
+        lr_coords = (2 * torch.rand(1, Lr, 2, generator=g) - 1).to(dev)
+        hr_coords = (2 * torch.rand(1, Q, 2, generator=g) - 1).to(dev)
+        enc = torch.randn(1, Lr, 128, generator=g).to(dev)
+        x_lr = torch.randn(1, T, 1, Lr, generator=g).to(dev)
+        t = torch.linspace(0, 1, 2 * T)[None].to(dev)
+
+        def decode():
+            z = m.continuous_decoder(x_lr, enc, lr_coords, hr_coords, t)
+            return m.projector(z)
+        for _ in range(2):
+            decode()
+        torch.cuda.synchronize()
+        reps = 3
+        ev0.record()
+        for _ in range(reps):
+            hr = decode()
+        ev1.record()
+        torch.cuda.synchronize()
+        out["inr_decode"] = {"value": Q * reps / (ev0.elapsed_time(ev1) * 1e-3), "unit": "query points/s (per GPU)",
+                             "queries": Q, "lowres_nodes": Lr, "k": 4, "time_steps": T,
+                             "includes": "kNN search + gather + proj_head + blend + projector MLP"}
+        del hr, enc, x_lr
+        # ---- rollout ----
+        b = {k: v.to(dev) for k, v in S.implicit_batch(B=32, L=256, Nq=256, nt=50, d=2, kind="concentrated", seed=600 + rank).items()}
+        for _ in range(2):
+            m.rollout(b, teacher_forcing=False)
+        torch.cuda.synchronize()
+        reps = 3
+        ev0.record()
+        for _ in range(reps):
+            m.rollout(b, teacher_forcing=False)
+        ev1.record()
+        torch.cuda.synchronize()
+        out["rollout"] = {"value": 4 * reps / (ev0.elapsed_time(ev1) * 1e-3), "unit": "rollout steps/s (per GPU)",
+                          "config": "MAgNet[GNN] B=32, L=Nq=256, time_slice 10, 4 steps per rollout, r=0.08, fp32"}
+    return out
+
+
+def ncu_traffic():
+    """dram bytes (read + write) per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "dominant_kernel_ncu.json")
+    try:
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from magnet_b200 import _lib, graph as MG, functional as MF
@@ -245,6 +316,11 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     e2e_ms = torch.tensor([ee0.elapsed_time(ee1)], device=dev)
     edges = torch.tensor([float(E)], device=dev)
+    extras = None
+    if not args.no_extra:
+        del d, out
+        torch.cuda.empty_cache()
+        extras = extra_metrics(dev, rank)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
@@ -262,7 +338,8 @@ def run_ours(args, rank, world, local_rank):
         alg_flops = 2 * FLOP_PER_EDGE_FWD * E            # dgrad + wgrad of both message Linears, reference formulation
         achieved = alg_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
-                    "traffic": None, "kernel": "gnn_edge_bwd_kernel", "peak_source": which,
+                    "traffic": ncu_traffic(), "kernel": "gnn_edge_bwd_tc_kernel" if args.precision != "fp32" else "gnn_edge_bwd_kernel",
+                    "peak_source": which,
                     "kernel_ms": bwd_ms, "kernel_share_of_step": bt / total_ms if total_ms > 0 else None,
                     "executed_tflops": 3 * EXEC_FLOP_PER_EDGE_FWD * E / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0,
                     "edge_fwd_kernel_ms": fwd_ms,
@@ -280,6 +357,8 @@ def run_ours(args, rank, world, local_rank):
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline, "edges_per_gpu": E,
         }
+        if not args.no_extra:
+            line["extra_metrics"] = extras
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, cms, ce = cpu_reference_run(1, 2, 1, threads)
@@ -298,6 +377,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the INR-decode and rollout side metrics")
     ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc", "bf16"],
                     help="edge-kernel arithmetic: fp32 FFMA | tcgen05 bf16 hi/lo split (1e-5 contract) | tcgen05 bf16 (1e-2)")
     args = ap.parse_args()

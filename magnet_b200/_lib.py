@@ -11,7 +11,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "magnet_b200.h")
-LIB_PATH = os.path.join(_HERE, "lib", "libmagnet_b200.so")
+_VARIANT = os.environ.get("MGB_VARIANT", "")      # developer builds (magnet_b200/build.py)
+LIB_PATH = os.path.join(_HERE, "lib" + ("_" + _VARIANT if _VARIANT else ""), "libmagnet_b200.so")
 
 _CTYPES = {
     "int": ctypes.c_int, "int64_t": ctypes.c_int64, "size_t": ctypes.c_size_t, "double": ctypes.c_double,

@@ -13,14 +13,16 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_DIR = os.path.join(_HERE, "lib")
+# developer variants (e.g. MGB_NVCC_EXTRA=-DMGB_TIMELINE MGB_VARIANT=tl) build into their own directory
+_VARIANT = os.environ.get("MGB_VARIANT", "")
+LIB_DIR = os.path.join(_HERE, "lib" + ("_" + _VARIANT if _VARIANT else ""))
 LIB_PATH = os.path.join(LIB_DIR, "libmagnet_b200.so")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("MGB_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

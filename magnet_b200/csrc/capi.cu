@@ -202,6 +202,10 @@ int mgb_inr_decode_bwd(const float* a, const float* xlr, const float* lr_coords,
                           dz, g, sx, dwsmall, ldw, accumulate, workspace, workspace_bytes, STREAM(stream));
 }
 
+#ifdef MGB_TIMELINE
+int mgb_debug_set_timeline(long long* p) { return mgb::set_timeline_buffer(p); }
+#endif
+
 int mgb_umma_selftest(const float* a, const float* b, int a_mn_major, int b_mn_major, int lbo_mn, int sbo_mn, float* d,
                       void* stream) {
     return umma_selftest(a, b, a_mn_major, b_mn_major, lbo_mn, sbo_mn, d, STREAM(stream));

@@ -412,6 +412,13 @@ int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, co
 //   epi2  dz1[e][k] = D2 * Swish'(P[dst_e][k] + Q[src_e][k])  -> global dz1 (by-source reduction later)
 //         and the segmented SUM over the dst-sorted positions -> dP[dst]      (no atomics)
 // ==================================================================================================
+#ifdef MGB_TIMELINE
+__device__ long long* g_timeline = nullptr;      // [role 0..4][it 0..15][event 0..3]
+#define TL(role, it_, ev) do { if (blockIdx.x == 0 && (it_) < 16 && (threadIdx.x & 31) == 0 && g_timeline) g_timeline[((role) * 16 + (it_)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define TL(role, it_, ev) do { } while (0)
+#endif
+
 struct EdgeBwdTcArgs {
     const float* pq;
     const int32_t* rowptr;
@@ -549,10 +556,13 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 return a.pq[(int64_t)M->segdst[j] * (2 * TCH) + n];
             };
             if (grp_id == 0) {
+            if (warp == 0) TL(2, it, 0);
             // ---- epi1: dz2 = dagg[dst]/deg * Swish'(z2) -> DZt (rows = channel, cols = edge) ----
             umma::mbar_wait(d1_full, ph);
+            if (warp == 0) TL(2, it, 1);
             umma::mbar_wait(dz_empty, ph ^ 1);
             umma::tc_fence_after();
+            if (warp == 0) TL(2, it, 2);
             {
                 int j = 0;
                 float g = seg_g(0);
@@ -603,6 +613,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             umma::fence_async_smem();
             umma::tc_fence_before();
             umma::mbar_arrive(dz_full);
+            if (warp == 0) TL(2, it, 3);
             // ---- drain a finished D3 group into this CTA's fp32 partial (round-to-nearest adds) ----
             umma::mbar_arrive(&mempty[ms]);
             const bool last = tile + gridDim.x >= n_tiles;
@@ -704,9 +715,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 // the Q re-gather of the next 16 positions is in flight while the current 16 are processed;
                 // the first batch is issued before waiting for MMA2
                 float qa[16], qb[16];
+                if ((warp & 3) == 0) TL(3 + half, it, 0);
                 load_q(qa, pos0);
                 umma::mbar_wait(d2_full, ph);
                 umma::tc_fence_after();
+                if ((warp & 3) == 0) TL(3 + half, it, 1);
 #pragma unroll 1
                 for (int c0 = pos0; c0 < pos0 + 64; c0 += 32) {
                     load_q(qb, c0 + 16);
@@ -715,6 +728,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                     process(qb, c0 + 16);
                 }
             }
+            if ((warp & 3) == 0) TL(3 + half, it, 2);
             umma::mbar_arrive(&mempty[ms]);
             }
         }
@@ -738,6 +752,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             const bool last = tile + gridDim.x >= n_tiles;
             umma::mbar_wait(&full[s], sph);
             umma::tc_fence_after();
+            TL(1, it, 0);
             if (lane == 0) {
                 uint32_t accum = 0;
 #pragma unroll
@@ -754,7 +769,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             }
             __syncwarp();
             umma::mbar_wait(dz_full, ph);
+            TL(1, it, 1);
             umma::mbar_wait(d2_empty, ph ^ 1);
+            TL(1, it, 2);
             if (first_in_group) umma::mbar_wait(&d3_empty[buf], ((grp >> 1) & 1) ^ 1);
             umma::tc_fence_after();
             if (lane == 0) {
@@ -802,16 +819,25 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % STAGES;
             const uint32_t sph = (it / STAGES) & 1;
+            if (pw == 0) TL(0, it, 0);
             produce_h1_rows<NSPLIT, FAST, BW_PROD_WARPS>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], sph ^ 1,
                                           h_img + (size_t)s * NSPLIT * TILE_BYTES);
             umma::fence_async_smem();
             umma::mbar_arrive(&full[s]);
+            if (pw == 0) TL(0, it, 1);
         }
     }
     umma::tc_fence_before();
     __syncthreads();
     if (warp == BW_MMA_WARP) umma::tmem_dealloc(tmem, 512);
 }
+
+#ifdef MGB_TIMELINE
+int set_timeline_buffer(long long* p) {
+    MGB_CUDA(cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)));
+    return MGB_OK;
+}
+#endif
 
 int edge_bwd_tc_grid(int64_t n_edges) {
     const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TCE);

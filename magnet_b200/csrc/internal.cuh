@@ -129,6 +129,9 @@ int launch_wgrad_tc(int precision, WgradTcArgs a, float* dw, int lddw, int n_val
                     size_t ws_bytes, cudaStream_t s);
 int launch_tail_dgrad(const float* dy, int lddy, int ny, const float* pre, int ldpre, int act, const float* wtail, int wt_sn,
                       int wt_st, int kt, int64_t rows, float* out, int ldo, cudaStream_t s);
+#ifdef MGB_TIMELINE
+int set_timeline_buffer(long long* p);
+#endif
 // umma_selftest.cu
 int umma_selftest(const float* a, const float* b, int a_mn, int b_mn, int lbo_mn, int sbo_mn, float* d, cudaStream_t s);
 
