@@ -162,7 +162,8 @@ def workload_config(n_gpus, note=None):
     c = {"workload": "mpnn_2d processor (5x GNN_Layer, hidden 128, tw 10) on synthetic 2-D irregular-uniform "
                      "64x64-point meshes, BASELINE configs[1]",
          "samples_per_gpu": SAMPLES_PER_GPU, "nodes_per_sample": NODES_PER_SAMPLE, "radius": RADIUS,
-         "max_num_neighbors": 32, "layers": N_LAYERS, "parallelism": f"samples sharded over {n_gpus} GPU(s), no data-path collective",
+         "max_num_neighbors": 32, "layers": N_LAYERS, "parallelism": f"samples sharded over {n_gpus} GPU(s), no data-path collective"
+                        + ("; one NCCL all-reduce of the flat gradient buffer per step" if n_gpus > 1 else ""),
          "l2": "working set per layer (~1 GB) exceeds the 126 MB L2; no explicit flush"}
     if note:
         c["note"] = note
@@ -242,7 +243,7 @@ def ncu_traffic():
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from magnet_b200 import _lib, graph as MG, functional as MF
+    from magnet_b200 import _lib, graph as MG, functional as MF, distributed as D
     from magnet_b200.mpnn import GNN_Layer
     MF.set_precision(args.precision)
     torch.cuda.set_device(local_rank)
@@ -271,6 +272,8 @@ def run_ours(args, rank, world, local_rank):
         for m in layers:
             out = m(out, u, pos, var, ei, batch, plan=plan, segments=seg)
         out.backward(gy)
+        if world > 1:          # training-step semantics: one flat-buffer NCCL all-reduce of the layer gradients per step
+            D.allreduce_gradients(params, world)
         for p in params:
             p.grad = None
         return out
