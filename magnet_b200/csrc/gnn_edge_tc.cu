@@ -214,8 +214,14 @@ constexpr size_t edge_fwd_tc_smem() {
     return 1024 + (size_t)NSPLIT * TILE_BYTES * (1 + TC_STAGES) + META_STAGES * sizeof(TileMeta) + 256;
 }
 
+// forward warp roles: 0-7 epilogue (warps 0-3 own edge positions 0-63 of the tile, warps 4-7 positions 64-127),
+// 8 MMA issue, 9 metadata, 10-17 producers
+constexpr int FW_EPI_WARPS = 8, FW_MMA_WARP = 8, FW_META_WARP = 9, FW_PROD_WARP0 = 10;
+constexpr int FW_THREADS = (FW_PROD_WARP0 + TC_PROD_WARPS) * 32;     // 576
+constexpr int FW_FLUSH_TE = 64;
+
 template <int NSPLIT, bool FAST>
-__global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const EdgeFwdTcArgs a) {
+__global__ void __launch_bounds__(FW_THREADS, 1) gnn_edge_fwd_tc_kernel(const EdgeFwdTcArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = umma::smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -240,24 +246,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
             umma::mbar_init(&full[s], TC_PROD_WARPS * 32);
             umma::mbar_init(&empty[s], 1);
             umma::mbar_init(&tfull[s], 1);
-            umma::mbar_init(&tempty[s], TC_EPI_WARPS * 32);
+            umma::mbar_init(&tempty[s], FW_EPI_WARPS * 32);
         }
         for (int s = 0; s < META_STAGES; ++s) {
             umma::mbar_init(&mfull[s], 32);
-            umma::mbar_init(&mempty[s], TC_EPI_WARPS * 32);
+            umma::mbar_init(&mempty[s], FW_EPI_WARPS * 32);
         }
         umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == TC_MMA_WARP) umma::tmem_alloc(tmem_slot, 256);
+    if (warp == FW_MMA_WARP) umma::tmem_alloc(tmem_slot, 256);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < TC_EPI_WARPS) {
+    if (warp < FW_EPI_WARPS) {
         // =========================== epilogue: thread = output channel n ===========================
-        const int n = tid;
+        const int n = tid & 127;
+        const int pos0 = (warp >> 2) * 64;      // this warp's half of the tile
         const float bias = a.b2[n];
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -270,16 +277,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
             umma::tc_fence_after();
             float sum = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < TCE; c0 += 32) {
+            for (int c0 = pos0; c0 < pos0 + 64; c0 += 32) {
                 float v[32];
-                umma::tmem_ld32(tmem + (uint32_t)(acc * TCE) + ((uint32_t)(warp * 32) << 16) + c0, v);
-                if (c0 + 32 >= TCE) {          // accumulator fully drained into registers: hand it back
+                umma::tmem_ld32(tmem + (uint32_t)(acc * TCE) + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+                if (c0 + 32 >= pos0 + 64) {          // accumulator fully drained into registers: hand it back
                     umma::tc_fence_before();
                     umma::mbar_arrive(&tempty[acc]);
                 }
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = swish_tc<FAST>(v[i] + bias);
-                const uint32_t em = M->endmask[c0 >> 5];
+                const uint32_t em = M->flushmask[c0 >> 5];
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
                     const uint32_t eq = (em >> (8 * qd)) & 0xffu;
@@ -301,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
             }
             umma::mbar_arrive(&mempty[ms]);
         }
-    } else if (warp == TC_MMA_WARP) {
+    } else if (warp == FW_MMA_WARP) {
         // =========================== MMA issue ====================================================
         if (lane == 0) load_w2_image(w_img, a.w2img, NSPLIT * TILE_BYTES, wbar);
         umma::mbar_wait(wbar, 0);
@@ -335,18 +342,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
             }
             __syncwarp();
         }
-    } else if (warp == TC_META_WARP) {
+    } else if (warp == FW_META_WARP) {
         // =========================== segment metadata, META_STAGES tiles ahead =====================
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ms = it % META_STAGES;
             umma::mbar_wait(&mempty[ms], ((it / META_STAGES) & 1) ^ 1);
-            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.agg, TCH, true, a.part_head, a.part_tail, TCE);
+            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.agg, TCH, true, a.part_head, a.part_tail, FW_FLUSH_TE);
             umma::mbar_arrive(&mfull[ms]);
         }
     } else {
         // =========================== producers: 16 consecutive edge rows per warp ===================
-        const int pw = warp - TC_PROD_WARP0;
+        const int pw = warp - FW_PROD_WARP0;
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
@@ -359,11 +366,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == TC_MMA_WARP) umma::tmem_dealloc(tmem, 256);
+    if (warp == FW_MMA_WARP) umma::tmem_dealloc(tmem, 256);
 }
 
 size_t edge_fwd_tc_workspace(int64_t n_edges) {
-    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TCE);
+    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, FW_FLUSH_TE);
     return 2 * align_up((size_t)tiles * TCH * sizeof(float)) + 512;
 }
 
@@ -373,9 +380,10 @@ int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, co
                        cudaStream_t s) {
     if (n_edges <= 0) return MGB_OK;
     const int64_t tiles = ceil_div<int64_t>(n_edges, TCE);
+    const int64_t subtiles = ceil_div<int64_t>(n_edges, FW_FLUSH_TE);
     Workspace ws(ws_ptr, ws_bytes);
-    float* part_head = ws.take<float>((size_t)tiles * TCH);
-    float* part_tail = ws.take<float>((size_t)tiles * TCH);
+    float* part_head = ws.take<float>((size_t)subtiles * TCH);
+    float* part_tail = ws.take<float>((size_t)subtiles * TCH);
     MGB_WS_CHECK(ws);
     EdgeFwdTcArgs a{pq, rowptr, dstv, srcv, n_edges, (const unsigned char*)w2img, b2, agg, part_head, part_tail};
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
@@ -384,16 +392,16 @@ int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, co
         if (precision == 2) {
             constexpr size_t smem = edge_fwd_tc_smem<1>();
             MGB_CUDA(cudaFuncSetAttribute(gnn_edge_fwd_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gnn_edge_fwd_tc_kernel<1, true><<<grid, TC_THREADS, smem, s>>>(a);
+            gnn_edge_fwd_tc_kernel<1, true><<<grid, FW_THREADS, smem, s>>>(a);
         } else {
             constexpr size_t smem = edge_fwd_tc_smem<2>();
             MGB_CUDA(cudaFuncSetAttribute(gnn_edge_fwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            gnn_edge_fwd_tc_kernel<2, false><<<grid, TC_THREADS, smem, s>>>(a);
+            gnn_edge_fwd_tc_kernel<2, false><<<grid, FW_THREADS, smem, s>>>(a);
         }
     }
     MGB_LAUNCH_CHECK();
-    if (tiles > 1) {
-        segment_fixup_tc_kernel<<<(unsigned)(tiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, TCE, part_head, part_tail, agg, TCH, 1);
+    if (subtiles > 1) {
+        segment_fixup_tc_kernel<<<(unsigned)(subtiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, FW_FLUSH_TE, part_head, part_tail, agg, TCH, 1);
         MGB_LAUNCH_CHECK();
     }
     return MGB_OK;
