@@ -71,33 +71,36 @@ segment_fixup_tc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __res
 }
 
 // ---- per-tile segment metadata, produced ahead of time by the meta warp ----------------------------------
-struct TileMeta {
-    int dst[TCE];          // destination node of every position (-1 past the end of the edge list)
-    int src[TCE];
-    float scale[TCE];      // at segment-END positions: factor applied to the segment sum before it is stored
+template <int TE>
+struct alignas(16) TileMetaT {
+    int dst[TE];           // destination node of every position (-1 past the end of the edge list)
+    int src[TE];
+    float scale[TE];       // at segment-END positions: factor applied to the segment sum before it is stored
                            // (1/in-degree for a mean over a segment that lies inside the tile, else 1)
-    float* out[TCE];       // at segment-END positions: row (channel 0) the segment sum goes to — the destination's
+    float* out[TE];        // at segment-END positions: row (channel 0) the segment sum goes to — the destination's
                            // output row, or this tile's head / tail partial row when the segment crosses a tile boundary
-    int segdst[TCE];       // the tile's segments in order: destination node, 1 / in-degree
-    float seginv[TCE];
-    uint32_t endmask[4];   // bit p of the 128-bit mask: position p is the last of its segment within the tile
-    uint32_t flushmask[4]; // bit p: a running segment sum is stored after position p (segment ends + sub-tile ends)
+    uint32_t qoff[TE];     // element offset of Q[src] inside pq: max(src, 0) * 256 + 128
+    int segdst[TE];        // the tile's segments in order: destination node, 1 / in-degree
+    float seginv[TE];
+    uint32_t endmask[TE / 32];   // bit p of the mask: position p is the last of its segment within the tile
+    uint32_t flushmask[TE / 32]; // bit p: a running segment sum is stored after position p (segment ends + sub-tile ends)
     int nseg;
-    int pad[3];
 };
+using TileMeta = TileMetaT<TCE>;
 
 // one warp; positions p = j*32 + lane
-__device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dstv,
+template <int TE>
+__device__ __forceinline__ void build_tile_meta(TileMetaT<TE>* M, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dstv,
                                                 const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int lane,
                                                 float* out_base, int ld_out, bool mean, float* part_head, float* part_tail,
                                                 int flush_te) {
-    // flush_te (128 or 64): granularity at which running segment sums are cut and stored; sums cut by a sub-tile
+    // flush_te: granularity at which running segment sums are cut and stored; sums cut by a sub-tile
     // boundary go to that sub-tile's head / tail partial row (sub-tile id = e / flush_te) and are merged by the fix-up kernel
-    const int64_t e0 = tile * TCE;
-    const int64_t e1 = (e0 + TCE < n_edges) ? e0 + TCE : n_edges;
+    const int64_t e0 = tile * TE;
+    const int64_t e1 = (e0 + TE < n_edges) ? e0 + TE : n_edges;
     int base = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < TE / 32; ++j) {
         const int p = j * 32 + lane;
         const int64_t e = e0 + p;
         const bool valid = e < e1;
@@ -116,6 +119,7 @@ __device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __re
         const float inv = 1.0f / (float)(s1 - s0);
         M->dst[p] = d;
         M->src[p] = sidx;
+        M->qoff[p] = (uint32_t)(sidx < 0 ? 0 : sidx) * (2u * TCH) + TCH;
         const int64_t f0 = e0 + (p / flush_te) * flush_te;                 // bounds of this position's sub-tile
         const int64_t f1 = (f0 + flush_te < e1) ? f0 + flush_te : e1;
         const bool inside = (int64_t)s0 >= f0 && (int64_t)s1 <= f1;
@@ -136,24 +140,24 @@ __device__ __forceinline__ void build_tile_meta(TileMeta* M, const int32_t* __re
     if (lane == 0) M->nseg = base;
 }
 
-// Producer warp `pw` of PROD_WARPS fills rows [pw*ROWS, (pw+1)*ROWS) of the edge tile (ROWS = 128 / PROD_WARPS):
-//   h1[e][:] = Swish(P[dst_e] + Q[src_e])  ->  bf16 (hi[/lo]) K-major swizzled image(s).
+// Producer warp `pw` fills rows [pw*ROWS, (pw+1)*ROWS) of an edge tile of TE positions (ROWS = 16 or 32):
+//   h1[e][:] = Swish(P[dst_e] + Q[src_e])  ->  bf16 (hi[/lo]) K-major swizzled image(s) of TE rows (lo image at +img_bytes).
 // The Q-row gathers are issued 16 rows at a time before their first use (one 512-byte coalesced row per
 // load instruction, float4 per lane); the P row is reused while dst stays the same.
-template <int NSPLIT, bool FAST, int PROD_WARPS>
+template <int NSPLIT, bool FAST, int TE, int ROWS>
 __device__ __forceinline__ void produce_h1_rows(const float* __restrict__ pq, const int32_t* __restrict__ dstv,
                                                 const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int pw,
-                                                int lane, uint64_t* empty_bar, uint32_t empty_parity, unsigned char* img) {
-    constexpr int ROWS = TCE / PROD_WARPS;   // 16 or 32
+                                                int lane, uint64_t* empty_bar, uint32_t empty_parity, unsigned char* img,
+                                                uint32_t img_bytes) {
     static_assert(ROWS == 16 || ROWS == 32, "16 or 32 rows per producer warp");
-    const int64_t e0 = tile * TCE + pw * ROWS;
+    const int64_t e0 = tile * TE + pw * ROWS;
     int my_d = -1, my_s = -1;
     if (lane < ROWS && e0 + lane < n_edges) {
         my_d = dstv[e0 + lane];
         my_s = srcv[e0 + lane];
     }
     // byte offset of this lane's 4 channels inside a row of the swizzled image (row & 7 == r & 7 as pw*ROWS % 8 == 0)
-    const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
+    const uint32_t lane_blk = (uint32_t)(lane >> 4) * ((uint32_t)TE * 128u) + (uint32_t)(lane & 1) * 8u;
     const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
     int prev_d = __shfl_sync(0xffffffffu, my_d, 0);
     float4 p = *reinterpret_cast<const float4*>(pq + (int64_t)(prev_d < 0 ? 0 : prev_d) * (2 * TCH) + lane * 4);
@@ -187,7 +191,7 @@ __device__ __forceinline__ void produce_h1_rows(const float* __restrict__ pq, co
                 split2_bf16(h.x, h.y, hi.x, lo.x);
                 split2_bf16(h.z, h.w, hi.y, lo.y);
                 *reinterpret_cast<uint2*>(img + off) = hi;
-                *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = lo;
+                *reinterpret_cast<uint2*>(img + img_bytes + off) = lo;
             }
         }
     }
@@ -358,8 +362,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int s = it % TC_STAGES;
             const uint32_t ph = (it / TC_STAGES) & 1;
-            produce_h1_rows<NSPLIT, FAST, TC_PROD_WARPS>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], ph ^ 1,
-                                          b_img + (size_t)s * NSPLIT * TILE_BYTES);
+            produce_h1_rows<NSPLIT, FAST, TCE, TCE / TC_PROD_WARPS>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], ph ^ 1,
+                                                                    b_img + (size_t)s * NSPLIT * TILE_BYTES, TILE_BYTES);
             umma::fence_async_smem();
             umma::mbar_arrive(&full[s]);
         }
@@ -408,17 +412,21 @@ int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, co
 }
 
 // ==================================================================================================
-// Backward (recompute).  Per 128-edge tile, all contractions on the tensor core, transposed so that an
+// Backward (recompute).  Per 64-edge tile, all contractions on the tensor core, transposed so that an
 // epilogue thread owns one channel:
-//   MMA1  D1[n][e] = sum_k W2[n][k] h1[e][k]          A = W2 image (K-major),  B = h1 tile (K-major)
+//   MMA1  D1[n][e] = sum_k W2[n][k] h1[e][k]          A = W2 image (K-major),  B = h1 tile (K-major)       N = 64
 //   epi1  dz2[e][n] = dagg[dst_e][n]/deg * Swish'(D1 + b2[n])  -> DZt tile [n][e] (bf16 hi[/lo]);  db2[n] += dz2
-//   MMA2  D2[k][e] = sum_n W2[n][k] dz2[e][n]         A = W2 image (MN-major), B = DZt tile (MN-major)
-//   MMA3  D3[n][k] += sum_e dz2[e][n] h1[e][k]        A = DZt tile (K-major),  B = h1 tile (MN-major)
+//   MMA2  D2[k][e] = sum_n W2[n][k] dz2[e][n]         A = W2 image (MN-major), B = DZt tile (MN-major)     N = 64
+//   MMA3  D3[n][k] += sum_e dz2[e][n] h1[e][k]        A = DZt tile (K-major),  B = h1 tile (MN-major)      K = 64
 //         D3 = dW2 accumulates in TMEM; two D3 buffers alternate every D3_GROUP tiles and are drained into
 //         the CTA's fp32 partial with round-to-nearest adds (the tensor core's own accumulation truncates,
 //         which would bias a sum over thousands of K-steps past the 1e-5 contract)
 //   epi2  dz1[e][k] = D2 * Swish'(P[dst_e][k] + Q[src_e][k])  -> global dz1 (by-source reduction later)
 //         and the segmented SUM over the dst-sorted positions -> dP[dst]      (no atomics)
+// Every buffer on the path is double-buffered (h1 tile, DZt tile, D1, D2, D3), so the five roles work on
+// different tiles at the same time: producers on t+1/t+2, MMA1 on t+1, epi1 on t, MMA2/3 on t, epi2 on t-1.
+// A 64-edge tile keeps all of it inside 227 KB of shared memory (W2 64 KB + h1 2x32 KB + DZt 2x32 KB in the
+// hi/lo mode) and 512 TMEM columns (D1 2x64, D2 2x64, D3 2x128).
 // ==================================================================================================
 #ifdef MGB_TIMELINE
 __device__ long long* g_timeline = nullptr;      // [role 0..4][it 0..15][event 0..3]
@@ -442,74 +450,136 @@ struct EdgeBwdTcArgs {
     float* part_head;
     float* part_tail;
     float* dw2_partial;      // [grid][128][128]
-    float* db2_partial;      // [grid][128]
+    float* db2_partial;      // [grid][2][128]
 };
 
-constexpr int BWD_NPRE = 8;      // segments per tile whose dagg / P rows are prefetched into shared memory
-template <int NSPLIT>
-constexpr int edge_bwd_tc_stages() { return NSPLIT == 1 ? 2 : 1; }
-template <int NSPLIT>
-constexpr int edge_bwd_meta_stages() { return NSPLIT == 1 ? 4 : 2; }
+constexpr int BTE = 64;                       // edge positions per backward tile
+constexpr int BW_HB = BTE * 256;              // bytes of one h1 image [64 e][128 k] bf16 (two 64-row swizzle blocks)
+constexpr int BW_ZB = TCH * 128;              // bytes of one DZt image [128 n][64 e] bf16 (one 128-row swizzle block)
+constexpr int BWD_NPRE = 6;                   // segments per half tile whose dagg / P rows are prefetched into shared memory
+constexpr int BW_MSTAGES = 4;
+// per-tile segment metadata of the backward kernel (see TileMetaT; only what the two epilogues read)
+struct alignas(16) BwdMeta {
+    uint32_t qoff[BTE];    // element offset of Q[src] inside pq: max(src, 0) * 256 + 128
+    float* out[BTE];       // at flush positions: row (channel 0) the running sum goes to
+    int segdst[BTE];       // the tile's segments in order: destination node, 1 / in-degree
+    float seginv[BTE];
+    uint32_t endmask[BTE / 32];
+    uint32_t flushmask[BTE / 32];
+    int nseg;
+};
+__device__ __forceinline__ void build_bwd_meta(BwdMeta* M, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dstv,
+                                               const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int lane,
+                                               float* out_base, int ld_out, float* part_head, float* part_tail, int flush_te) {
+    const int64_t e0 = tile * BTE;
+    const int64_t e1 = (e0 + BTE < n_edges) ? e0 + BTE : n_edges;
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < BTE / 32; ++j) {
+        const int p = j * 32 + lane;
+        const int64_t e = e0 + p;
+        const bool valid = e < e1;
+        const int d = valid ? dstv[e] : -1;
+        const int sidx = valid ? srcv[e] : 0;
+        const int nxt = (valid && e + 1 < e1) ? dstv[e + 1] : -2;
+        const int prv = (valid && p > 0) ? dstv[e - 1] : -2;
+        const bool is_end = valid && nxt != d;
+        const bool is_start = valid && prv != d;
+        const bool is_flush = is_end || (valid && (p % flush_te) == flush_te - 1);
+        int s0 = 0, s1 = 1;
+        if (is_flush || is_start) {
+            s0 = rowptr[d];
+            s1 = rowptr[d + 1];
+        }
+        M->qoff[p] = (uint32_t)sidx * (2u * TCH) + TCH;
+        const int64_t f0 = e0 + (p / flush_te) * flush_te;                 // bounds of this position's sub-tile
+        const int64_t f1 = (f0 + flush_te < e1) ? f0 + flush_te : e1;
+        const bool inside = (int64_t)s0 >= f0 && (int64_t)s1 <= f1;
+        if (is_flush)
+            M->out[p] = inside ? out_base + (int64_t)d * ld_out : ((int64_t)s0 < f0 ? part_head : part_tail) + (f0 / flush_te) * TCH;
+        const uint32_t em = __ballot_sync(0xffffffffu, is_end);
+        const uint32_t fm = __ballot_sync(0xffffffffu, is_flush);
+        const uint32_t sm = __ballot_sync(0xffffffffu, is_start);
+        if (lane == 0) { M->endmask[j] = em; M->flushmask[j] = fm; }
+        if (is_start) {
+            const int idx = base + __popc(sm & ((1u << lane) - 1u));
+            M->segdst[idx] = d;
+            M->seginv[idx] = 1.0f / (float)(s1 - s0);
+        }
+        base += __popc(sm);
+    }
+    if (lane == 0) M->nseg = base;
+}
+// 4-byte asynchronous copy global -> shared (no register staging); visible to the issuing thread after cp_async_wait_all
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(umma::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 template <int NSPLIT>
 constexpr size_t edge_bwd_tc_smem() {
-    return 1024 + (size_t)NSPLIT * TILE_BYTES * (2 + edge_bwd_tc_stages<NSPLIT>()) +
-           edge_bwd_meta_stages<NSPLIT>() * sizeof(TileMeta) + 3 * BWD_NPRE * TCH * sizeof(float) + 256;
+    return 1024 + (size_t)NSPLIT * TILE_BYTES + (size_t)2 * NSPLIT * BW_HB + (size_t)2 * NSPLIT * BW_ZB +
+           BW_MSTAGES * sizeof(BwdMeta) + 8 * BWD_NPRE * TCH * sizeof(float) + 512;
 }
 
 // warp roles of the backward kernel: 0-3 epilogue 1 (dz2, dW2 drain); 4-11 epilogue 2 (dz1, dP; warps 4-7 own edge
-// positions 0-63 of the tile, warps 8-11 positions 64-127); 12 MMA; 13 metadata; 14-17 producers
-constexpr int BW_MMA_WARP = 12, BW_META_WARP = 13, BW_PROD_WARP0 = 14, BW_PROD_WARPS = 4;
-constexpr int BW_THREADS = (BW_PROD_WARP0 + BW_PROD_WARPS) * 32;     // 576
-constexpr int BW_FLUSH_TE = 64;
+// positions 0-31 of the tile, warps 8-11 positions 32-63); 12 MMA; 13 metadata; 14-21 producers (two groups of four
+// warps, group g fills stage g for the tiles with (it & 1) == g, 16 rows per warp)
+constexpr int BW_E1_WARPS = 8, BW_E2_WARPS = 8;
+constexpr int BW_MMA_WARP = 16, BW_META_WARP = 17, BW_PROD_WARP0 = 18, BW_PROD_WARPS = 8;
+constexpr int BW_THREADS = (BW_PROD_WARP0 + BW_PROD_WARPS) * 32;     // 704
+constexpr int BW_FLUSH_TE = 32;
+constexpr int BW_D3_GROUP = 8;
 
 template <int NSPLIT, bool FAST>
 __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const EdgeBwdTcArgs a) {
-    constexpr int STAGES = edge_bwd_tc_stages<NSPLIT>();
-    constexpr int MSTAGES = edge_bwd_meta_stages<NSPLIT>();
-    constexpr int D3_GROUP = FAST ? (1 << 30) : 4;
+    constexpr int D3_GROUP = FAST ? (1 << 30) : BW_D3_GROUP;
+    constexpr int NTERM = NSPLIT == 1 ? 1 : 3;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = umma::smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    unsigned char* w_img = base;
-    unsigned char* h_img = w_img + (size_t)NSPLIT * TILE_BYTES;                 // [stage][split]
-    unsigned char* dz_img = h_img + (size_t)STAGES * NSPLIT * TILE_BYTES;       // [split]   DZt[n][e]
-    TileMeta* metas = reinterpret_cast<TileMeta*>(dz_img + (size_t)NSPLIT * TILE_BYTES);
-    float* gtab = reinterpret_cast<float*>(metas + MSTAGES);       // [BWD_NPRE][128]  dagg[segdst]/deg
-    float* ptab_all = gtab + BWD_NPRE * TCH;                       // [2 halves][BWD_NPRE][128]  P[segdst]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(ptab_all + 2 * BWD_NPRE * TCH);
-    uint64_t* full = bars;               // [2] producers -> MMA (h1 tile ready)
-    uint64_t* empty = bars + 2;          // [2] MMA3 done -> producers
-    uint64_t* d1_full = bars + 4;        // MMA1 done -> epilogue
-    uint64_t* dz_full = bars + 5;        // epilogue wrote DZt -> MMA
-    uint64_t* dz_empty = bars + 6;       // MMA2+MMA3 done reading DZt -> epilogue
-    uint64_t* d2_full = bars + 7;        // MMA2 done -> epilogue
-    uint64_t* d2_empty = bars + 8;       // epilogue drained D2 -> MMA
-    uint64_t* d3_full = bars + 9;        // [2] a D3 group is complete -> epilogue
-    uint64_t* d3_empty = bars + 11;      // [2] epilogue drained D3 buffer -> MMA
-    uint64_t* mfull = bars + 13;         // [MSTAGES]
-    uint64_t* mempty = bars + 13 + MSTAGES;
-    uint64_t* wbar = bars + 13 + 2 * MSTAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14 + 2 * MSTAGES);
+    unsigned char* w_img = base;                                              // [split]
+    unsigned char* h_img = w_img + (size_t)NSPLIT * TILE_BYTES;               // [stage][split]   h1[e][k]
+    unsigned char* dz_img = h_img + (size_t)2 * NSPLIT * BW_HB;               // [stage][split]   DZt[n][e]
+    BwdMeta* metas = reinterpret_cast<BwdMeta*>(dz_img + (size_t)2 * NSPLIT * BW_ZB);
+    float* gtab_all = reinterpret_cast<float*>(metas + BW_MSTAGES);    // [2 buffers][2 halves][BWD_NPRE][128]  dagg[segdst]
+    float* ptab_all = gtab_all + 4 * BWD_NPRE * TCH;                   // [2 buffers][2 halves][BWD_NPRE][128]  P[segdst]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ptab_all + 4 * BWD_NPRE * TCH);
+    uint64_t* h_full = bars;             // [2] producers -> MMA (h1 tile ready)
+    uint64_t* h_empty = bars + 2;        // [2] MMA3 done -> producers
+    uint64_t* d1_full = bars + 4;        // [2] MMA1 done -> epilogue 1
+    uint64_t* d1_empty = bars + 6;       // [2] epilogue 1 drained D1 -> MMA
+    uint64_t* dz_full = bars + 8;        // [2] epilogue 1 wrote DZt -> MMA
+    uint64_t* dz_empty = bars + 10;      // [2] MMA2+MMA3 done reading DZt -> epilogue 1
+    uint64_t* d2_full = bars + 12;       // [2] MMA2 done -> epilogue 2
+    uint64_t* d2_empty = bars + 14;      // [2] epilogue 2 drained D2 -> MMA
+    uint64_t* d3_full = bars + 16;       // [2] a D3 group is complete -> epilogue 1
+    uint64_t* d3_empty = bars + 18;      // [2] epilogue 1 drained D3 buffer -> MMA
+    uint64_t* mfull = bars + 20;         // [BW_MSTAGES]
+    uint64_t* mempty = bars + 20 + BW_MSTAGES;
+    uint64_t* wbar = bars + 20 + 2 * BW_MSTAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21 + 2 * BW_MSTAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_tiles = ceil_div<int64_t>(a.n_edges, TCE);
+    const int64_t n_tiles = ceil_div<int64_t>(a.n_edges, BTE);
+    const int nt = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);     // tiles of this CTA (>= 1)
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            umma::mbar_init(&full[s], BW_PROD_WARPS * 32);
-            umma::mbar_init(&empty[s], 1);
+            umma::mbar_init(&h_full[s], BW_PROD_WARPS * 32);
+            umma::mbar_init(&h_empty[s], 1);
+            umma::mbar_init(&d1_full[s], 1);
+            umma::mbar_init(&d1_empty[s], BW_E1_WARPS * 32);
+            umma::mbar_init(&dz_full[s], BW_E1_WARPS * 32);
+            umma::mbar_init(&dz_empty[s], 1);
+            umma::mbar_init(&d2_full[s], 1);
+            umma::mbar_init(&d2_empty[s], BW_E2_WARPS * 32);
             umma::mbar_init(&d3_full[s], 1);
-            umma::mbar_init(&d3_empty[s], TC_EPI_WARPS * 32);
+            umma::mbar_init(&d3_empty[s], BW_E1_WARPS * 32);
         }
-        for (int s = 0; s < MSTAGES; ++s) {
+        for (int s = 0; s < BW_MSTAGES; ++s) {
             umma::mbar_init(&mfull[s], 32);
-            umma::mbar_init(&mempty[s], 3 * TC_EPI_WARPS * 32);
+            umma::mbar_init(&mempty[s], (BW_E1_WARPS + BW_E2_WARPS) * 32);
         }
-        umma::mbar_init(d1_full, 1);
-        umma::mbar_init(dz_full, TC_EPI_WARPS * 32);
-        umma::mbar_init(dz_empty, 1);
-        umma::mbar_init(d2_full, 1);
-        umma::mbar_init(d2_empty, 2 * TC_EPI_WARPS * 32);
         umma::mbar_init(wbar, 1);
         umma::fence_barrier_init();
     }
@@ -518,321 +588,417 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;   // D3 buffers at +256, +384
+    const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;   // D1[s] at +64 s, D2[s] at +128 + 64 s, D3[buf] at +256 + 128 buf
 
-    if (warp < 3 * TC_EPI_WARPS) {
-        // =========================== epilogues: thread = channel; group 0 (warps 0-3) runs epi1 of every tile,
-        // group 1 (warps 4-7) runs epi2, so epi1 of tile t+1 overlaps epi2 of tile t ==============================
-        const int grp_id = warp < TC_EPI_WARPS ? 0 : 1;
-        const int half = warp < 2 * TC_EPI_WARPS ? 0 : 1;       // epilogue 2: which 64 positions of the tile
-        float* ptab = ptab_all + half * BWD_NPRE * TCH;         // the two halves run independently: own table each
+    if (warp < BW_E1_WARPS) {
+        // =========================== epilogue 1: thread = channel n; warps 0-3 positions 0-31, warps 4-7 positions 32-63
+        const int half = warp >> 2;
+        const int pos0 = half * 32;
         const int n = tid & 127;
         const float bias = a.b2[n];
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        float* dw_out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH;
+        float* gtab = gtab_all + half * BWD_NPRE * TCH + n;    // [buffer][half][segment][channel]: own column per thread
+        float* dw_out = a.dw2_partial + ((int64_t)blockIdx.x * TCH + n) * TCH + half * 64;
+        const float* dagg_n = a.dagg + n;
         float db = 0.f;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t ph = it & 1;
-            const int64_t e0 = tile * TCE;
-            const int ne = (int)((a.n_edges - e0) < (int64_t)TCE ? (a.n_edges - e0) : (int64_t)TCE);
-            const int ms = it % MSTAGES;
-            const TileMeta* M = metas + ms;
-            umma::mbar_wait(&mfull[ms], (it / MSTAGES) & 1);
-            const int nseg = M->nseg;
-            // prefetch the per-segment rows this thread needs (independent loads; own column of the group's table)
-            {
-                float tv[BWD_NPRE];
-#pragma unroll
-                for (int j = 0; j < BWD_NPRE; ++j) {          // all loads issued before the first use
-                    const int jj = j < nseg ? j : nseg - 1;
-                    const int d = M->segdst[jj];
-                    tv[j] = grp_id == 0 ? a.dagg[(int64_t)d * a.ld_dagg + n] * M->seginv[jj] : a.pq[(int64_t)d * (2 * TCH) + n];
+        auto drain_d3 = [&](int grp) {
+            // a finished D3 group -> this CTA's fp32 partial (round-to-nearest adds); this half owns 64 of the 128 columns
+            const int buf = grp & 1;
+            umma::mbar_wait(&d3_full[buf], (grp >> 1) & 1);
+            umma::tc_fence_after();
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 16) {
+                float v[16];
+                umma::tmem_ld16(tm_d3 + (uint32_t)(buf * 128 + half * 64) + lane_base + c0, v);
+                if (c0 + 16 >= 64) {
+                    umma::tc_fence_before();
+                    umma::mbar_arrive(&d3_empty[buf]);
                 }
-                float* tab = grp_id == 0 ? gtab : ptab;
+                float4* o = reinterpret_cast<float4*>(dw_out + c0);
 #pragma unroll
-                for (int j = 0; j < BWD_NPRE; ++j) tab[j * TCH + n] = tv[j];
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                    if (grp > 0) {
+                        const float4 old = o[q4];
+                        w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                    }
+                    o[q4] = w;
+                }
             }
-            auto seg_g = [&](int j) -> float {
-                if (j >= nseg) return 0.f;
-                if (j < BWD_NPRE) return gtab[j * TCH + n];
-                return a.dagg[(int64_t)M->segdst[j] * a.ld_dagg + n] * M->seginv[j];
-            };
-            auto seg_p = [&](int j) -> float {
-                if (j >= nseg) return 0.f;
-                if (j < BWD_NPRE) return ptab[j * TCH + n];
-                return a.pq[(int64_t)M->segdst[j] * (2 * TCH) + n];
-            };
-            if (grp_id == 0) {
+        };
+        // dagg[dst] of the first BWD_NPRE segments of this half goes global -> shared (cp.async, no registers) one tile
+        // ahead, into the other buffer of the table
+        auto prefetch_tab = [&](const BwdMeta* M, int buf) {
+            const int nseg = M->nseg;
+            const int j0 = half ? __popc(M->endmask[0]) : 0;
+            float* dstp = gtab + buf * (2 * BWD_NPRE * TCH);
+#pragma unroll
+            for (int j = 0; j < BWD_NPRE; ++j) {
+                int jj = j0 + j;
+                jj = jj < nseg ? jj : nseg - 1;
+                cp_async4(dstp + j * TCH, dagg_n + (int64_t)M->segdst[jj] * a.ld_dagg);
+            }
+        };
+        umma::mbar_wait(&mfull[0], 0);
+        prefetch_tab(metas, 0);
+#pragma unroll 1
+        for (int it = 0; it < nt; ++it) {
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int ms = it % BW_MSTAGES;
+            const BwdMeta* M = metas + ms;
+            unsigned char* dz_row = dz_img + (size_t)s * NSPLIT * BW_ZB + n * 128;
+            const float* gt = gtab + s * (2 * BWD_NPRE * TCH);
+            const int nseg = M->nseg;
+            const int j0 = half ? __popc(M->endmask[0]) : 0;     // segment that contains position pos0
+            cp_async_wait_all();
+            if (it + 1 < nt) {
+                const int ms1 = (it + 1) % BW_MSTAGES;
+                umma::mbar_wait(&mfull[ms1], ((it + 1) / BW_MSTAGES) & 1);
+                prefetch_tab(metas + ms1, s ^ 1);
+            }
             if (warp == 0) TL(2, it, 0);
-            // ---- epi1: dz2 = dagg[dst]/deg * Swish'(z2) -> DZt (rows = channel, cols = edge) ----
-            umma::mbar_wait(d1_full, ph);
+            umma::mbar_wait(&d1_full[s], ph);
             if (warp == 0) TL(2, it, 1);
-            umma::mbar_wait(dz_empty, ph ^ 1);
+            umma::mbar_wait(&dz_empty[s], ph ^ 1);
             umma::tc_fence_after();
             if (warp == 0) TL(2, it, 2);
-            {
-                int j = 0;
-                float g = seg_g(0);
+            int j = j0;
+            float g = j < nseg ? gt[0] * M->seginv[j] : 0.f;
+            const uint32_t emw = M->endmask[half];
 #pragma unroll 1
-                for (int c0 = 0; c0 < TCE; c0 += 32) {
-                    float v[32];
-                    umma::tmem_ld32(tm_d1 + lane_base + c0, v);
+            for (int cb = 0; cb < 32; cb += 8) {
+                const int c0 = pos0 + cb;
+                float v[8];
+                umma::tmem_ld8(tm_d1 + (uint32_t)(s * BTE) + lane_base + c0, v);
+                if (cb + 8 >= 32) {              // this thread's part of D1[s] is in registers: MMA1 of tile it+2 may overwrite it
+                    umma::tc_fence_before();
+                    umma::mbar_arrive(&d1_empty[s]);
+                }
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = swish_grad_tc<FAST>(v[i] + bias);
-                    const uint32_t em = M->endmask[c0 >> 5];
+                for (int i = 0; i < 8; ++i) v[i] = swish_grad_tc<FAST>(v[i] + bias);
+                // dagg[dst]/deg is constant along a segment: one pass per segment that intersects the chunk (usually one)
+                uint32_t em = (emw >> cb) & 0xffu, todo = 0xffu;
+                while (true) {
+                    const uint32_t upto = em ? (((em & (0u - em)) << 1) - 1u) : 0xffu;
+                    const uint32_t rng = todo & upto;
 #pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const uint32_t eq = (em >> (8 * qd)) & 0xffu;
-                        float* w = v + 8 * qd;
-                        if (eq == 0) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) w[i] *= g;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                w[i] *= g;
-                                if (eq & (1u << i)) g = seg_g(++j);
-                            }
-                        }
-                        db += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
-                    }
-#pragma unroll
-                    for (int q8 = 0; q8 < 4; ++q8) {
-                        const uint32_t off = umma::tile_off(128, n, c0 + 8 * q8);
-                        uint4 hi, lo;
-                        if (NSPLIT == 1) {
-                            hi.x = umma::pack_bf16(v[8 * q8 + 0], v[8 * q8 + 1]);
-                            hi.y = umma::pack_bf16(v[8 * q8 + 2], v[8 * q8 + 3]);
-                            hi.z = umma::pack_bf16(v[8 * q8 + 4], v[8 * q8 + 5]);
-                            hi.w = umma::pack_bf16(v[8 * q8 + 6], v[8 * q8 + 7]);
-                            *reinterpret_cast<uint4*>(dz_img + off) = hi;
-                        } else {
-                            split2_bf16(v[8 * q8 + 0], v[8 * q8 + 1], hi.x, lo.x);
-                            split2_bf16(v[8 * q8 + 2], v[8 * q8 + 3], hi.y, lo.y);
-                            split2_bf16(v[8 * q8 + 4], v[8 * q8 + 5], hi.z, lo.z);
-                            split2_bf16(v[8 * q8 + 6], v[8 * q8 + 7], hi.w, lo.w);
-                            *reinterpret_cast<uint4*>(dz_img + off) = hi;
-                            *reinterpret_cast<uint4*>(dz_img + TILE_BYTES + off) = lo;
-                        }
-                    }
+                    for (int i = 0; i < 8; ++i)
+                        if (rng & (1u << i)) v[i] *= g;
+                    if (!em) break;
+                    todo &= ~upto;
+                    em &= em - 1;
+                    ++j;
+                    g = j >= nseg ? 0.f : (j - j0 < BWD_NPRE ? gt[(j - j0) * TCH] : dagg_n[(int64_t)M->segdst[j] * a.ld_dagg]) * M->seginv[j < nseg ? j : 0];
+                }
+                db += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                const uint32_t off = (uint32_t)(((c0 >> 3) ^ (n & 7)) << 4);
+                uint4 hi, lo;
+                if (NSPLIT == 1) {
+                    hi.x = umma::pack_bf16(v[0], v[1]);
+                    hi.y = umma::pack_bf16(v[2], v[3]);
+                    hi.z = umma::pack_bf16(v[4], v[5]);
+                    hi.w = umma::pack_bf16(v[6], v[7]);
+                    *reinterpret_cast<uint4*>(dz_row + off) = hi;
+                } else {
+                    split2_bf16(v[0], v[1], hi.x, lo.x);
+                    split2_bf16(v[2], v[3], hi.y, lo.y);
+                    split2_bf16(v[4], v[5], hi.z, lo.z);
+                    split2_bf16(v[6], v[7], hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(dz_row + off) = hi;
+                    *reinterpret_cast<uint4*>(dz_row + BW_ZB + off) = lo;
                 }
             }
             umma::fence_async_smem();
             umma::tc_fence_before();
-            umma::mbar_arrive(dz_full);
+            umma::mbar_arrive(&dz_full[s]);
             if (warp == 0) TL(2, it, 3);
-            // ---- drain a finished D3 group into this CTA's fp32 partial (round-to-nearest adds) ----
             umma::mbar_arrive(&mempty[ms]);
-            const bool last = tile + gridDim.x >= n_tiles;
-            if ((it % D3_GROUP) == D3_GROUP - 1 || last) {
-                const int grp = it / D3_GROUP, buf = grp & 1;
-                umma::mbar_wait(&d3_full[buf], (grp >> 1) & 1);
-                umma::tc_fence_after();
-#pragma unroll 1
-                for (int c0 = 0; c0 < TCH; c0 += 32) {
-                    float v[32];
-                    umma::tmem_ld32(tm_d3 + (uint32_t)(buf * 128) + lane_base + c0, v);
-                    if (c0 + 32 >= TCH) {
-                        umma::tc_fence_before();
-                        umma::mbar_arrive(&d3_empty[buf]);
-                    }
-                    float4* o = reinterpret_cast<float4*>(dw_out + c0);
+            // D3 drains run one tile late (MMA3 of the group's last tile has finished by then), except at the very end
+            if (it > 0 && ((it - 1) % D3_GROUP) == D3_GROUP - 1) drain_d3((it - 1) / D3_GROUP);
+            if (it == nt - 1) drain_d3(it / D3_GROUP);
+        }
+        a.db2_partial[((int64_t)blockIdx.x * 2 + half) * TCH + n] = db;
+    } else if (warp < BW_E1_WARPS + BW_E2_WARPS) {
+        // =========================== epilogue 2: thread = channel k; warps 8-11 positions 0-31, warps 12-15 positions 32-63
+        const int half = (warp - BW_E1_WARPS) >> 2;
+        const int pos0 = half * 32;
+        const int n = tid & 127;
+        float* ptab = ptab_all + half * BWD_NPRE * TCH + n;     // [buffer][half][segment][channel]: own column per thread
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float* pq_n = a.pq + n;
+        // P[dst] of the first BWD_NPRE segments of this half: global -> shared (cp.async) one tile ahead
+        auto prefetch_tab = [&](const BwdMeta* M, int buf) {
+            const int nseg = M->nseg;
+            const int j0 = half ? __popc(M->endmask[0]) : 0;
+            float* dstp = ptab + buf * (2 * BWD_NPRE * TCH);
 #pragma unroll
-                    for (int q4 = 0; q4 < 8; ++q4) {
-                        float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-                        if (grp > 0) {
-                            const float4 old = o[q4];
-                            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-                        }
-                        o[q4] = w;
-                    }
-                }
+            for (int j = 0; j < BWD_NPRE; ++j) {
+                int jj = j0 + j;
+                jj = jj < nseg ? jj : nseg - 1;
+                cp_async4(dstp + j * TCH, pq_n + (int64_t)M->segdst[jj] * (2 * TCH));
             }
-            } else {
-            // ---- epi2: dz1 = dh1 * Swish'(z1) -> global + segmented sum by destination -> dP ----
-            {
-                const int pos0 = half * 64;
-                int j = half ? __popc(M->endmask[0]) + __popc(M->endmask[1]) : 0;     // segment that contains position pos0
-                float pk = seg_p(j);
-                float sum = 0.f;
-                const bool full_tile = ne == TCE;
-                auto load_q = [&](float (&q)[16], int c0) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int sidx = M->src[c0 + i];
-                        q[i] = a.pq[(int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + n];
-                    }
-                };
-                auto process = [&](float (&q)[16], int c0) {
-                    float v[16];
-                    umma::tmem_ld16(tm_d2 + lane_base + c0, v);
-                    if (c0 + 16 >= pos0 + 64) {
-                        umma::tc_fence_before();
-                        umma::mbar_arrive(d2_empty);
-                    }
-                    if (c0 >= ne) return;
-                    const uint32_t em = (M->endmask[c0 >> 5] >> (c0 & 16)) & 0xffffu;
-                    const uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 16)) & 0xffffu;
-#pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
-                        const uint32_t eq = (em >> (8 * h8)) & 0xffu;
-                        float* w = q + 8 * h8;
-                        if (eq == 0) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) w[i] += pk;
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                w[i] += pk;
-                                if (eq & (1u << i)) pk = seg_p(++j);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] *= swish_grad_tc<FAST>(q[i]);
-                    float* dzrow = a.dz1 + (e0 + c0) * TCH + n;
-                    if (full_tile) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) dzrow[(int64_t)i * TCH] = v[i];
-                    } else {
-                        const int nvalid = ne - c0;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (i < nvalid) dzrow[(int64_t)i * TCH] = v[i];
-                    }
-#pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
-                        const uint32_t eq = (fm >> (8 * h8)) & 0xffu;
-                        const float* w = v + 8 * h8;
-                        if (eq == 0) {
-                            sum += ((w[0] + w[1]) + (w[2] + w[3])) + ((w[4] + w[5]) + (w[6] + w[7]));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                sum += w[i];
-                                if (eq & (1u << i)) {
-                                    const int pos = c0 + 8 * h8 + i;
-                                    M->out[pos][n] = sum;
-                                    sum = 0.f;
-                                }
-                            }
-                        }
-                    }
-                };
-                // the Q re-gather of the next 16 positions is in flight while the current 16 are processed;
-                // the first batch is issued before waiting for MMA2
-                float qa[16], qb[16];
-                if ((warp & 3) == 0) TL(3 + half, it, 0);
-                load_q(qa, pos0);
-                umma::mbar_wait(d2_full, ph);
-                umma::tc_fence_after();
-                if ((warp & 3) == 0) TL(3 + half, it, 1);
+        };
+        umma::mbar_wait(&mfull[0], 0);
+        prefetch_tab(metas, 0);
 #pragma unroll 1
-                for (int c0 = pos0; c0 < pos0 + 64; c0 += 32) {
-                    load_q(qb, c0 + 16);
-                    process(qa, c0);
-                    if (c0 + 32 < pos0 + 64) load_q(qa, c0 + 32);
-                    process(qb, c0 + 16);
+        for (int it = 0; it < nt; ++it) {
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            const int ms = it % BW_MSTAGES;
+            const BwdMeta* M = metas + ms;
+            const float* pt = ptab + s * (2 * BWD_NPRE * TCH);
+            const int nseg = M->nseg;
+            const int j0 = half ? __popc(M->endmask[0]) : 0;     // segment that contains position pos0
+            // Q re-gather, two 8-position chunks ahead of the chunk being processed; the first two are issued before
+            // MMA2 of the tile is waited for
+            float qn1[8], qn2[8];
+            {
+                const uint4 o0 = *reinterpret_cast<const uint4*>(&M->qoff[pos0]), o1 = *reinterpret_cast<const uint4*>(&M->qoff[pos0 + 4]);
+                const uint4 o2 = *reinterpret_cast<const uint4*>(&M->qoff[pos0 + 8]), o3 = *reinterpret_cast<const uint4*>(&M->qoff[pos0 + 12]);
+                qn1[0] = pq_n[o0.x]; qn1[1] = pq_n[o0.y]; qn1[2] = pq_n[o0.z]; qn1[3] = pq_n[o0.w];
+                qn1[4] = pq_n[o1.x]; qn1[5] = pq_n[o1.y]; qn1[6] = pq_n[o1.z]; qn1[7] = pq_n[o1.w];
+                qn2[0] = pq_n[o2.x]; qn2[1] = pq_n[o2.y]; qn2[2] = pq_n[o2.z]; qn2[3] = pq_n[o2.w];
+                qn2[4] = pq_n[o3.x]; qn2[5] = pq_n[o3.y]; qn2[6] = pq_n[o3.z]; qn2[7] = pq_n[o3.w];
+            }
+            cp_async_wait_all();
+            if (it + 1 < nt) {
+                const int ms1 = (it + 1) % BW_MSTAGES;
+                umma::mbar_wait(&mfull[ms1], ((it + 1) / BW_MSTAGES) & 1);
+                prefetch_tab(metas + ms1, s ^ 1);
+            }
+            int j = j0;
+            float pk = j < nseg ? pt[0] : 0.f;
+            float sum = 0.f;
+            const uint32_t emw = M->endmask[half], fmw = M->flushmask[half];
+            float* dz_tile = a.dz1 + (tile * BTE + pos0) * TCH + n;     // dz1 is padded to whole tiles: no bounds checks
+            if ((warp & 3) == 0) TL(3 + half, it, 0);
+            umma::mbar_wait(&d2_full[s], ph);
+            umma::tc_fence_after();
+            if ((warp & 3) == 0) TL(3 + half, it, 1);
+#pragma unroll 1
+            for (int cb = 0; cb < 32; cb += 8) {
+                float q[8], v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { q[i] = qn1[i]; qn1[i] = qn2[i]; }
+                if (cb + 16 < 32) {
+                    const uint4 o0 = *reinterpret_cast<const uint4*>(&M->qoff[pos0 + cb + 16]);
+                    const uint4 o1 = *reinterpret_cast<const uint4*>(&M->qoff[pos0 + cb + 20]);
+                    qn2[0] = pq_n[o0.x]; qn2[1] = pq_n[o0.y]; qn2[2] = pq_n[o0.z]; qn2[3] = pq_n[o0.w];
+                    qn2[4] = pq_n[o1.x]; qn2[5] = pq_n[o1.y]; qn2[6] = pq_n[o1.z]; qn2[7] = pq_n[o1.w];
                 }
+                umma::tmem_ld8(tm_d2 + (uint32_t)(s * BTE) + lane_base + pos0 + cb, v);
+                if (cb + 8 >= 32) {
+                    umma::tc_fence_before();
+                    umma::mbar_arrive(&d2_empty[s]);
+                }
+                // z1 = P[dst] + Q[src]; P is constant along a segment: one pass per segment that intersects the chunk.
+                // Positions past the end of the edge list carry D2 = 0 and belong to no segment: they store zeros
+                // into the padding of dz1 and add nothing to any sum.
+                uint32_t em = (emw >> cb) & 0xffu, todo = 0xffu;
+                while (true) {
+                    const uint32_t upto = em ? (((em & (0u - em)) << 1) - 1u) : 0xffu;
+                    const uint32_t rng = todo & upto;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (rng & (1u << i)) q[i] += pk;
+                    if (!em) break;
+                    todo &= ~upto;
+                    em &= em - 1;
+                    ++j;
+                    pk = j >= nseg ? 0.f : (j - j0 < BWD_NPRE ? pt[(j - j0) * TCH] : pq_n[(int64_t)M->segdst[j] * (2 * TCH)]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] *= swish_grad_tc<FAST>(q[i]);
+                float* dzrow = dz_tile + cb * TCH;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dzrow[i * TCH] = v[i];
+                // segmented sum over the destination-sorted positions: one pass per stored sum (segment end or sub-tile end)
+                uint32_t fm = (fmw >> cb) & 0xffu;
+                todo = 0xffu;
+                while (fm) {
+                    const uint32_t low = fm & (0u - fm);
+                    const uint32_t upto = (low << 1) - 1u;
+                    const uint32_t rng = todo & upto;
+                    float part = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (rng & (1u << i)) part += v[i];
+                    M->out[pos0 + cb + (31 - __clz(low))][n] = sum + part;
+                    sum = 0.f;
+                    todo &= ~upto;
+                    fm &= fm - 1;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (todo & (1u << i)) sum += v[i];
             }
             if ((warp & 3) == 0) TL(3 + half, it, 2);
             umma::mbar_arrive(&mempty[ms]);
-            }
         }
-        if (grp_id == 0) a.db2_partial[(int64_t)blockIdx.x * TCH + n] = db;
     } else if (warp == BW_MMA_WARP) {
         // =========================== MMA issue ====================================================
         if (lane == 0) load_w2_image(w_img, a.w2img, NSPLIT * TILE_BYTES, wbar);
         umma::mbar_wait(wbar, 0);
-        const uint32_t id_kk = umma::idesc_bf16(128, 128, 0, 0);     // A K-major,  B K-major   (MMA1)
-        const uint32_t id_mm = umma::idesc_bf16(128, 128, 1, 1);     // A MN-major, B MN-major  (MMA2)
-        const uint32_t id_km = umma::idesc_bf16(128, 128, 0, 1);     // A K-major,  B MN-major  (MMA3)
-        const uint32_t w_s = umma::smem_u32(w_img), dz_s = umma::smem_u32(dz_img);
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % STAGES;
-            const uint32_t sph = (it / STAGES) & 1;
-            const uint32_t ph = it & 1;
-            const uint32_t h_s = umma::smem_u32(h_img + (size_t)s * NSPLIT * TILE_BYTES);
+        const uint32_t id_1 = umma::idesc_bf16(128, BTE, 0, 0);     // A K-major,  B K-major   (MMA1)
+        const uint32_t id_2 = umma::idesc_bf16(128, BTE, 1, 1);     // A MN-major, B MN-major  (MMA2)
+        const uint32_t id_3 = umma::idesc_bf16(128, 128, 0, 1);     // A K-major,  B MN-major  (MMA3)
+        // descriptors of k-step 0; a k-step only moves the 14-bit start-address field (bytes >> 4), so the
+        // per-MMA work is one add per operand
+        const uint64_t w_k = umma::desc_sw128(umma::smem_u32(w_img), 16, 1024);             // W2, K-major
+        const uint64_t w_m = umma::desc_sw128(umma::smem_u32(w_img), 128 * 128, 1024);      // W2, MN-major
+        const uint64_t h_k = umma::desc_sw128(umma::smem_u32(h_img), 16, 1024);             // h1[e][k], K-major  (K = k)
+        const uint64_t h_m = umma::desc_sw128(umma::smem_u32(h_img), BTE * 128, 1024);      // h1[e][k], MN-major (K = e)
+        const uint64_t z_k = umma::desc_sw128(umma::smem_u32(dz_img), 16, 1024);            // DZt[n][e], K-major (K = e)
+        const uint64_t z_m = umma::desc_sw128(umma::smem_u32(dz_img), 128 * 128, 1024);     // DZt[n][e], MN-major (K = n)
+        constexpr uint32_t WT = TILE_BYTES >> 4, HS = (NSPLIT * BW_HB) >> 4, HT = BW_HB >> 4, ZS = (NSPLIT * BW_ZB) >> 4,
+                           ZT = BW_ZB >> 4;
+        // MMA1 of tile it+1 is issued before MMA2/MMA3 of tile it: the tensor pipe works on the next tile while
+        // epilogue 1 runs on this one
+#pragma unroll 1
+        for (int it = -1; it < nt; ++it) {
+            if (it + 1 < nt) {
+                const int it1 = it + 1, s1 = it1 & 1;
+                umma::mbar_wait(&h_full[s1], (it1 >> 1) & 1);
+                umma::mbar_wait(&d1_empty[s1], ((it1 >> 1) & 1) ^ 1);
+                umma::tc_fence_after();
+                TL(1, it1, 0);
+                if (umma::elect_one()) {
+                    const uint64_t hb = h_k + (uint64_t)(s1 * HS);
+                    const uint32_t d = tm_d1 + (uint32_t)(s1 * BTE);
+#pragma unroll
+                    for (int term = 0; term < NTERM; ++term) {
+                        const uint64_t wa = w_k + (term == 2 ? WT : 0), hh = hb + (term == 1 ? HT : 0);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma::mma_bf16(d, wa + (uint64_t)((k >> 2) * (128 * 128 >> 4) + (k & 3) * 2),
+                                           hh + (uint64_t)((k >> 2) * (BTE * 128 >> 4) + (k & 3) * 2), id_1, (term | k) ? 1u : 0u);
+                    }
+                    umma::mma_commit(&d1_full[s1]);
+                }
+                __syncwarp();
+            }
+            if (it < 0) continue;
+            const int s = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
             const int grp = it / D3_GROUP, buf = grp & 1;
             const bool first_in_group = (it % D3_GROUP) == 0;
-            const bool last = tile + gridDim.x >= n_tiles;
-            umma::mbar_wait(&full[s], sph);
-            umma::tc_fence_after();
-            TL(1, it, 0);
-            if (lane == 0) {
-                uint32_t accum = 0;
-#pragma unroll
-                for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
-                    const int wa = term == 2 ? 1 : 0, hb = term == 1 ? 1 : 0;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        umma::mma_bf16(tm_d1, umma::desc_kmajor(w_s + wa * TILE_BYTES, k), umma::desc_kmajor(h_s + hb * TILE_BYTES, k),
-                                       id_kk, accum);
-                        accum = 1;
-                    }
-                }
-                umma::mma_commit(d1_full);
-            }
-            __syncwarp();
-            umma::mbar_wait(dz_full, ph);
-            TL(1, it, 1);
-            umma::mbar_wait(d2_empty, ph ^ 1);
-            TL(1, it, 2);
+            const bool last = it == nt - 1;
+            umma::mbar_wait(&dz_full[s], ph);
+            umma::mbar_wait(&d2_empty[s], ph ^ 1);
             if (first_in_group) umma::mbar_wait(&d3_empty[buf], ((grp >> 1) & 1) ^ 1);
             umma::tc_fence_after();
-            if (lane == 0) {
-                uint32_t accum = 0;
+            TL(1, it, 1);
+            if (umma::elect_one()) {
+                const uint64_t hb = h_m + (uint64_t)(s * HS), zk = z_k + (uint64_t)(s * ZS), zm = z_m + (uint64_t)(s * ZS);
+                const uint32_t d2 = tm_d2 + (uint32_t)(s * BTE), d3 = tm_d3 + (uint32_t)(buf * 128);
 #pragma unroll
-                for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
-                    const int wa = term == 2 ? 1 : 0, zb = term == 1 ? 1 : 0;
+                for (int term = 0; term < NTERM; ++term) {
+                    const uint64_t wa = w_m + (term == 2 ? WT : 0), zz = zm + (term == 1 ? ZT : 0);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {     // K = n
-                        umma::mma_bf16(tm_d2, umma::desc_mnmajor(w_s + wa * TILE_BYTES, k), umma::desc_mnmajor(dz_s + zb * TILE_BYTES, k),
-                                       id_mm, accum);
-                        accum = 1;
-                    }
+                    for (int k = 0; k < 8; ++k)     // K = n: 16 rows = 2048 bytes per step
+                        umma::mma_bf16(d2, wa + (uint64_t)(k * 128), zz + (uint64_t)(k * 128), id_2, (term | k) ? 1u : 0u);
                 }
-                umma::mma_commit(d2_full);
-                accum = first_in_group ? 0u : 1u;
+                umma::mma_commit(&d2_full[s]);
 #pragma unroll
-                for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
-                    const int za = term == 2 ? 1 : 0, hb = term == 1 ? 1 : 0;
+                for (int term = 0; term < NTERM; ++term) {
+                    const uint64_t za = zk + (term == 2 ? ZT : 0), hh = hb + (term == 1 ? HT : 0);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {     // K = e
-                        umma::mma_bf16(tm_d3 + (uint32_t)(buf * 128), umma::desc_kmajor(dz_s + za * TILE_BYTES, k),
-                                       umma::desc_mnmajor(h_s + hb * TILE_BYTES, k), id_km, accum);
-                        accum = 1;
-                    }
+                    for (int k = 0; k < BTE / 16; ++k)     // K = e
+                        umma::mma_bf16(d3, za + (uint64_t)(k * 2), hh + (uint64_t)(k * 128), id_3, (term | k) ? 1u : (first_in_group ? 0u : 1u));
                 }
-                umma::mma_commit(&empty[s]);
-                umma::mma_commit(dz_empty);
+                umma::mma_commit(&h_empty[s]);
+                umma::mma_commit(&dz_empty[s]);
                 if ((it % D3_GROUP) == D3_GROUP - 1 || last) umma::mma_commit(&d3_full[buf]);
             }
             __syncwarp();
+            TL(1, it, 2);
         }
     } else if (warp == BW_META_WARP) {
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int ms = it % MSTAGES;
-            umma::mbar_wait(&mempty[ms], ((it / MSTAGES) & 1) ^ 1);
-            build_tile_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.dpq, 2 * TCH, false, a.part_head, a.part_tail, BW_FLUSH_TE);
+        for (int it = 0; it < nt; ++it) {
+            const int ms = it % BW_MSTAGES;
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            umma::mbar_wait_relaxed(&mempty[ms], ((it / BW_MSTAGES) & 1) ^ 1);
+            build_bwd_meta(metas + ms, a.rowptr, a.dstv, a.srcv, a.n_edges, tile, lane, a.dpq, 2 * TCH, a.part_head, a.part_tail, BW_FLUSH_TE);
             umma::mbar_arrive(&mfull[ms]);
         }
     } else {
-        // =========================== producers ====================================================
+        // =========================== producers: 8 rows per warp ====================================
+        // h1[e][:] = Swish(P[dst_e] + Q[src_e]) -> bf16 (hi[/lo]) K-major swizzled image(s).  The eight Q-row gathers of a
+        // tile (one 512-byte coalesced row per load instruction) and its edge indices are issued while the previous
+        // tiles are still in the pipeline, so that only Swish + split + stores follow the stage's release.
         const int pw = warp - BW_PROD_WARP0;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % STAGES;
-            const uint32_t sph = (it / STAGES) & 1;
+        const uint32_t lane_blk = (uint32_t)(lane >> 4) * ((uint32_t)BTE * 128u) + (uint32_t)(lane & 1) * 8u;
+        const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
+        auto load_idx = [&](int it, int& d, int& sidx) {
+            const int64_t e = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * BTE + pw * 8 + lane;
+            d = -1; sidx = -1;
+            if (it < nt && lane < 8 && e < a.n_edges) { d = a.dstv[e]; sidx = a.srcv[e]; }
+        };
+        int d_cur, s_cur, d_nxt, s_nxt;
+        load_idx(0, d_cur, s_cur);
+        load_idx(1, d_nxt, s_nxt);
+        float4 q[8], p0, p1;
+        int pd0, pd1;
+        auto issue_gathers = [&]() {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int sidx = __shfl_sync(0xffffffffu, s_cur, r);
+                q[r] = *reinterpret_cast<const float4*>(a.pq + (int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + lane * 4);
+            }
+            // the P row of the first position and of the first position with another destination (if any)
+            pd0 = __shfl_sync(0xffffffffu, d_cur, 0);
+            const uint32_t chg = __ballot_sync(0xffffffffu, lane < 8 && d_cur != pd0 && d_cur >= 0);
+            pd1 = chg ? __shfl_sync(0xffffffffu, d_cur, __ffs(chg) - 1) : pd0;
+            p0 = *reinterpret_cast<const float4*>(a.pq + (int64_t)(pd0 < 0 ? 0 : pd0) * (2 * TCH) + lane * 4);
+            p1 = *reinterpret_cast<const float4*>(a.pq + (int64_t)(pd1 < 0 ? 0 : pd1) * (2 * TCH) + lane * 4);
+        };
+        issue_gathers();
+#pragma unroll 1
+        for (int it = 0; it < nt; ++it) {
+            const int s = it & 1;
+            unsigned char* img = h_img + (size_t)s * NSPLIT * BW_HB;
             if (pw == 0) TL(0, it, 0);
-            produce_h1_rows<NSPLIT, FAST, BW_PROD_WARPS>(a.pq, a.dstv, a.srcv, a.n_edges, tile, pw, lane, &empty[s], sph ^ 1,
-                                          h_img + (size_t)s * NSPLIT * TILE_BYTES);
+            // Swish + split run before the stage is waited for (results stay in the registers the gathered rows came
+            // in), so only the stores follow the release of the stage
+            uint4 hl[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int d = __shfl_sync(0xffffffffu, d_cur, r);
+                if (d != pd0) {
+                    if (d == pd1) p0 = p1;
+                    else if (d >= 0) p0 = *reinterpret_cast<const float4*>(a.pq + (int64_t)d * (2 * TCH) + lane * 4);
+                    pd0 = d;
+                }
+                float4 h;
+                h.x = swish_tc<FAST>(p0.x + q[r].x);
+                h.y = swish_tc<FAST>(p0.y + q[r].y);
+                h.z = swish_tc<FAST>(p0.z + q[r].z);
+                h.w = swish_tc<FAST>(p0.w + q[r].w);
+                if (d < 0) h = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NSPLIT == 1) {
+                    hl[r].x = umma::pack_bf16(h.x, h.y);
+                    hl[r].y = umma::pack_bf16(h.z, h.w);
+                } else {
+                    split2_bf16(h.x, h.y, hl[r].x, hl[r].z);
+                    split2_bf16(h.z, h.w, hl[r].y, hl[r].w);
+                }
+            }
+            umma::mbar_wait(&h_empty[s], ((it >> 1) & 1) ^ 1);
+            if (pw == 0) TL(0, it, 2);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t off = lane_blk + (uint32_t)(pw * 8 + r) * 128u + ((lane_chunk ^ (uint32_t)r) << 4);
+                *reinterpret_cast<uint2*>(img + off) = make_uint2(hl[r].x, hl[r].y);
+                if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + BW_HB + off) = make_uint2(hl[r].z, hl[r].w);
+            }
             umma::fence_async_smem();
-            umma::mbar_arrive(&full[s]);
+            umma::mbar_arrive(&h_full[s]);
             if (pw == 0) TL(0, it, 1);
+            d_cur = d_nxt; s_cur = s_nxt;
+            if (it + 1 < nt) issue_gathers();
+            load_idx(it + 2, d_nxt, s_nxt);
         }
     }
     umma::tc_fence_before();
@@ -848,7 +1014,7 @@ int set_timeline_buffer(long long* p) {
 #endif
 
 int edge_bwd_tc_grid(int64_t n_edges) {
-    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, TCE);
+    const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, BTE);
     return (int)(tiles < sm_count() ? tiles : sm_count());
 }
 
@@ -856,7 +1022,7 @@ size_t edge_bwd_tc_workspace(int64_t n_edges) {
     const int64_t tiles = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, BW_FLUSH_TE);
     const int grid = edge_bwd_tc_grid(n_edges);
     return 2 * align_up((size_t)tiles * TCH * sizeof(float)) + align_up((size_t)grid * TCH * TCH * sizeof(float)) +
-           align_up((size_t)grid * TCH * sizeof(float)) + 1024;
+           align_up((size_t)grid * 2 * TCH * sizeof(float)) + 1024;
 }
 
 __global__ void __launch_bounds__(256)
@@ -878,7 +1044,7 @@ int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, co
     float* part_head = ws.take<float>((size_t)subtiles * TCH);
     float* part_tail = ws.take<float>((size_t)subtiles * TCH);
     float* dw2_part = ws.take<float>((size_t)grid * TCH * TCH);
-    float* db2_part = ws.take<float>((size_t)grid * TCH);
+    float* db2_part = ws.take<float>((size_t)grid * 2 * TCH);
     MGB_WS_CHECK(ws);
     EdgeBwdTcArgs a{pq, rowptr, dstv, srcv, n_edges, (const unsigned char*)w2img, b2, dagg, ld_dagg, dz1, dpq,
                     part_head, part_tail, dw2_part, db2_part};
@@ -901,7 +1067,7 @@ int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, co
     }
     sum_partials_tc_kernel<<<ceil_div(TCH * TCH, 256), 256, 0, s>>>(dw2_part, grid, (int64_t)TCH * TCH, dW2, accumulate);
     MGB_LAUNCH_CHECK();
-    sum_partials_tc_kernel<<<1, 256, 0, s>>>(db2_part, grid, TCH, db2, accumulate);
+    sum_partials_tc_kernel<<<1, 256, 0, s>>>(db2_part, 2 * grid, TCH, db2, accumulate);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }

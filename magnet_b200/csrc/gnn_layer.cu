@@ -664,7 +664,7 @@ size_t gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp,
     b += align_up((size_t)n_nodes * ld4(sh.K3()) * 4);                // dc
     b += align_up((size_t)n_nodes * 2 * H * 4);                       // dpq
     b += align_up((size_t)n_nodes * ld4(sh.Kc()) * 4);                // dxc
-    b += align_up((size_t)(n_edges > 0 ? n_edges : 1) * H * 4);       // dz1
+    b += align_up((size_t)((n_edges > 0 ? n_edges : 1) + 127) / 128 * 128 * H * 4);       // dz1, padded to whole edge tiles
     b += 2 * align_up((size_t)tiles * H * 4);                         // part head/tail
     b += align_up((size_t)grid * H * H * 4) + align_up((size_t)grid * H * 4);
     b += align_up((size_t)2 * H * sh.Kc() * 4) + align_up(2 * H * 4);  // dwcat, dbcat
@@ -693,7 +693,7 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     float* dc = ws.take<float>((size_t)N * ldc);
     float* dpq = ws.take<float>((size_t)N * 2 * H);
     float* dxc = ws.take<float>((size_t)N * ldx);
-    float* dz1 = ws.take<float>((size_t)(sh.n_edges > 0 ? sh.n_edges : 1) * H);
+    float* dz1 = ws.take<float>((size_t)((sh.n_edges > 0 ? sh.n_edges : 1) + 127) / 128 * 128 * H);   // padded to whole edge tiles
     float* part_head = ws.take<float>((size_t)tiles * H);
     float* part_tail = ws.take<float>((size_t)tiles * H);
     float* dw2_part = ws.take<float>((size_t)grid * H * H);
@@ -753,7 +753,8 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         a.wimg = p.img_w3; a.nm = 2; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[1][0] = 1;
         a.act = ACT_NONE; a.y = dc; a.ldy = ldc; a.rows = N;
         MGB_TRY(launch_linear_tc(sh.precision, a, s));
-        MGB_TRY(launch_tail_dgrad(d1, H, H, io.y1_pre, H, ACT_SWISH, io.W3 + 2 * H, sh.K3(), 1, sh.nv, N, dc + 2 * H, ldc, s));
+        if (io.dvar)      // the tail columns of dc feed dvar only
+            MGB_TRY(launch_tail_dgrad(d1, H, H, io.y1_pre, H, ACT_SWISH, io.W3 + 2 * H, sh.K3(), 1, sh.nv, N, dc + 2 * H, ldc, s));
     } else {
         WgradArgs w{};
         w.dy = d1; w.lddy = H; w.y_pre = io.y1_pre; w.y_act = ACT_SWISH;
@@ -821,7 +822,8 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         a.wimg = p.img_pq; a.nm = 1; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[0][1] = 1;
         a.act = ACT_NONE; a.y = dxc; a.ldy = ldx; a.rows = N;
         MGB_TRY(launch_linear_tc(sh.precision, a, s));
-        MGB_TRY(launch_tail_dgrad(dpq, 2 * H, 2 * H, nullptr, 0, ACT_NONE, p.wcat + H, sh.Kc(), 1, kt_pq, N, dxc + H, ldx, s));
+        if (io.du || io.dpos || io.dvar)      // the tail columns of dxc feed du / dpos / dvar only
+            MGB_TRY(launch_tail_dgrad(dpq, 2 * H, 2 * H, nullptr, 0, ACT_NONE, p.wcat + H, sh.Kc(), 1, kt_pq, N, dxc + H, ldx, s));
     } else {
         WgradArgs w{};
         w.dy = dpq; w.lddy = 2 * H;

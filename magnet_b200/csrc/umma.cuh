@@ -27,26 +27,64 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the hint expires,
-// so a waiting warp does not compete for issue slots with the working warps of its scheduler
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// Wait for the phase with the given parity.  try_wait parks the thread for a hardware-bounded time (about 80 cycles on
+// B200, whatever hint is passed) and a CTA here has twenty-odd warps waiting at any time, so the retry loop has to be
+// as short as possible or the waiting warps eat the issue slots of the working ones: try_wait, branch, count, compare.
+// Bounded: a protocol bug must trap (reported as a CUDA error through the C ABI), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "MGB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+        "@p bra MGB_DONE;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, 0x1000000;\n\t"
+        "@p bra MGB_WAIT;\n\t"
+        "trap;\n"
+        "MGB_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// one poll: true once the phase with the given parity has completed (parks the thread for a bounded time otherwise)
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (reported as a CUDA error through the C ABI), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) {
-            printf("magnet_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
+// same, for waits that are not on the critical path (metadata several tiles ahead): back off between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "MGB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+        "@p bra MGB_DONE;\n\t"
+        "nanosleep.u32 256;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, 0x400000;\n\t"
+        "@p bra MGB_WAIT;\n\t"
+        "trap;\n"
+        "MGB_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// one lane of a converged warp (the compiler then knows the guarded region is single-threaded, which keeps the
+// uniform-register operands of tcgen05.mma free of per-instruction convergence loops)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
@@ -79,6 +117,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // 32 lanes x 16 consecutive fp32 columns
