@@ -53,21 +53,30 @@ int pack_w2_image(const float* W2, void* img, cudaStream_t s) {
     return MGB_OK;
 }
 
-__global__ void __launch_bounds__(TCH)
+// Segments cut by a sub-tile boundary: merge the tail partial of the sub-tile the segment starts in, the head partials
+// of the sub-tiles it covers and the head partial of the sub-tile it ends in.  One warp per sub-tile (4 channels per lane).
+__global__ void __launch_bounds__(256)
 segment_fixup_tc_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ dstv, int64_t n_edges, int te,
                         const float* __restrict__ part_head, const float* __restrict__ part_tail, float* __restrict__ out,
                         int ld_out, int mean) {
-    const int64_t t = (int64_t)blockIdx.x + 1;
+    const int64_t t = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
     const int64_t e0 = t * te;
     if (e0 >= n_edges) return;
     const int node = dstv[e0];
     const int64_t s0 = rowptr[node], s1 = rowptr[node + 1];
     if (!(s0 < e0 && s1 <= e0 + te)) return;
-    const int c = threadIdx.x;
+    const int c = (threadIdx.x & 31) * 4;
     const int64_t t0 = s0 / te;
-    float acc = part_tail[t0 * TCH + c];
-    for (int64_t tt = t0 + 1; tt <= t; ++tt) acc += part_head[tt * TCH + c];
-    out[(int64_t)node * ld_out + c] = mean ? acc / (float)(s1 - s0) : acc;
+    float4 acc = *reinterpret_cast<const float4*>(part_tail + t0 * TCH + c);
+    for (int64_t tt = t0 + 1; tt <= t; ++tt) {
+        const float4 h = *reinterpret_cast<const float4*>(part_head + tt * TCH + c);
+        acc.x += h.x; acc.y += h.y; acc.z += h.z; acc.w += h.w;
+    }
+    if (mean) {
+        const float inv = 1.0f / (float)(s1 - s0);       // same rounding as the in-tile mean (multiply by 1/deg)
+        acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    }
+    *reinterpret_cast<float4*>(out + (int64_t)node * ld_out + c) = acc;
 }
 
 // ---- per-tile segment metadata, produced ahead of time by the meta warp ----------------------------------
@@ -405,7 +414,7 @@ int launch_edge_fwd_tc(int precision, const float* pq, const int32_t* rowptr, co
     }
     MGB_LAUNCH_CHECK();
     if (subtiles > 1) {
-        segment_fixup_tc_kernel<<<(unsigned)(subtiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, FW_FLUSH_TE, part_head, part_tail, agg, TCH, 1);
+        segment_fixup_tc_kernel<<<(unsigned)ceil_div<int64_t>(subtiles - 1, 8), 256, 0, s>>>(rowptr, dstv, n_edges, FW_FLUSH_TE, part_head, part_tail, agg, TCH, 1);
         MGB_LAUNCH_CHECK();
     }
     return MGB_OK;
@@ -1062,7 +1071,7 @@ int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, co
     }
     MGB_LAUNCH_CHECK();
     if (subtiles > 1) {
-        segment_fixup_tc_kernel<<<(unsigned)(subtiles - 1), TCH, 0, s>>>(rowptr, dstv, n_edges, BW_FLUSH_TE, part_head, part_tail, dpq, 2 * TCH, 0);
+        segment_fixup_tc_kernel<<<(unsigned)ceil_div<int64_t>(subtiles - 1, 8), 256, 0, s>>>(rowptr, dstv, n_edges, BW_FLUSH_TE, part_head, part_tail, dpq, 2 * TCH, 0);
         MGB_LAUNCH_CHECK();
     }
     sum_partials_tc_kernel<<<ceil_div(TCH * TCH, 256), 256, 0, s>>>(dw2_part, grid, (int64_t)TCH * TCH, dW2, accumulate);

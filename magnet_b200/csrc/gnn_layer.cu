@@ -717,10 +717,12 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     // B2. update_net_2:  dW4 = (d0*Swish'(y2_pre))^T Swish(y1_pre);  d1 = (d0*Swish'(y2_pre)) W4
     if (tc_nodes) {
         WgradTcArgs w{};
-        w.dy = d0; w.lddy = H; w.y_pre = io.y2_pre; w.ldyp = H; w.y_act = ACT_SWISH;
-        w.x = io.y1_pre; w.ldx = H; w.x_act = ACT_SWISH; w.rows = N;
-        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW4, H, H, H, acc, wg_ws, wg_bytes, s));
-        MGB_TRY(launch_colsum(d0, H, io.y2_pre, ACT_SWISH, N, H, io.db4, acc, sub_ws, sub_bytes, s));
+        w.dy = d0; w.lddy = H; w.ny = 1; w.y_pre = io.y2_pre; w.ldyp = H; w.y_act = ACT_SWISH;
+        w.nx = 1; w.x[0] = io.y1_pre; w.ldx[0] = H; w.x_act[0] = ACT_SWISH; w.rows = N;
+        w.db[0] = io.db4; w.db_accumulate = acc;
+        WgradTcOut o[1] = {};
+        o[0].dw = io.dW4; o[0].lddw = H; o[0].n_valid = H; o[0].k_valid = H; o[0].accumulate = acc;
+        MGB_TRY(launch_wgrad_tc(sh.precision, w, o, wg_ws, wg_bytes, s));
         LinTcArgs a{};
         a.src[0] = d0; a.ld[0] = H; a.nk = 1; a.pre = io.y2_pre; a.ldpre = H; a.pre_act = ACT_SWISH;
         a.wimg = p.img_w4; a.nm = 1; a.a_trans = 1; a.tile_of[0][0] = 0;
@@ -740,14 +742,14 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     // B3. update_net_1:  dW3 = (d1*Swish'(y1_pre))^T [x,agg,var];  dc = (d1*Swish'(y1_pre)) W3
     if (tc_nodes) {
         WgradTcArgs w{};
-        w.dy = d1; w.lddy = H; w.y_pre = io.y1_pre; w.ldyp = H; w.y_act = ACT_SWISH; w.rows = N;
-        w.x = io.x; w.ldx = H;
-        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW3, sh.K3(), H, H, acc, wg_ws, wg_bytes, s));
-        w.x = io.agg;
-        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW3 + H, sh.K3(), H, H, acc, wg_ws, wg_bytes, s));
-        w.x = nullptr; w.tsrc[0] = io.var; w.tld[0] = sh.nv; w.tk[0] = sh.nv; w.kt = sh.nv;
-        MGB_TRY(launch_wgrad_tc(sh.precision, w, io.dW3 + 2 * H, sh.K3(), H, sh.nv, acc, wg_ws, wg_bytes, s));
-        MGB_TRY(launch_colsum(d1, H, io.y1_pre, ACT_SWISH, N, H, io.db3, acc, sub_ws, sub_bytes, s));
+        w.dy = d1; w.lddy = H; w.ny = 1; w.y_pre = io.y1_pre; w.ldyp = H; w.y_act = ACT_SWISH; w.rows = N;
+        w.nx = 2; w.x[0] = io.x; w.ldx[0] = H; w.x[1] = io.agg; w.ldx[1] = H;
+        w.tail = 1; w.tsrc[0] = io.var; w.tld[0] = sh.nv; w.tk[0] = sh.nv; w.kt = sh.nv;
+        WgradTcOut o[3] = {};
+        o[0].dw = io.dW3; o[1].dw = io.dW3 + H; o[2].dw = io.dW3 + 2 * H;
+        for (int i = 0; i < 3; ++i) { o[i].lddw = sh.K3(); o[i].n_valid = H; o[i].k_valid = i < 2 ? H : sh.nv; o[i].accumulate = acc; }
+        w.db[0] = io.db3; w.db_accumulate = acc;
+        MGB_TRY(launch_wgrad_tc(sh.precision, w, o, wg_ws, wg_bytes, s));
         LinTcArgs a{};
         a.src[0] = d1; a.ld[0] = H; a.nk = 1; a.pre = io.y1_pre; a.ldpre = H; a.pre_act = ACT_SWISH;
         a.wimg = p.img_w3; a.nm = 2; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[1][0] = 1;
@@ -801,18 +803,24 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     }
     // B6. first Linear (factorised): dWcat = dPQ^T [x,u,pos,var];  dxc = dPQ Wcat
     if (tc_nodes) {
-        for (int half = 0; half < 2; ++half) {       // rows of dWcat: P outputs, Q outputs
+        {   // rows of dWcat: P outputs (Y' tile 0), Q outputs (Y' tile 1); columns: x | u,pos,var; dbcat from the ones column
             WgradTcArgs w{};
-            w.dy = dpq + half * H; w.lddy = 2 * H; w.rows = N;
-            w.x = io.x; w.ldx = H;
-            MGB_TRY(launch_wgrad_tc(sh.precision, w, dwcat + (size_t)half * H * sh.Kc(), sh.Kc(), H, H, 0, wg_ws, wg_bytes, s));
-            w.x = nullptr;
+            w.dy = dpq; w.lddy = 2 * H; w.ny = 2; w.rows = N;
+            w.nx = 1; w.x[0] = io.x; w.ldx[0] = H;
+            w.tail = 1;
             w.tsrc[0] = io.u; w.tld[0] = sh.tw; w.tk[0] = sh.tw;
             w.tsrc[1] = io.pos; w.tld[1] = sh.dp; w.tk[1] = sh.dp;
             w.tsrc[2] = io.var; w.tld[2] = sh.nv; w.tk[2] = sh.nv; w.kt = kt_pq;
-            MGB_TRY(launch_wgrad_tc(sh.precision, w, dwcat + (size_t)half * H * sh.Kc() + H, sh.Kc(), H, kt_pq, 0, wg_ws, wg_bytes, s));
+            WgradTcOut o[4] = {};
+            for (int half = 0; half < 2; ++half) {
+                WgradTcOut& ox = o[half * 2];
+                WgradTcOut& ot = o[half * 2 + 1];
+                ox.dw = dwcat + (size_t)half * H * sh.Kc(); ox.lddw = sh.Kc(); ox.n_valid = H; ox.k_valid = H;
+                ot.dw = dwcat + (size_t)half * H * sh.Kc() + H; ot.lddw = sh.Kc(); ot.n_valid = H; ot.k_valid = kt_pq;
+                w.db[half] = dbcat + half * H;
+            }
+            MGB_TRY(launch_wgrad_tc(sh.precision, w, o, wg_ws, wg_bytes, s));
         }
-        MGB_TRY(launch_colsum(dpq, 2 * H, nullptr, ACT_NONE, N, 2 * H, dbcat, 0, sub_ws, sub_bytes, s));
         unpack_dw1_kernel<<<ceil_div(H * sh.K1(), 256), 256, 0, s>>>(dwcat, sh.tw, sh.dp, sh.nv, io.dW1, acc);
         MGB_LAUNCH_CHECK();
         sum_partials_kernel<<<1, 256, 0, s>>>(dbcat, 1, H, io.db1, acc);

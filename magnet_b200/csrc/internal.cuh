@@ -116,17 +116,24 @@ struct LinTcArgs {
     int64_t rows;
 };
 struct WgradTcArgs {
-    const float* dy; int lddy; const float* y_pre; int ldyp; int y_act;   // Y' = dy * act'(y_pre)
-    const float* x; int ldx; int x_act;                                   // X (128 columns) or null -> tail columns
-    const float* tsrc[3]; int tld[3]; int tk[3]; int kt;
+    const float* dy; int lddy; int ny;                    // Y'_y = dy[:, 128 y : 128 y + 128] * act'(y_pre[:, same])
+    const float* y_pre; int ldyp; int y_act;
+    int nx; const float* x[2]; int ldx[2]; int x_act[2];  // 128-column sources (optionally act(x))
+    int tail;                                             // 1: a tail tile [small-K columns | 0...] follows the sources
+    const float* tsrc[3]; int tld[3]; int tk[3]; int kt;  // small-K columns, sum tk = kt <= 16
+    float* db[2]; int db_accumulate;                      // optional bias gradients: column sums of Y'_y (exact fp32 adds)
     int64_t rows;
-    float* partial;                                                       // filled by the launcher
+    float* partial;                                       // filled by the launcher
+    float* bias_partial;                                  // filled by the launcher: [grid][producer warps][ny][128]
+};
+struct WgradTcOut {          // destination of accumulator (y, x): dw[n*lddw + k], n < n_valid, k < k_valid
+    float* dw; int lddw; int n_valid, k_valid; int accumulate;
 };
 int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s);
 int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s);
 size_t wgrad_tc_workspace(int64_t rows);
-int launch_wgrad_tc(int precision, WgradTcArgs a, float* dw, int lddw, int n_valid, int k_valid, int accumulate, void* ws,
-                    size_t ws_bytes, cudaStream_t s);
+int launch_wgrad_tc(int precision, WgradTcArgs a, const WgradTcOut* outs /*[ny][nx + tail]*/, void* ws, size_t ws_bytes,
+                    cudaStream_t s);
 int launch_tail_dgrad(const float* dy, int lddy, int ny, const float* pre, int ldpre, int act, const float* wtail, int wt_sn,
                       int wt_st, int kt, int64_t rows, float* out, int ldo, cudaStream_t s);
 #ifdef MGB_TIMELINE

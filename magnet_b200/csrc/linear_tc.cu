@@ -15,9 +15,9 @@
 
 namespace mgb {
 
-constexpr int LT_EPI_WARPS = 4, LT_PROD_WARPS = 8;
+constexpr int LT_EPI_WARPS = 8, LT_PROD_WARPS = 8;
 constexpr int LT_MMA_WARP = LT_EPI_WARPS, LT_PROD_WARP0 = LT_EPI_WARPS + 1;
-constexpr int LT_THREADS = (LT_EPI_WARPS + 1 + LT_PROD_WARPS) * 32;   // 416
+constexpr int LT_THREADS = (LT_EPI_WARPS + 1 + LT_PROD_WARPS) * 32;   // 544
 constexpr int LT_TAIL = 16;
 
 // W [rows_total][ld] fp32, tile = W[r0:r0+128, c0:c0+128] (zero outside) -> swizzled bf16 images hi | lo
@@ -40,18 +40,20 @@ int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int
     return MGB_OK;
 }
 
-// 2 weight tiles (always hi|lo) + B stages (2 x bf16 or 1 x hi|lo) + 2 tail tiles
+// 2 weight tiles (always hi|lo) + one B stage + 2 tail tiles; with a single weight tile the second weight slot
+// serves as a second B stage
 constexpr size_t LINEAR_TC_SMEM = 1024 + (size_t)4 * TILE_BYTES + (size_t)2 * TILE_BYTES + 2 * 128 * LT_TAIL * sizeof(float) + 256;
 
+// All role loops are kept small on purpose: the three roles of a CTA run at the same time and share the SM's
+// 32 KB instruction cache (a fully unrolled version of this kernel was 100 KB of SASS and fetch-bound).
 template <int NSPLIT, bool FAST>
 __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArgs a) {
-    constexpr int BSTAGES = NSPLIT == 1 ? 2 : 1;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = umma::smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
     unsigned char* w_img = base;                                        // [2 tiles][hi|lo]
-    unsigned char* b_img = w_img + (size_t)4 * TILE_BYTES;               // [BSTAGES][NSPLIT]
-    float* tails = reinterpret_cast<float*>(b_img + (size_t)BSTAGES * NSPLIT * TILE_BYTES);   // [2][128][LT_TAIL]
+    unsigned char* b_img = w_img + (size_t)4 * TILE_BYTES;               // B stage 0 (NSPLIT = 1: stages 0 and 1)
+    float* tails = reinterpret_cast<float*>(b_img + (size_t)2 * TILE_BYTES);   // [2][128][LT_TAIL]
     uint64_t* bars = reinterpret_cast<uint64_t*>(tails + 2 * 128 * LT_TAIL);
     uint64_t* full = bars;            // [2]
     uint64_t* empty = bars + 2;       // [2]
@@ -63,7 +65,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = ceil_div<int64_t>(a.rows, 128);
+    const int nt = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int n_wtiles = a.nm * a.nk;
+    const int bstages = (NSPLIT == 1 || n_wtiles == 1) ? 2 : 1;
+    // stage s of the B operand
+    auto b_stage = [&](int s) -> unsigned char* {
+        if (NSPLIT == 1) return b_img + (size_t)s * TILE_BYTES;
+        return s == 0 ? b_img : w_img + (size_t)2 * TILE_BYTES;
+    };
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
@@ -83,67 +92,81 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
     const uint32_t tmem = *tmem_slot;
 
     if (warp < LT_EPI_WARPS) {
-        // =========================== epilogue: thread = output channel within the block =================
-        const int n = tid;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        // =========================== epilogue: thread = output channel within the block; warps 0-3 rows 0-63 of the
+        // tile, warps 4-7 rows 64-127 ====================================================================
+        const int n = tid & 127;
+        const int hf = warp >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+#pragma unroll 1
+        for (int it = 0; it < nt; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int64_t r0 = tile * 128;
+            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128;
             const int nr = (int)((a.rows - r0) < 128 ? (a.rows - r0) : 128);
             const float* tl = tails + acc * 128 * LT_TAIL;
             if (a.kt > 0) umma::mbar_wait(&tailfull[acc], aph);
             umma::mbar_wait(&tfull[acc], aph);
             umma::tc_fence_after();
+#pragma unroll 1
             for (int m = 0; m < a.nm; ++m) {
                 const int col = m * 128 + n;
                 const float bias = a.bias ? a.bias[col] : 0.f;
                 float wt[LT_TAIL];
 #pragma unroll
                 for (int t = 0; t < LT_TAIL; ++t) wt[t] = t < a.kt ? a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st] : 0.f;
+                const bool last_m = m == a.nm - 1;
 #pragma unroll 1
-                for (int c0 = 0; c0 < 128; c0 += 32) {
-                    float v[32];
-                    umma::tmem_ld32(tmem + (uint32_t)((acc * 2 + m) * 128) + ((uint32_t)(warp * 32) << 16) + c0, v);
-                    if (m == a.nm - 1 && c0 + 32 >= 128 && a.kt == 0) {
+                for (int cb = 0; cb < 64; cb += 8) {
+                    const int c0 = hf * 64 + cb;
+                    float v[8];
+                    umma::tmem_ld8(tmem + (uint32_t)((acc * 2 + m) * 128) + lane_base + c0, v);
+                    if (last_m && cb + 8 >= 64 && a.kt == 0) {
                         umma::tc_fence_before();
                         umma::mbar_arrive(&tempty[acc]);
                     }
                     if (c0 >= nr) continue;
                     if (a.kt > 0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float4* trow = reinterpret_cast<const float4*>(tl + (c0 + i) * LT_TAIL);
-                            float s = v[i];
+                        for (int t4 = 0; t4 < LT_TAIL / 4; ++t4) {
+                            if (t4 * 4 < a.kt) {
 #pragma unroll
-                            for (int t4 = 0; t4 < LT_TAIL / 4; ++t4) {
-                                if (t4 * 4 < a.kt) {
-                                    const float4 x = trow[t4];
-                                    s = fmaf(x.x, wt[t4 * 4 + 0], s);
-                                    s = fmaf(x.y, wt[t4 * 4 + 1], s);
-                                    s = fmaf(x.z, wt[t4 * 4 + 2], s);
-                                    s = fmaf(x.w, wt[t4 * 4 + 3], s);
+                                for (int i = 0; i < 8; ++i) {
+                                    const float4 x = *reinterpret_cast<const float4*>(tl + (c0 + i) * LT_TAIL + t4 * 4);
+                                    v[i] = fmaf(x.x, wt[t4 * 4 + 0], v[i]);
+                                    v[i] = fmaf(x.y, wt[t4 * 4 + 1], v[i]);
+                                    v[i] = fmaf(x.z, wt[t4 * 4 + 2], v[i]);
+                                    v[i] = fmaf(x.w, wt[t4 * 4 + 3], v[i]);
                                 }
                             }
-                            v[i] = s;
                         }
                     }
-                    const int lim = nr - c0 < 32 ? nr - c0 : 32;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += bias;
+                    const int lim = nr - c0;
+                    const int64_t row0 = r0 + c0;
                     if (a.y_pre) {
+                        float* yp = a.y_pre + row0 * a.ldyp + col;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < lim) a.y_pre[(r0 + c0 + i) * a.ldyp + col] = v[i] + bias;
+                        for (int i = 0; i < 8; ++i)
+                            if (i < lim) yp[(int64_t)i * a.ldyp] = v[i];
                     }
+                    if (a.act == ACT_SWISH) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = act_tc<FAST>(a.act, v[i] + bias);
+                        for (int i = 0; i < 8; ++i) v[i] = swish_tc<FAST>(v[i]);
+                    } else if (a.act == ACT_RELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                    }
                     if (a.residual) {
+                        const float* rp = a.residual + row0 * a.ldr + col;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < lim) v[i] += a.residual[(r0 + c0 + i) * a.ldr + col];
+                        for (int i = 0; i < 8; ++i)
+                            if (i < lim) v[i] += rp[(int64_t)i * a.ldr];
                     }
+                    float* yo = a.y + row0 * a.ldy + col;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < lim) a.y[(r0 + c0 + i) * a.ldy + col] = v[i];
+                    for (int i = 0; i < 8; ++i)
+                        if (i < lim) yo[(int64_t)i * a.ldy] = v[i];
                 }
             }
             if (a.kt > 0) {          // the tail tile is read until the end: release accumulators and tail together
@@ -156,31 +179,36 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
         if (lane == 0) load_w2_image(w_img, (const unsigned char*)a.wimg, (uint32_t)(n_wtiles * 2 * TILE_BYTES), wbar);   // global images always hold hi|lo
         umma::mbar_wait(wbar, 0);
         const uint32_t idesc = umma::idesc_bf16(128, 128, a.a_trans, 0);
-        const uint32_t w_s = umma::smem_u32(w_img);
-        int it = 0, sc = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        // descriptors of k-step 0; a k-step only moves the start-address field (bytes >> 4)
+        const uint64_t w_d = a.a_trans ? umma::desc_sw128(umma::smem_u32(w_img), 128 * 128, 1024) : umma::desc_sw128(umma::smem_u32(w_img), 16, 1024);
+        const uint64_t b_d0 = umma::desc_sw128(umma::smem_u32(b_stage(0)), 16, 1024);
+        const uint64_t b_d1 = umma::desc_sw128(umma::smem_u32(b_stage(1)), 16, 1024);
+        constexpr uint32_t TB = TILE_BYTES >> 4;
+        int sc = 0;
+#pragma unroll 1
+        for (int it = 0; it < nt; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             umma::mbar_wait(&tempty[acc], aph ^ 1);
+#pragma unroll 1
             for (int kc = 0; kc < a.nk; ++kc, ++sc) {
-                const int s = sc % BSTAGES;
-                umma::mbar_wait(&full[s], (sc / BSTAGES) & 1);
+                const int s = sc % bstages;
+                umma::mbar_wait(&full[s], (sc / bstages) & 1);
                 umma::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t b_s = umma::smem_u32(b_img + (size_t)s * NSPLIT * TILE_BYTES);
+                if (umma::elect_one()) {
+                    const uint64_t bd = s ? b_d1 : b_d0;
+#pragma unroll 1
                     for (int m = 0; m < a.nm; ++m) {
                         const uint32_t d = tmem + (uint32_t)((acc * 2 + m) * 128);
-                        const uint32_t wt_s = w_s + (uint32_t)a.tile_of[m][kc] * 2 * TILE_BYTES;
-                        uint32_t accum = kc > 0 ? 1u : 0u;
+                        const uint64_t wd = w_d + (uint64_t)((uint32_t)a.tile_of[m][kc] * 2 * TB);
 #pragma unroll
                         for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
-                            const int wa = term == 2 ? 1 : 0, hb = term == 1 ? 1 : 0;
+                            const uint64_t wa = wd + (term == 2 ? TB : 0), bb = bd + (term == 1 ? TB : 0);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                const uint64_t da = a.a_trans ? umma::desc_mnmajor(wt_s + wa * TILE_BYTES, k)
-                                                              : umma::desc_kmajor(wt_s + wa * TILE_BYTES, k);
-                                umma::mma_bf16(d, da, umma::desc_kmajor(b_s + hb * TILE_BYTES, k), idesc, accum);
-                                accum = 1;
+                                const uint32_t koff_k = (uint32_t)((k >> 2) * (128 * 128 >> 4) + (k & 3) * 2), koff_m = (uint32_t)(k * 128);
+                                umma::mma_bf16(d, wa + (uint64_t)(a.a_trans ? koff_m : koff_k), bb + (uint64_t)koff_k, idesc,
+                                               (kc | term | k) ? 1u : 0u);
                             }
                         }
                     }
@@ -192,19 +220,22 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
         }
     } else {
         // =========================== producers: 16 rows per warp ===================================
+        // x rows -> (optional act'(pre) / act) -> bf16 hi/lo in place in the registers the rows came in, all before the
+        // stage is waited for; only the stores follow its release
         const int pw = warp - LT_PROD_WARP0;
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
-        int it = 0, sc = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        int sc = 0;
+#pragma unroll 1
+        for (int it = 0; it < nt; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            const int64_t r0 = tile * 128 + pw * 16;
+            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + pw * 16;
             if (a.kt > 0) {
                 umma::mbar_wait(&tempty[acc], aph ^ 1);
                 float* tl = tails + acc * 128 * LT_TAIL + pw * 16 * LT_TAIL;
-                // lane -> (row = lane/2 + 16*half..., ) : 16 rows x 16 tail slots = 256 values, 8 per lane
-#pragma unroll
+                // 16 rows x 16 tail slots = 256 values, 8 per lane
+#pragma unroll 1
                 for (int j = 0; j < 8; ++j) {
                     const int e = j * 32 + lane, r = e >> 4, t = e & 15;
                     float v = 0.f;
@@ -217,52 +248,74 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                 }
                 umma::mbar_arrive(&tailfull[acc]);
             }
+#pragma unroll 1
             for (int kc = 0; kc < a.nk; ++kc, ++sc) {
-                const int s = sc % BSTAGES;
-                const float* src = a.src[kc];
+                const int s = sc % bstages;
+                const float* src = a.src[kc] + lane * 4;
                 const int ld = a.ld[kc];
                 float4 x[16];
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                    x[r] = *reinterpret_cast<const float4*>(src + row * ld + lane * 4);
+                    x[r] = *reinterpret_cast<const float4*>(src + row * ld);
                 }
                 if (kc == 0 && a.pre) {
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                        const float4 p = *reinterpret_cast<const float4*>(a.pre + row * a.ldpre + lane * 4);
-                        x[r].x *= act_grad_tc<FAST>(a.pre_act, p.x);
-                        x[r].y *= act_grad_tc<FAST>(a.pre_act, p.y);
-                        x[r].z *= act_grad_tc<FAST>(a.pre_act, p.z);
-                        x[r].w *= act_grad_tc<FAST>(a.pre_act, p.w);
+                    const float* pre = a.pre + lane * 4;
+                    if (a.pre_act == ACT_SWISH) {
+#pragma unroll 4
+                        for (int r = 0; r < 16; ++r) {
+                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
+                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldpre);
+                            x[r].x *= swish_grad_tc<FAST>(p.x);
+                            x[r].y *= swish_grad_tc<FAST>(p.y);
+                            x[r].z *= swish_grad_tc<FAST>(p.z);
+                            x[r].w *= swish_grad_tc<FAST>(p.w);
+                        }
+                    } else if (a.pre_act == ACT_RELU) {
+#pragma unroll 4
+                        for (int r = 0; r < 16; ++r) {
+                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
+                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldpre);
+                            x[r].x = p.x > 0.f ? x[r].x : 0.f;
+                            x[r].y = p.y > 0.f ? x[r].y : 0.f;
+                            x[r].z = p.z > 0.f ? x[r].z : 0.f;
+                            x[r].w = p.w > 0.f ? x[r].w : 0.f;
+                        }
                     }
                 }
-                if (kc == 0 && a.self_act) {
+                if (kc == 0 && a.self_act == ACT_SWISH) {
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
-                        x[r].x = act_tc<FAST>(a.self_act, x[r].x);
-                        x[r].y = act_tc<FAST>(a.self_act, x[r].y);
-                        x[r].z = act_tc<FAST>(a.self_act, x[r].z);
-                        x[r].w = act_tc<FAST>(a.self_act, x[r].w);
+                        x[r].x = swish_tc<FAST>(x[r].x); x[r].y = swish_tc<FAST>(x[r].y);
+                        x[r].z = swish_tc<FAST>(x[r].z); x[r].w = swish_tc<FAST>(x[r].w);
+                    }
+                } else if (kc == 0 && a.self_act == ACT_RELU) {
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        x[r].x = fmaxf(x[r].x, 0.f); x[r].y = fmaxf(x[r].y, 0.f);
+                        x[r].z = fmaxf(x[r].z, 0.f); x[r].w = fmaxf(x[r].w, 0.f);
                     }
                 }
-                umma::mbar_wait(&empty[s], ((sc / BSTAGES) & 1) ^ 1);
-                unsigned char* img = b_img + (size_t)s * NSPLIT * TILE_BYTES;
+                uint4 hl[16];
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     float4 h = x[r];
                     if (r0 + r >= a.rows) h = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
                     if (NSPLIT == 1) {
-                        *reinterpret_cast<uint2*>(img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
+                        hl[r].x = umma::pack_bf16(h.x, h.y);
+                        hl[r].y = umma::pack_bf16(h.z, h.w);
                     } else {
-                        uint2 hi, lo;
-                        split2_bf16(h.x, h.y, hi.x, lo.x);
-                        split2_bf16(h.z, h.w, hi.y, lo.y);
-                        *reinterpret_cast<uint2*>(img + off) = hi;
-                        *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = lo;
+                        split2_bf16(h.x, h.y, hl[r].x, hl[r].z);
+                        split2_bf16(h.z, h.w, hl[r].y, hl[r].w);
                     }
+                }
+                umma::mbar_wait(&empty[s], ((sc / bstages) & 1) ^ 1);
+                unsigned char* img = b_stage(s);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
+                    *reinterpret_cast<uint2*>(img + off) = make_uint2(hl[r].x, hl[r].y);
+                    if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = make_uint2(hl[r].z, hl[r].w);
                 }
                 umma::fence_async_smem();
                 umma::mbar_arrive(&full[s]);
@@ -294,216 +347,353 @@ int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s) {
 }
 
 // ==================================================================================================
-// Weight gradient on the tensor cores:  dW[n][k] (+)= sum_rows Y'[row][n] X[row][k]   (one 128x128 tile per launch)
-//   Y' = dy * act'(y_pre) (optional), X = a 128-column source (optionally act(x)) or the packed small-K tail columns.
-// Both operands are row tiles [row][col] used as MN-major operands (K = rows); the accumulator lives in TMEM across
-// the CTA's row tiles, two buffers alternate every 4 tiles and are drained with round-to-nearest adds (see gnn_edge_tc.cu).
+// Weight gradients on the tensor cores, all sources of one Linear in ONE launch:
+//   dW[y][x][n][k] (+)= sum_rows Y'_y[row][n] X_x[row][k]
+//   Y'_y = dy_y * act'(y_pre) (ny <= 2 tiles of 128 output channels),
+//   X_x  = up to two 128-column sources (optionally act(x)) and a tail tile that packs the small-K columns (u, pos,
+//          variables).  The bias gradient (column sums of Y') is accumulated by the producers on the way, in fp32.
+// Both operands are row tiles [row][col] used as MN-major operands (K = rows).  The ny*(nx+1) <= 4 accumulators live in
+// TMEM across the CTA's row tiles and are drained into the CTA's fp32 partial every WG_GROUP tiles with round-to-nearest
+// adds (the tensor core's own accumulation truncates; see gnn_edge_tc.cu).
+// Shared memory: Y' tiles 2 x 64 KB, one X stage 64 KB (with ny = 1 the second Y' slot is a second X stage).
 // ==================================================================================================
-constexpr size_t WGRAD_TC_SMEM = 1024 + (size_t)4 * TILE_BYTES + 256;
+constexpr size_t WGRAD_TC_SMEM = 1024 + (size_t)6 * TILE_BYTES + 256;
+constexpr int WG_GROUP = 8;
 
 template <int NSPLIT, bool FAST>
 __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcArgs a) {
-    constexpr int GROUP = FAST ? (1 << 30) : 4;
+    constexpr int GROUP = FAST ? (1 << 30) : WG_GROUP;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = umma::smem_u32(smem_raw);
     unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
-    unsigned char* y_img = base;                                  // [NSPLIT]  Y'[row][n]
-    unsigned char* x_img = base + (size_t)2 * TILE_BYTES;         // [NSPLIT]  X[row][k]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)4 * TILE_BYTES);
-    uint64_t* full = bars;          // producers -> MMA
-    uint64_t* empty = bars + 1;     // MMA -> producers
-    uint64_t* d_full = bars + 2;    // [2]
-    uint64_t* d_empty = bars + 4;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    unsigned char* y_img = base;                                  // [2][hi|lo]  Y'[row][n]
+    unsigned char* x_img = base + (size_t)4 * TILE_BYTES;         // [hi|lo]     X[row][k]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)6 * TILE_BYTES);
+    uint64_t* y_full = bars;        // producers -> MMA: all Y' tiles of the row tile written
+    uint64_t* y_empty = bars + 1;   // MMA -> producers: every MMA of the row tile has completed
+    uint64_t* x_full = bars + 2;    // [2]
+    uint64_t* x_empty = bars + 4;   // [2]
+    uint64_t* d_full = bars + 6;    // MMA -> epilogue: a group of row tiles is complete
+    uint64_t* d_empty = bars + 7;   // epilogue -> MMA: accumulators drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n_tiles = ceil_div<int64_t>(a.rows, 128);
+    const int nt = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int nxt = a.nx + (a.tail ? 1 : 0);      // X tiles per row tile
+    const int nacc = a.ny * nxt;
+    const int xstages = a.ny == 1 ? 2 : 1;
+    auto x_stage = [&](int s) -> unsigned char* { return s == 0 ? x_img : y_img + (size_t)2 * TILE_BYTES; };
     if (tid == 0) {
-        umma::mbar_init(full, LT_PROD_WARPS * 32);
-        umma::mbar_init(empty, 1);
+        umma::mbar_init(y_full, LT_PROD_WARPS * 32);
+        umma::mbar_init(y_empty, 1);
         for (int s = 0; s < 2; ++s) {
-            umma::mbar_init(&d_full[s], 1);
-            umma::mbar_init(&d_empty[s], LT_EPI_WARPS * 32);
+            umma::mbar_init(&x_full[s], LT_PROD_WARPS * 32);
+            umma::mbar_init(&x_empty[s], 1);
         }
+        umma::mbar_init(d_full, 1);
+        umma::mbar_init(d_empty, LT_EPI_WARPS * 32);
         umma::fence_barrier_init();
     }
-    if (warp == LT_MMA_WARP) umma::tmem_alloc(tmem_slot, 256);
+    if (warp == LT_MMA_WARP) umma::tmem_alloc(tmem_slot, 512);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
     if (warp < LT_EPI_WARPS) {
-        const int n = tid;
-        float* out = a.partial + ((int64_t)blockIdx.x * 128 + n) * 128;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const bool last = tile + gridDim.x >= n_tiles;
-            if ((it % GROUP) != GROUP - 1 && !last) continue;
-            const int grp = it / GROUP, buf = grp & 1;
-            umma::mbar_wait(&d_full[buf], (grp >> 1) & 1);
+        // =========================== drain: thread = output channel n; warps 0-3 columns 0-63, warps 4-7 columns 64-127
+        const int n = tid & 127, hf = warp >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int ngroups = (nt + GROUP - 1) / GROUP;
+#pragma unroll 1
+        for (int grp = 0; grp < ngroups; ++grp) {
+            umma::mbar_wait(d_full, grp & 1);
             umma::tc_fence_after();
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
-                float v[32];
-                umma::tmem_ld32(tmem + (uint32_t)(buf * 128) + ((uint32_t)(warp * 32) << 16) + c0, v);
-                if (c0 + 32 >= 128) {
-                    umma::tc_fence_before();
-                    umma::mbar_arrive(&d_empty[buf]);
-                }
-                float4* o = reinterpret_cast<float4*>(out + c0);
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                    float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-                    if (grp > 0) {
-                        const float4 old = o[q4];
-                        w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+            for (int ac = 0; ac < nacc; ++ac) {
+                float* out = a.partial + (((int64_t)blockIdx.x * nacc + ac) * 128 + n) * 128 + hf * 64;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    float v[16];
+                    umma::tmem_ld16(tmem + (uint32_t)(ac * 128 + hf * 64) + lane_base + c0, v);
+                    if (ac == nacc - 1 && c0 + 16 >= 64) {
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(d_empty);
                     }
-                    o[q4] = w;
+                    float4* o = reinterpret_cast<float4*>(out + c0);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+                        if (grp > 0) {
+                            const float4 old = o[q4];
+                            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                        }
+                        o[q4] = w;
+                    }
                 }
             }
         }
     } else if (warp == LT_MMA_WARP) {
         const uint32_t idesc = umma::idesc_bf16(128, 128, 1, 1);
-        const uint32_t y_s = umma::smem_u32(y_img), x_s = umma::smem_u32(x_img);
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int grp = it / GROUP, buf = grp & 1;
+        const uint64_t y_d = umma::desc_sw128(umma::smem_u32(y_img), 128 * 128, 1024);
+        const uint64_t x_d0 = umma::desc_sw128(umma::smem_u32(x_stage(0)), 128 * 128, 1024);
+        const uint64_t x_d1 = umma::desc_sw128(umma::smem_u32(x_stage(1)), 128 * 128, 1024);
+        constexpr uint32_t TB = TILE_BYTES >> 4;
+        int sc = 0;
+#pragma unroll 1
+        for (int it = 0; it < nt; ++it) {
+            const int grp = it / GROUP;
             const bool first_in_group = (it % GROUP) == 0;
-            const bool last = tile + gridDim.x >= n_tiles;
-            if (first_in_group) umma::mbar_wait(&d_empty[buf], ((grp >> 1) & 1) ^ 1);
-            umma::mbar_wait(full, it & 1);
-            umma::tc_fence_after();
-            if (lane == 0) {
-                uint32_t accum = first_in_group ? 0u : 1u;
+            const bool last = it == nt - 1;
+            if (first_in_group) umma::mbar_wait(d_empty, (grp & 1) ^ 1);
+            umma::mbar_wait(y_full, it & 1);
+#pragma unroll 1
+            for (int xi = 0; xi < nxt; ++xi, ++sc) {
+                const int s = sc % xstages;
+                umma::mbar_wait(&x_full[s], (sc / xstages) & 1);
+                umma::tc_fence_after();
+                if (umma::elect_one()) {
+                    const uint64_t xd = s ? x_d1 : x_d0;
+#pragma unroll 1
+                    for (int yi = 0; yi < a.ny; ++yi) {
+                        const uint32_t d = tmem + (uint32_t)((yi * nxt + xi) * 128);
+                        const uint64_t yd = y_d + (uint64_t)((uint32_t)yi * 2 * TB);
 #pragma unroll
-                for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
-                    const int ya = term == 2 ? 1 : 0, xb = term == 1 ? 1 : 0;
+                        for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
+                            const uint64_t ya = yd + (term == 2 ? TB : 0), xb = xd + (term == 1 ? TB : 0);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        umma::mma_bf16(tmem + (uint32_t)(buf * 128), umma::desc_mnmajor(y_s + ya * TILE_BYTES, k),
-                                       umma::desc_mnmajor(x_s + xb * TILE_BYTES, k), idesc, accum);
-                        accum = 1;
+                            for (int k = 0; k < 8; ++k)     // K = rows: 16 rows = 2048 bytes per step
+                                umma::mma_bf16(d, ya + (uint64_t)(k * 128), xb + (uint64_t)(k * 128), idesc,
+                                               (term | k) ? 1u : (first_in_group ? 0u : 1u));
+                        }
+                    }
+                    umma::mma_commit(&x_empty[s]);
+                    if (xi == nxt - 1) {
+                        umma::mma_commit(y_empty);
+                        if ((it % GROUP) == GROUP - 1 || last) umma::mma_commit(d_full);
                     }
                 }
-                umma::mma_commit(empty);
-                if ((it % GROUP) == GROUP - 1 || last) umma::mma_commit(&d_full[buf]);
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else {
+        // =========================== producers: 16 rows per warp ===================================
         const int pw = warp - LT_PROD_WARP0;
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int64_t r0 = tile * 128 + pw * 16;
-            float4 yv[16];
+        // 16 rows of one operand tile: converted in place in the registers the rows came in; only the stores follow the wait
+        auto store_tile = [&](float4 (&x)[16], int64_t r0, unsigned char* img, uint64_t* bar, uint32_t parity) {
+            uint4 hl[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                yv[r] = *reinterpret_cast<const float4*>(a.dy + row * a.lddy + lane * 4);
+                float4 h = x[r];
+                if (r0 + r >= a.rows) h = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (NSPLIT == 1) {
+                    hl[r].x = umma::pack_bf16(h.x, h.y);
+                    hl[r].y = umma::pack_bf16(h.z, h.w);
+                } else {
+                    split2_bf16(h.x, h.y, hl[r].x, hl[r].z);
+                    split2_bf16(h.z, h.w, hl[r].y, hl[r].w);
+                }
             }
-            if (a.y_pre) {
+            umma::mbar_wait(bar, parity);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
+                *reinterpret_cast<uint2*>(img + off) = make_uint2(hl[r].x, hl[r].y);
+                if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = make_uint2(hl[r].z, hl[r].w);
+            }
+            umma::fence_async_smem();
+        };
+        // this lane's four columns of the tail tile: source pointer (column already applied) and row stride, or a constant
+        const float* tp[4];
+        int tl[4];
+        float tone[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = lane * 4 + u;
+            tp[u] = nullptr; tl[u] = 0; tone[u] = 0.f;
+            if (t < a.kt) {
+                int tt = t, seg = 0;
+                while (tt >= a.tk[seg]) { tt -= a.tk[seg]; ++seg; }
+                tp[u] = a.tsrc[seg] + tt; tl[u] = a.tld[seg];
+            }
+        }
+        float4 bsum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};     // column sums of Y' (this warp's rows)
+        int sc = 0;
+#pragma unroll 1
+        for (int it = 0; it < nt; ++it) {
+            const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + pw * 16;
+            float4 x[16];
+#pragma unroll 1
+            for (int yi = 0; yi < a.ny; ++yi) {
+                const float* dy = a.dy + yi * 128 + lane * 4;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
                     const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                    const float4 p = *reinterpret_cast<const float4*>(a.y_pre + row * a.ldyp + lane * 4);
-                    yv[r].x *= act_grad_tc<FAST>(a.y_act, p.x);
-                    yv[r].y *= act_grad_tc<FAST>(a.y_act, p.y);
-                    yv[r].z *= act_grad_tc<FAST>(a.y_act, p.z);
-                    yv[r].w *= act_grad_tc<FAST>(a.y_act, p.w);
+                    x[r] = *reinterpret_cast<const float4*>(dy + row * a.lddy);
                 }
-            }
-            umma::mbar_wait(empty, (it & 1) ^ 1);
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                float4 h = yv[r];
-                if (r0 + r >= a.rows) h = make_float4(0.f, 0.f, 0.f, 0.f);
-                const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
-                if (NSPLIT == 1) {
-                    *reinterpret_cast<uint2*>(y_img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
-                } else {
-                    uint2 hi, lo;
-                    split2_bf16(h.x, h.y, hi.x, lo.x);
-                    split2_bf16(h.z, h.w, hi.y, lo.y);
-                    *reinterpret_cast<uint2*>(y_img + off) = hi;
-                    *reinterpret_cast<uint2*>(y_img + TILE_BYTES + off) = lo;
-                }
-            }
-            // X tile: a 128-column source, or the small-K tail columns packed into columns [0, kt)
+                if (a.y_pre) {
+                    const float* pre = a.y_pre + yi * 128 + lane * 4;
+                    if (a.y_act == ACT_SWISH) {
 #pragma unroll 4
-            for (int r = 0; r < 16; ++r) {
-                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r0 + r < a.rows) {
-                    if (a.x) {
-                        h = *reinterpret_cast<const float4*>(a.x + (r0 + r) * a.ldx + lane * 4);
-                        if (a.x_act) {
-                            h.x = act_tc<FAST>(a.x_act, h.x); h.y = act_tc<FAST>(a.x_act, h.y);
-                            h.z = act_tc<FAST>(a.x_act, h.z); h.w = act_tc<FAST>(a.x_act, h.w);
+                        for (int r = 0; r < 16; ++r) {
+                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
+                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldyp);
+                            x[r].x *= swish_grad_tc<FAST>(p.x);
+                            x[r].y *= swish_grad_tc<FAST>(p.y);
+                            x[r].z *= swish_grad_tc<FAST>(p.z);
+                            x[r].w *= swish_grad_tc<FAST>(p.w);
                         }
-                    } else {
-                        float t4[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int t = lane * 4 + u;
-                            float v = 0.f;
-                            if (t < a.kt) {
-                                int tt = t, seg = 0;
-                                while (tt >= a.tk[seg]) { tt -= a.tk[seg]; ++seg; }
-                                v = a.tsrc[seg][(r0 + r) * a.tld[seg] + tt];
-                            }
-                            t4[u] = v;
+                    } else if (a.y_act == ACT_RELU) {
+#pragma unroll 4
+                        for (int r = 0; r < 16; ++r) {
+                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
+                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldyp);
+                            x[r].x = p.x > 0.f ? x[r].x : 0.f;
+                            x[r].y = p.y > 0.f ? x[r].y : 0.f;
+                            x[r].z = p.z > 0.f ? x[r].z : 0.f;
+                            x[r].w = p.w > 0.f ? x[r].w : 0.f;
                         }
-                        h = make_float4(t4[0], t4[1], t4[2], t4[3]);
                     }
                 }
-                const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
-                if (NSPLIT == 1) {
-                    *reinterpret_cast<uint2*>(x_img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
-                } else {
-                    uint2 hi, lo;
-                    split2_bf16(h.x, h.y, hi.x, lo.x);
-                    split2_bf16(h.z, h.w, hi.y, lo.y);
-                    *reinterpret_cast<uint2*>(x_img + off) = hi;
-                    *reinterpret_cast<uint2*>(x_img + TILE_BYTES + off) = lo;
+                {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        if (r0 + r < a.rows) { t.x += x[r].x; t.y += x[r].y; t.z += x[r].z; t.w += x[r].w; }
+                    }
+                    float4& b = yi ? bsum[1] : bsum[0];
+                    b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w;
                 }
+                // every Y' tile of the row tile is released together (after the last MMA of the previous row tile)
+                store_tile(x, r0, y_img + (size_t)yi * 2 * TILE_BYTES, y_empty, (it & 1) ^ 1);
             }
-            umma::fence_async_smem();
-            umma::mbar_arrive(full);
+            umma::mbar_arrive(y_full);
+#pragma unroll 1
+            for (int xi = 0; xi < nxt; ++xi, ++sc) {
+                const int s = sc % xstages;
+                if (xi < a.nx) {
+                    const float* src = a.x[xi] + lane * 4;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
+                        x[r] = *reinterpret_cast<const float4*>(src + row * a.ldx[xi]);
+                    }
+                    if (a.x_act[xi] == ACT_SWISH) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            x[r].x = swish_tc<FAST>(x[r].x); x[r].y = swish_tc<FAST>(x[r].y);
+                            x[r].z = swish_tc<FAST>(x[r].z); x[r].w = swish_tc<FAST>(x[r].w);
+                        }
+                    } else if (a.x_act[xi] == ACT_RELU) {
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            x[r].x = fmaxf(x[r].x, 0.f); x[r].y = fmaxf(x[r].y, 0.f);
+                            x[r].z = fmaxf(x[r].z, 0.f); x[r].w = fmaxf(x[r].w, 0.f);
+                        }
+                    }
+                } else {
+                    // tail tile: columns [0, kt) = the small-K sources, the rest 0
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
+                        x[r].x = tp[0] ? tp[0][row * tl[0]] : tone[0];
+                        x[r].y = tp[1] ? tp[1][row * tl[1]] : tone[1];
+                        x[r].z = tp[2] ? tp[2][row * tl[2]] : tone[2];
+                        x[r].w = tp[3] ? tp[3][row * tl[3]] : tone[3];
+                    }
+                }
+                store_tile(x, r0, x_stage(s), &x_empty[s], ((sc / xstages) & 1) ^ 1);
+                umma::mbar_arrive(&x_full[s]);
+            }
+        }
+        if (a.bias_partial) {
+            for (int yi = 0; yi < a.ny; ++yi)
+                *reinterpret_cast<float4*>(a.bias_partial + (((int64_t)blockIdx.x * LT_PROD_WARPS + pw) * a.ny + yi) * 128 + lane * 4) = yi ? bsum[1] : bsum[0];
         }
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == LT_MMA_WARP) umma::tmem_dealloc(tmem, 256);
+    if (warp == LT_MMA_WARP) umma::tmem_dealloc(tmem, 512);
 }
 
-// dw[(n0+n)*lddw + k0 + k] (+)= sum over CTA partials, for n < n_valid, k < k_valid
+// One launch reduces every accumulator of a wgrad launch over the CTA partials:
+//   outs[j].dw[n*lddw + k] (+)= sum_p partial[p][j][n][k]   (n < n_valid, k < k_valid),   db[y][n] (+)= sum_p bias_partial[p][y][n].
+// Block = 32 outputs x 8 partial groups (group g sums the partials p = g, g+8, ...; fixed order: deterministic).
+struct WgradReduceArgs {
+    const float* partial; int nacc; int n_parts;
+    WgradTcOut outs[4];
+    const float* bias_partial; int ny; int n_bias_parts;
+    float* db[2]; int db_accumulate;
+};
 __global__ void __launch_bounds__(256)
-wgrad_tc_reduce_kernel(const float* __restrict__ partial, int n_parts, int n_valid, int k_valid, float* __restrict__ dw, int lddw,
-                       int accumulate) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= 128 * 128) return;
-    const int n = idx >> 7, k = idx & 127;
-    if (n >= n_valid || k >= k_valid) return;
+wgrad_tc_reduce_kernel(const WgradReduceArgs a) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int j = blockIdx.y;
+    const float* src;
+    int64_t stride;
+    int n_parts;
+    float* dst = nullptr;
+    int accumulate;
+    const int idx = blockIdx.x * 32 + lane;       // output index inside the 128 x 128 accumulator (or the 128 bias entries)
+    if (j < a.nacc) {
+        const WgradTcOut& o = a.outs[j];
+        const int n = idx >> 7, k = idx & 127;
+        src = a.partial + (int64_t)j * 128 * 128 + idx;
+        stride = (int64_t)a.nacc * 128 * 128;
+        n_parts = a.n_parts;
+        accumulate = o.accumulate;
+        if (o.dw && n < o.n_valid && k < o.k_valid) dst = o.dw + (int64_t)n * o.lddw + k;
+    } else {
+        const int y = j - a.nacc;
+        src = a.bias_partial + (int64_t)y * 128 + idx;
+        stride = (int64_t)a.ny * 128;
+        n_parts = a.n_bias_parts;
+        accumulate = a.db_accumulate;
+        if (blockIdx.x < 4 && a.db[y]) dst = a.db[y] + idx;
+    }
+    // whole warps share one row n (32 consecutive k), so the test is warp-uniform up to the k_valid edge
     float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += partial[(int64_t)p * 128 * 128 + idx];
-    float* o = dw + (int64_t)n * lddw + k;
-    *o = accumulate ? *o + s : s;
+    if (dst) {
+        int p = g;
+        for (; p + 24 < n_parts; p += 32) {
+            const float v0 = src[(int64_t)p * stride], v1 = src[(int64_t)(p + 8) * stride];
+            const float v2 = src[(int64_t)(p + 16) * stride], v3 = src[(int64_t)(p + 24) * stride];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; p < n_parts; p += 8) s += src[(int64_t)p * stride];
+    }
+    red[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && dst) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += red[q][lane];
+        *dst = accumulate ? *dst + t : t;
+    }
 }
 
 static int wgrad_tc_grid(int64_t rows) {
     const int64_t tiles = ceil_div<int64_t>(rows > 0 ? rows : 1, 128);
     return (int)(tiles < sm_count() ? tiles : sm_count());
 }
-size_t wgrad_tc_workspace(int64_t rows) { return align_up((size_t)wgrad_tc_grid(rows) * 128 * 128 * sizeof(float)) + 256; }
+size_t wgrad_tc_workspace(int64_t rows) {
+    return align_up((size_t)wgrad_tc_grid(rows) * 4 * 128 * 128 * sizeof(float)) + align_up((size_t)wgrad_tc_grid(rows) * LT_PROD_WARPS * 2 * 128 * sizeof(float)) + 256;
+}
 
-int launch_wgrad_tc(int precision, WgradTcArgs a, float* dw, int lddw, int n_valid, int k_valid, int accumulate, void* ws_ptr,
-                    size_t ws_bytes, cudaStream_t s) {
+int launch_wgrad_tc(int precision, WgradTcArgs a, const WgradTcOut* outs, void* ws_ptr, size_t ws_bytes, cudaStream_t s) {
     MGB_REQUIRE(a.rows < ((int64_t)1 << 31), "wgrad_tc: row count out of range");
+    const int nxt = a.nx + (a.tail ? 1 : 0);
+    MGB_REQUIRE(a.ny >= 1 && a.ny <= 2 && a.nx >= 0 && a.nx <= 2 && nxt >= 1 && a.ny * nxt <= 4, "wgrad_tc: at most four accumulators");
+    MGB_REQUIRE(a.kt >= 0 && a.kt <= LT_TAIL, "wgrad_tc: tail width must be <= %d", LT_TAIL);
     if (a.rows <= 0) return MGB_OK;
     const int grid = wgrad_tc_grid(a.rows);
+    const int nacc = a.ny * nxt;
     Workspace ws(ws_ptr, ws_bytes);
-    a.partial = ws.take<float>((size_t)grid * 128 * 128);
+    a.partial = ws.take<float>((size_t)grid * nacc * 128 * 128);
+    a.bias_partial = (a.db[0] || a.db[1]) ? ws.take<float>((size_t)grid * LT_PROD_WARPS * a.ny * 128) : nullptr;
     MGB_WS_CHECK(ws);
     {
         ProfScope prof(PROF_WGRAD, s);
@@ -516,7 +706,12 @@ int launch_wgrad_tc(int precision, WgradTcArgs a, float* dw, int lddw, int n_val
         }
     }
     MGB_LAUNCH_CHECK();
-    wgrad_tc_reduce_kernel<<<64, 256, 0, s>>>(a.partial, grid, n_valid, k_valid, dw, lddw, accumulate);
+    WgradReduceArgs r{};
+    r.partial = a.partial; r.nacc = nacc; r.n_parts = grid;
+    for (int j = 0; j < nacc; ++j) r.outs[j] = outs[j];
+    r.bias_partial = a.bias_partial; r.ny = a.ny; r.n_bias_parts = grid * LT_PROD_WARPS;
+    r.db[0] = a.db[0]; r.db[1] = a.db[1]; r.db_accumulate = a.db_accumulate;
+    wgrad_tc_reduce_kernel<<<dim3(128 * 128 / 32, nacc + (a.bias_partial ? a.ny : 0)), 256, 0, s>>>(r);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }

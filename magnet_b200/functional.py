@@ -40,6 +40,8 @@ def _empty(shape, ref):
 # GNN_Layer (models/mpnn_2d.py:27-90)
 # --------------------------------------------------------------------------------------------
 def pack_gnn_layer(W1, b1, W2, W3, W4, tw: int, dp: int, nv: int) -> torch.Tensor:
+    """Packed / transposed / bf16-imaged copies of a layer's weights for the kernels (the nn.Parameters stay the
+    canonical [out, in] fp32 tensors).  GNN_Layer caches the result per module, keyed on the parameters' version counters."""
     L = _lib.lib()
     packed = _empty((L.mgb_gnn_layer_packed_floats(tw, dp, nv),), W1)
     _lib.check(L.mgb_gnn_layer_pack(_lib.ptr(W1), _lib.ptr(b1), _lib.ptr(W2), _lib.ptr(W3), _lib.ptr(W4), tw, dp, nv,
@@ -51,7 +53,7 @@ class GNNLayerFn(torch.autograd.Function):
     """y = InstanceNorm(x + update(x, mean_j message(x_i, x_j, u, pos, var)))"""
 
     @staticmethod
-    def forward(ctx, x, u, pos, var, W1, b1, W2, b2, W3, b3, W4, b4, plan: AggregationPlan, seg: GraphSegments):
+    def forward(ctx, x, u, pos, var, W1, b1, W2, b2, W3, b3, W4, b4, plan: AggregationPlan, seg: GraphSegments, packed=None):
         _lib.require_cuda(x, u, pos, var, W1)
         L = _lib.lib()
         x, u, pos, var = (_lib.f32c(t) for t in (x, u, pos, var))
@@ -63,7 +65,8 @@ class GNNLayerFn(torch.autograd.Function):
                                f"256+tw+dp+nv; got x {tuple(x.shape)}, W1 {tuple(W1.shape)}, W3 {tuple(W3.shape)}")
         if plan.n_nodes != N:
             raise RuntimeError("aggregation plan was built for a different node count")
-        packed = pack_gnn_layer(W1, b1, W2, W3, W4, tw, dp, nv)
+        if packed is None:
+            packed = pack_gnn_layer(W1, b1, W2, W3, W4, tw, dp, nv)
         prec = PRECISIONS[_precision]
         y = _empty((N, H), x)
         pq = _empty((N, 2 * H), x)
@@ -111,7 +114,7 @@ class GNNLayerFn(torch.autograd.Function):
                 _lib.ptr(b2), _lib.ptr(W3), _lib.ptr(W4), _lib.ptr(dx), _lib.ptr(du), _lib.ptr(dpos), _lib.ptr(dvar),
                 _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2), _lib.ptr(dW3), _lib.ptr(db3),
                 _lib.ptr(dW4), _lib.ptr(db4), 0, ctx.prec, _lib.ptr(ws), ws.numel(), _lib.stream()), "gnn_layer_bwd")
-        return dx, du, dpos, dvar, dW1, db1, dW2, db2, dW3, db3, dW4, db4, None, None
+        return dx, du, dpos, dvar, dW1, db1, dW2, db2, dW3, db3, dW4, db4, None, None, None
 
 
 # --------------------------------------------------------------------------------------------

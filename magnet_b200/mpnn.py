@@ -53,6 +53,7 @@ class GNN_Layer(nn.Module):
         self.update_net_1 = nn.Sequential(nn.Linear(in_features + hidden_features + n_variables, hidden_features), Swish())
         self.update_net_2 = nn.Sequential(nn.Linear(hidden_features, out_features), Swish())
         # the reference's `norm = InstanceNorm(hidden_features)` has no parameters or buffers
+        self._packed, self._pack_key = None, None
 
     def forward(self, x, u, pos, variables, edge_index, batch, *, plan=None, segments=None):
         n = x.shape[0]
@@ -61,8 +62,18 @@ class GNN_Layer(nn.Module):
         if segments is None:
             segments = MG.segments_for(batch, n)
         m1, m2, u1, u2 = self.message_net_1[0], self.message_net_2[0], self.update_net_1[0], self.update_net_2[0]
+        # kernel-side copies of the weights (packed, transposed, bf16 images): rebuilt only when a parameter changed
+        # (optimizer steps and load_state_dict bump the version counters); the module keeps its parameters alive, so
+        # (data_ptr, version) identifies their contents
+        ws = (m1.weight, m1.bias, m2.weight, u1.weight, u2.weight)
+        key = tuple((w.data_ptr(), w._version) for w in ws) + (u.shape[1], pos.shape[1], variables.shape[1],
+                                                               torch.cuda.current_stream().cuda_stream)
+        if self._pack_key != key:
+            f32 = [w.detach().float().contiguous() for w in ws]
+            self._packed = MF.pack_gnn_layer(*f32, u.shape[1], pos.shape[1], variables.shape[1])
+            self._pack_key = key
         return MF.GNNLayerFn.apply(x, u, pos, variables, m1.weight, m1.bias, m2.weight, m2.bias, u1.weight, u1.bias,
-                                   u2.weight, u2.bias, plan, segments)
+                                   u2.weight, u2.bias, plan, segments, self._packed)
 
 
 # temporal-bundling decoder shapes: time_window -> (kernel1, stride1, kernel2)   models/mpnn_2d.py:138-162
