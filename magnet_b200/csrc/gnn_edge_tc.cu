@@ -534,7 +534,7 @@ constexpr size_t edge_bwd_tc_smem() {
 // positions 0-31 of the tile, warps 8-11 positions 32-63); 12 MMA; 13 metadata; 14-21 producers (two groups of four
 // warps, group g fills stage g for the tiles with (it & 1) == g, 16 rows per warp)
 constexpr int BW_E1_WARPS = 8, BW_E2_WARPS = 8;
-constexpr int BW_MMA_WARP = 16, BW_META_WARP = 17, BW_PROD_WARP0 = 18, BW_PROD_WARPS = 8;
+constexpr int BW_MMA_WARP = 16, BW_META_WARP = 17, BW_PROD_WARP0 = 20, BW_PROD_WARPS = 8;     // warps 18, 19 idle (warpgroup padding)
 constexpr int BW_THREADS = (BW_PROD_WARP0 + BW_PROD_WARPS) * 32;     // 704
 constexpr int BW_FLUSH_TE = 32;
 constexpr int BW_D3_GROUP = 8;
@@ -599,7 +599,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
     const uint32_t tmem = *tmem_slot;
     const uint32_t tm_d1 = tmem, tm_d2 = tmem + 128, tm_d3 = tmem + 256;   // D1[s] at +64 s, D2[s] at +128 + 64 s, D3[buf] at +256 + 128 buf
 
+    // Registers follow the work: the producers hold a whole tile of gathered rows plus its converted image, the MMA and
+    // metadata warps need next to nothing (setmaxnreg moves registers between whole warpgroups; 896 x 72 in total).
     if (warp < BW_E1_WARPS) {
+        umma::reg_dec<56>();
         // =========================== epilogue 1: thread = channel n; warps 0-3 positions 0-31, warps 4-7 positions 32-63
         const int half = warp >> 2;
         const int pos0 = half * 32;
@@ -846,7 +849,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             if ((warp & 3) == 0) TL(3 + half, it, 2);
             umma::mbar_arrive(&mempty[ms]);
         }
+    } else if (warp < BW_PROD_WARP0 && warp != BW_MMA_WARP && warp != BW_META_WARP) {
+        umma::reg_dec<40>();          // padding warps of the MMA / metadata warpgroup
     } else if (warp == BW_MMA_WARP) {
+        umma::reg_dec<40>();
         // =========================== MMA issue ====================================================
         if (lane == 0) load_w2_image(w_img, a.w2img, NSPLIT * TILE_BYTES, wbar);
         umma::mbar_wait(wbar, 0);
@@ -863,6 +869,79 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         const uint64_t z_m = umma::desc_sw128(umma::smem_u32(dz_img), 128 * 128, 1024);     // DZt[n][e], MN-major (K = n)
         constexpr uint32_t WT = TILE_BYTES >> 4, HS = (NSPLIT * BW_HB) >> 4, HT = BW_HB >> 4, ZS = (NSPLIT * BW_ZB) >> 4,
                            ZT = BW_ZB >> 4;
+#ifdef MGB_BW_EVLOOP
+        // Event loop: MMA2/MMA3 of the oldest tile whose DZt is ready, else MMA1 of the next tile whose h1 is ready.
+        // (A fixed order would chain MMA3(t-1) -> producers(t+1) -> MMA1(t+1) -> MMA3(t): the two stages of h1 make
+        // the producers of tile t+1 wait for MMA3 of tile t-1.)
+        int i1 = 0, i2 = 0;
+        uint32_t idle = 0;
+#pragma unroll 1
+        while (i2 < nt) {
+            bool did = false;
+            if (i2 < i1) {
+                const int it = i2, s = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                const int grp = it / D3_GROUP, buf = grp & 1;
+                const bool first_in_group = (it % D3_GROUP) == 0;
+                const bool last = it == nt - 1;
+                if (umma::mbar_try(&dz_full[s], ph) && umma::mbar_try(&d2_empty[s], ph ^ 1) &&
+                    (!first_in_group || umma::mbar_try(&d3_empty[buf], ((grp >> 1) & 1) ^ 1))) {
+                    umma::tc_fence_after();
+                    TL(1, it, 1);
+                    if (umma::elect_one()) {
+                        const uint64_t hb = h_m + (uint64_t)(s * HS), zk = z_k + (uint64_t)(s * ZS), zm = z_m + (uint64_t)(s * ZS);
+                        const uint32_t d2 = tm_d2 + (uint32_t)(s * BTE), d3 = tm_d3 + (uint32_t)(buf * 128);
+#pragma unroll
+                        for (int term = 0; term < NTERM; ++term) {
+                            const uint64_t wa = w_m + (term == 2 ? WT : 0), zz = zm + (term == 1 ? ZT : 0);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)     // K = n: 16 rows = 2048 bytes per step
+                                umma::mma_bf16(d2, wa + (uint64_t)(k * 128), zz + (uint64_t)(k * 128), id_2, (term | k) ? 1u : 0u);
+                        }
+                        umma::mma_commit(&d2_full[s]);
+#pragma unroll
+                        for (int term = 0; term < NTERM; ++term) {
+                            const uint64_t za = zk + (term == 2 ? ZT : 0), hh = hb + (term == 1 ? HT : 0);
+#pragma unroll
+                            for (int k = 0; k < BTE / 16; ++k)     // K = e
+                                umma::mma_bf16(d3, za + (uint64_t)(k * 2), hh + (uint64_t)(k * 128), id_3, (term | k) ? 1u : (first_in_group ? 0u : 1u));
+                        }
+                        umma::mma_commit(&h_empty[s]);
+                        umma::mma_commit(&dz_empty[s]);
+                        if ((it % D3_GROUP) == D3_GROUP - 1 || last) umma::mma_commit(&d3_full[buf]);
+                    }
+                    __syncwarp();
+                    ++i2;
+                    did = true;
+                }
+            }
+            if (i1 < nt && i1 < i2 + 2) {
+                const int it1 = i1, s1 = it1 & 1;
+                if (umma::mbar_try(&h_full[s1], (it1 >> 1) & 1) && umma::mbar_try(&d1_empty[s1], ((it1 >> 1) & 1) ^ 1)) {
+                    umma::tc_fence_after();
+                    TL(1, it1, 0);
+                    if (umma::elect_one()) {
+                        const uint64_t hb = h_k + (uint64_t)(s1 * HS);
+                        const uint32_t d = tm_d1 + (uint32_t)(s1 * BTE);
+#pragma unroll
+                        for (int term = 0; term < NTERM; ++term) {
+                            const uint64_t wa = w_k + (term == 2 ? WT : 0), hh = hb + (term == 1 ? HT : 0);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                umma::mma_bf16(d, wa + (uint64_t)((k >> 2) * (128 * 128 >> 4) + (k & 3) * 2),
+                                               hh + (uint64_t)((k >> 2) * (BTE * 128 >> 4) + (k & 3) * 2), id_1, (term | k) ? 1u : 0u);
+                        }
+                        umma::mma_commit(&d1_full[s1]);
+                    }
+                    __syncwarp();
+                    ++i1;
+                    did = true;
+                }
+            }
+            if (did) idle = 0;
+            else if (++idle > (1u << 24)) __trap();      // bounded like every wait here: a protocol bug must not hang the GPU
+        }
+#else
         // MMA1 of tile it+1 is issued before MMA2/MMA3 of tile it: the tensor pipe works on the next tile while
         // epilogue 1 runs on this one
 #pragma unroll 1
@@ -924,7 +1003,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             __syncwarp();
             TL(1, it, 2);
         }
+#endif
     } else if (warp == BW_META_WARP) {
+        umma::reg_dec<40>();
         for (int it = 0; it < nt; ++it) {
             const int ms = it % BW_MSTAGES;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
@@ -933,6 +1014,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             umma::mbar_arrive(&mfull[ms]);
         }
     } else {
+        umma::reg_inc<104>();
         // =========================== producers: 8 rows per warp ====================================
         // h1[e][:] = Swish(P[dst_e] + Q[src_e]) -> bf16 (hi[/lo]) K-major swizzled image(s).  The eight Q-row gathers of a
         // tile (one 512-byte coalesced row per load instruction) and its edge indices are issued while the previous
@@ -994,7 +1076,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                     split2_bf16(h.z, h.w, hl[r].y, hl[r].w);
                 }
             }
-            umma::mbar_wait(&h_empty[s], ((it >> 1) & 1) ^ 1);
+            // the gathers of the next tile go out before this tile's stage is waited for: their latency overlaps the wait
+            d_cur = d_nxt; s_cur = s_nxt;
+            if (it + 1 < nt) issue_gathers();
+            load_idx(it + 2, d_nxt, s_nxt);
+            umma::mbar_wait_relaxed<128>(&h_empty[s], ((it >> 1) & 1) ^ 1);
             if (pw == 0) TL(0, it, 2);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
@@ -1005,9 +1091,6 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             umma::fence_async_smem();
             umma::mbar_arrive(&h_full[s]);
             if (pw == 0) TL(0, it, 1);
-            d_cur = d_nxt; s_cur = s_nxt;
-            if (it + 1 < nt) issue_gathers();
-            load_idx(it + 2, d_nxt, s_nxt);
         }
     }
     umma::tc_fence_before();

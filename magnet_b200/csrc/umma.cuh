@@ -27,6 +27,13 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per warp: every lane has done its part (writes, proxy fence, tcgen05 fence) before the warp barrier.
+// Waiting warps are woken by every arrival on any barrier of the CTA, so a barrier that 256 threads arrive on one by
+// one costs the sleepers hundreds of wake-ups per tile; counts are therefore in warps, not threads.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // Wait for the phase with the given parity.  try_wait parks the thread for a hardware-bounded time (about 80 cycles on
 // B200, whatever hint is passed) and a CTA here has twenty-odd warps waiting at any time, so the retry loop has to be
 // as short as possible or the waiting warps eat the issue slots of the working ones: try_wait, branch, count, compare.
@@ -58,7 +65,10 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// same, for waits that are not on the critical path (metadata several tiles ahead): back off between polls
+// same, for waits that are long by construction (a role that runs ahead of the pipeline): back off between polls so the
+// sleeper does not eat the issue slots of the working warps (a poll returns after ~60 cycles whether or not the phase
+// has completed; NS nanoseconds of sleep are added per failed poll)
+template <int NS = 256>
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -68,13 +78,13 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         "MGB_WAIT:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
         "@p bra MGB_DONE;\n\t"
-        "nanosleep.u32 256;\n\t"
+        "nanosleep.u32 %2;\n\t"
         "add.u32 c, c, 1;\n\t"
         "setp.lt.u32 p, c, 0x400000;\n\t"
         "@p bra MGB_WAIT;\n\t"
         "trap;\n"
         "MGB_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "n"(NS)
         : "memory");
 }
 // one lane of a converged warp (the compiler then knows the guarded region is single-threaded, which keeps the
@@ -91,6 +101,12 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- register re-allocation between the roles of a CTA (whole warpgroups: 4 consecutive warps) -------------------
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- TMEM -------------------------------------------------------------------------------------
 // whole warp; ncols power of two in [32, 512]; the base address lands in *dst_smem
