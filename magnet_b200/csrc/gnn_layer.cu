@@ -711,6 +711,8 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
     void* sub_ws = ws.base + ws.off;
     size_t sub_bytes = ws.cap - ws.off;
     const int acc = io.accumulate_params;
+    // nobody asked for du / dpos / dvar (the usual case: they are data): dx comes straight out of the last data-gradient Linear
+    const bool fuse_dx = tc_nodes && !io.du && !io.dpos && !io.dvar;
 
     // B1. InstanceNorm backward -> d0 = d(out)
     MGB_TRY(instance_norm_bwd(io.dy, io.y, io.rstd, io.gptr, sh.n_graphs, sh.max_nodes_per_graph, d0, sub_ws, sub_bytes, s));
@@ -754,6 +756,7 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         a.src[0] = d1; a.ld[0] = H; a.nk = 1; a.pre = io.y1_pre; a.ldpre = H; a.pre_act = ACT_SWISH;
         a.wimg = p.img_w3; a.nm = 2; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[1][0] = 1;
         a.act = ACT_NONE; a.y = dc; a.ldy = ldc; a.rows = N;
+        if (fuse_dx) { a.residual = d0; a.ldr = H; a.res_blocks = 1; }      // dc[:, :H] += d0 (the residual branch of the update)
         MGB_TRY(launch_linear_tc(sh.precision, a, s));
         if (io.dvar)      // the tail columns of dc feed dvar only
             MGB_TRY(launch_tail_dgrad(d1, H, H, io.y1_pre, H, ACT_SWISH, io.W3 + 2 * H, sh.K3(), 1, sh.nv, N, dc + 2 * H, ldc, s));
@@ -829,6 +832,7 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         a.src[0] = dpq; a.ld[0] = 2 * H; a.src[1] = dpq + H; a.ld[1] = 2 * H; a.nk = 2;
         a.wimg = p.img_pq; a.nm = 1; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[0][1] = 1;
         a.act = ACT_NONE; a.y = dxc; a.ldy = ldx; a.rows = N;
+        if (fuse_dx) { a.y = io.dx; a.ldy = H; a.residual = dc; a.ldr = ldc; }   // dx = dPQ Wcat[:, :H] + (d0 + dc[:, :H]): no assembly pass
         MGB_TRY(launch_linear_tc(sh.precision, a, s));
         if (io.du || io.dpos || io.dvar)      // the tail columns of dxc feed du / dpos / dvar only
             MGB_TRY(launch_tail_dgrad(dpq, 2 * H, 2 * H, nullptr, 0, ACT_NONE, p.wcat + H, sh.Kc(), 1, kt_pq, N, dxc + H, ldx, s));
@@ -851,6 +855,7 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         MGB_TRY(launch_gemm(g, s));
     }
     // B7. assemble the input gradients
+    if (!fuse_dx)
     gnn_combine_grads_kernel<<<(unsigned)ceil_div<int64_t>((int64_t)N * sh.Kc(), 256), 256, 0, s>>>(
         d0, dc, ldc, dxc, ldx, N, sh.tw, sh.dp, sh.nv, io.dx, io.du, io.dpos, io.dvar);
     MGB_LAUNCH_CHECK();

@@ -20,6 +20,17 @@ constexpr int LT_MMA_WARP = LT_EPI_WARPS, LT_PROD_WARP0 = LT_EPI_WARPS + 1;
 constexpr int LT_THREADS = (LT_EPI_WARPS + 1 + LT_PROD_WARPS) * 32;   // 544
 constexpr int LT_TAIL = 16;
 
+// L2 prefetch of 16 rows x 512 bytes (64 lines of 128 bytes, two per lane): the row loads of the next tile and the 4-byte
+// residual loads of the epilogue then hit L2 instead of paying the HBM latency in the middle of the pipeline
+__device__ __forceinline__ void prefetch_rows16(const float* base, int64_t ld, int64_t r0, int64_t n_rows, int lane) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int line = j * 32 + lane;            // row = line / 4, 128-byte line inside the row = line % 4
+        const int64_t row = r0 + (line >> 2);
+        if (row < n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + row * ld + (line & 3) * 32));
+    }
+}
+
 // W [rows_total][ld] fp32, tile = W[r0:r0+128, c0:c0+128] (zero outside) -> swizzled bf16 images hi | lo
 __global__ void pack_weight_tile_kernel(const float* __restrict__ W, int ld, int n_rows, int n_cols, int r0, int c0,
                                         unsigned char* __restrict__ img) {
@@ -115,10 +126,26 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
 #pragma unroll
                 for (int t = 0; t < LT_TAIL; ++t) wt[t] = t < a.kt ? a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st] : 0.f;
                 const bool last_m = m == a.nm - 1;
+                // residual values two chunks ahead of the chunk being processed (4-byte loads, one coalesced 128-byte
+                // line per warp and row: their latency must not sit between two chunks)
+                const float* rp = (a.residual && (a.res_blocks == 0 || ((a.res_blocks >> m) & 1))) ? a.residual + (r0 + hf * 64) * a.ldr + col : nullptr;
+                const int rlim = nr - hf * 64;
+                float rn1[8], rn2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    rn1[i] = (rp && i < rlim) ? rp[(int64_t)i * a.ldr] : 0.f;
+                    rn2[i] = (rp && 8 + i < rlim) ? rp[(int64_t)(8 + i) * a.ldr] : 0.f;
+                }
 #pragma unroll 1
                 for (int cb = 0; cb < 64; cb += 8) {
                     const int c0 = hf * 64 + cb;
-                    float v[8];
+                    float v[8], res[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { res[i] = rn1[i]; rn1[i] = rn2[i]; }
+                    if (rp && cb + 16 < 64) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) rn2[i] = cb + 16 + i < rlim ? rp[(int64_t)(cb + 16 + i) * a.ldr] : 0.f;
+                    }
                     umma::tmem_ld8(tmem + (uint32_t)((acc * 2 + m) * 128) + lane_base + c0, v);
                     if (last_m && cb + 8 >= 64 && a.kt == 0) {
                         umma::tc_fence_before();
@@ -157,12 +184,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (a.residual) {
-                        const float* rp = a.residual + row0 * a.ldr + col;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (i < lim) v[i] += rp[(int64_t)i * a.ldr];
-                    }
+                    for (int i = 0; i < 8; ++i) v[i] += res[i];
                     float* yo = a.y + row0 * a.ldy + col;
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
@@ -231,6 +254,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + pw * 16;
+            {
+                const int64_t rn = r0 + (int64_t)gridDim.x * 128;      // this warp's rows of the CTA's next tile
+                for (int kc = 0; kc < a.nk; ++kc) prefetch_rows16(a.src[kc], a.ld[kc], rn, a.rows, lane);
+                if (a.pre) prefetch_rows16(a.pre, a.ldpre, rn, a.rows, lane);
+                if (a.residual) prefetch_rows16(a.residual, a.ldr, r0, a.rows, lane);      // read by the epilogue of this tile
+            }
             if (a.kt > 0) {
                 umma::mbar_wait(&tempty[acc], aph ^ 1);
                 float* tl = tails + acc * 128 * LT_TAIL + pw * 16 * LT_TAIL;
@@ -524,6 +553,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
 #pragma unroll 1
         for (int it = 0; it < nt; ++it) {
             const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + pw * 16;
+            {
+                const int64_t rn = r0 + (int64_t)gridDim.x * 128;      // this warp's rows of the CTA's next tile
+                for (int yi = 0; yi < a.ny; ++yi) {
+                    prefetch_rows16(a.dy + yi * 128, a.lddy, rn, a.rows, lane);
+                    if (a.y_pre) prefetch_rows16(a.y_pre + yi * 128, a.ldyp, rn, a.rows, lane);
+                }
+                for (int xi = 0; xi < a.nx; ++xi) prefetch_rows16(a.x[xi], a.ldx[xi], rn, a.rows, lane);
+            }
             float4 x[16];
 #pragma unroll 1
             for (int yi = 0; yi < a.ny; ++yi) {
