@@ -125,6 +125,14 @@ int mgb_gnn_layer_bwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
 int mgb_transpose(const float* in, int rows, int cols, float* out, void* stream);
 int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* wt, const float* bias,
                    int act, const float* residual, float* y, float* y_pre, void* stream);
+/* The same Linear on the tensor cores (tcgen05, bf16 hi/lo split: 1e-5 contract; or plain bf16: 1e-2), for
+ * in_features 128 or 256 and out_features <= 256 (mgb_linear_tc_packed_floats returns 0 for anything else).
+ * packed = swizzled bf16 images of W [out, in] (row stride ldw), built once per weight version by mgb_linear_tc_pack. */
+size_t mgb_linear_tc_packed_floats(int in_features, int out_features);
+int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, float* packed, void* stream);
+int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* packed,
+                      const float* bias, int act, const float* residual, float* y, float* y_pre, int precision,
+                      void* stream);
 size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features);
 /* dx = (dy * act'(y_pre)) W;  dW (+)= (dy * act'(y_pre))^T x;  db (+)= colsum.  dx may be NULL. */
 int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features,

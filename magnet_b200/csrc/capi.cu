@@ -113,6 +113,47 @@ int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_featur
     return launch_gemm(g, STREAM(stream));
 }
 
+// ---- nn.Linear on the tensor cores (linear_tc.cu): in_features 128 or 256, out_features <= 256, at most two weight tiles
+static bool linear_tc_shape(int in_features, int out_features, int* nk, int* nm) {
+    if (in_features != 128 && in_features != 256) return false;
+    if (out_features < 1 || out_features > 256) return false;
+    *nk = in_features / 128;
+    *nm = (out_features + 127) / 128;
+    return *nk * *nm <= 2;
+}
+
+size_t mgb_linear_tc_packed_floats(int in_features, int out_features) {
+    int nk, nm;
+    if (!linear_tc_shape(in_features, out_features, &nk, &nm)) return 0;
+    return (size_t)nk * nm * 2 * 128 * 128 / 2;       // per tile: two bf16 images (hi | lo) of 128 x 128
+}
+
+int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, float* packed, void* stream) {
+    int nk, nm;
+    MGB_REQUIRE(linear_tc_shape(in_features, out_features, &nk, &nm), "linear_tc_pack: unsupported shape %d -> %d", in_features, out_features);
+    for (int m = 0; m < nm; ++m)
+        for (int kc = 0; kc < nk; ++kc)
+            MGB_TRY(pack_weight_tile(W, ldw, out_features, in_features, m * 128, kc * 128, packed + (size_t)(m * nk + kc) * 128 * 128, STREAM(stream)));
+    return MGB_OK;
+}
+
+int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* packed, const float* bias,
+                      int act, const float* residual, float* y, float* y_pre, int precision, void* stream) {
+    int nk, nm;
+    MGB_REQUIRE(linear_tc_shape(in_features, out_features, &nk, &nm), "linear_tc_fwd: unsupported shape %d -> %d", in_features, out_features);
+    MGB_REQUIRE(act >= 0 && act <= 2, "linear_tc_fwd: unknown activation %d", act);
+    MGB_REQUIRE(precision == 1 || precision == 2, "linear_tc_fwd: precision must be 1 (bf16 hi/lo split) or 2 (bf16)");
+    LinTcArgs a{};
+    for (int kc = 0; kc < nk; ++kc) { a.src[kc] = x + kc * 128; a.ld[kc] = in_features; }
+    a.nk = nk; a.nm = nm;
+    for (int m = 0; m < nm; ++m)
+        for (int kc = 0; kc < nk; ++kc) a.tile_of[m][kc] = m * nk + kc;
+    a.wimg = packed; a.bias = bias; a.act = act; a.n_out = out_features;
+    a.residual = residual; a.ldr = out_features;
+    a.y = y; a.ldy = out_features; a.y_pre = y_pre; a.ldyp = out_features; a.rows = rows;
+    return launch_linear_tc(precision, a, STREAM(stream));
+}
+
 size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features) {
     return wgrad_workspace_bytes((int)rows, out_features, in_features) + 1024;
 }

@@ -111,6 +111,7 @@ struct LinTcArgs {
     const void* wimg;                               // weight tiles (hi|lo images), 64 KB each
     int nm, a_trans; int tile_of[2][2];             // tile index used by (output block m, chunk kc)
     const float* bias; int act;
+    int n_out;                                      // valid output columns (0 = all 128*nm): the rest is neither biased nor stored
     const float* residual; int ldr; int res_blocks;   // residual added to output block m if bit m of res_blocks is set (0 = all blocks)
     float* y; int ldy; float* y_pre; int ldyp;
     int64_t rows;

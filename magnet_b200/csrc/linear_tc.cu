@@ -121,14 +121,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
 #pragma unroll 1
             for (int m = 0; m < a.nm; ++m) {
                 const int col = m * 128 + n;
-                const float bias = a.bias ? a.bias[col] : 0.f;
+                const bool col_ok = a.n_out == 0 || col < a.n_out;
+                const float bias = (a.bias && col_ok) ? a.bias[col] : 0.f;
                 float wt[LT_TAIL];
 #pragma unroll
-                for (int t = 0; t < LT_TAIL; ++t) wt[t] = t < a.kt ? a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st] : 0.f;
+                for (int t = 0; t < LT_TAIL; ++t) wt[t] = (t < a.kt && col_ok) ? a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st] : 0.f;
                 const bool last_m = m == a.nm - 1;
                 // residual values two chunks ahead of the chunk being processed (4-byte loads, one coalesced 128-byte
                 // line per warp and row: their latency must not sit between two chunks)
-                const float* rp = (a.residual && (a.res_blocks == 0 || ((a.res_blocks >> m) & 1))) ? a.residual + (r0 + hf * 64) * a.ldr + col : nullptr;
+                const float* rp = (a.residual && col_ok && (a.res_blocks == 0 || ((a.res_blocks >> m) & 1))) ? a.residual + (r0 + hf * 64) * a.ldr + col : nullptr;
                 const int rlim = nr - hf * 64;
                 float rn1[8], rn2[8];
 #pragma unroll
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] += bias;
-                    const int lim = nr - c0;
+                    const int lim = col_ok ? nr - c0 : 0;
                     const int64_t row0 = r0 + c0;
                     if (a.y_pre) {
                         float* yp = a.y_pre + row0 * a.ldyp + col;

@@ -26,9 +26,19 @@ def _layer_shapes(tw, dp):
                                                (129, 128, 10, "none"), (5, 132, 128, "relu"), (2048, 128, 1, "none")])
 def test_linear_act_fwd_bwd(rows, fin, fout, act):
     g = S._gen(rows)
-    x = torch.randn(rows, fin, generator=g).to(DEV).requires_grad_()
-    W = (torch.randn(fout, fin, generator=g) / fin ** 0.5).to(DEV).requires_grad_()
-    b = torch.randn(fout, generator=g).to(DEV).requires_grad_()
+    x = torch.randn(rows, fin, generator=g)
+    W = torch.randn(fout, fin, generator=g) / fin ** 0.5
+    b = torch.randn(fout, generator=g)
+    if act == "relu":
+        # ReLU' is discontinuous at 0: a pre-activation within rounding distance of the kink flips the mask of any fp32
+        # implementation (the reference's included), so rows that have one are redrawn until none is closer than 1e-3
+        for _ in range(50):
+            near = ((x.double() @ W.double().T + b.double()).abs() < 1e-3).any(1)
+            if not near.any():
+                break
+            x[near] = torch.randn(int(near.sum()), fin, generator=g)
+        assert not near.any()
+    x, W, b = x.to(DEV).requires_grad_(), W.to(DEV).requires_grad_(), b.to(DEV).requires_grad_()
     res = torch.randn(rows, fout, generator=g).to(DEV).requires_grad_()
     y = MF.linear_act(x, W, b, act, res)
     gy = torch.randn(rows, fout, generator=g).to(DEV)
@@ -40,6 +50,28 @@ def test_linear_act_fwd_bwd(rows, fin, fout, act):
     assert rel_err(y, z) < TOL
     for got, want in ((x.grad, xd.grad), (W.grad, Wd.grad), (b.grad, bd.grad), (res.grad, rd.grad)):
         assert rel_err(got, want) < TOL
+
+
+@pytest.mark.parametrize("rows,fin,fout,act", [(777, 128, 128, "relu"), (129, 128, 10, "none"), (2048, 128, 1, "none"),
+                                               (1000, 256, 128, "swish"), (300, 128, 256, "none")])
+def test_linear_act_tensor_core_path(rows, fin, fout, act):
+    """Opt-in tcgen05 Linear (bf16 hi/lo split): same call, same results within the 1e-5 contract of a single Linear."""
+    g = S._gen(rows + 1)
+    x = torch.randn(rows, fin, generator=g).to(DEV)
+    W = (torch.randn(fout, fin, generator=g) / fin ** 0.5).to(DEV)
+    b = torch.randn(fout, generator=g).to(DEV)
+    res = torch.randn(rows, fout, generator=g).to(DEV)
+    old = MF.set_linear_tc(True)
+    try:
+        assert MF._tc_weight_images(W) is not None
+        with torch.no_grad():
+            y = MF.linear_act(x, W, b, act, res)
+            y2 = MF.linear_act(x, W, b, act, res)          # cached weight images
+    finally:
+        MF.set_linear_tc(old)
+    z = torch.nn.functional.linear(x.double().cpu(), W.double().cpu(), b.double().cpu())
+    z = {"swish": lambda v: v * torch.sigmoid(v), "relu": torch.relu, "none": lambda v: v}[act](z) + res.double().cpu()
+    assert rel_err(y, z) < TOL and torch.equal(y, y2)
 
 
 def test_layernorm_fwd_bwd():
