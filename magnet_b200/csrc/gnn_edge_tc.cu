@@ -149,63 +149,6 @@ __device__ __forceinline__ void build_tile_meta(TileMetaT<TE>* M, const int32_t*
     if (lane == 0) M->nseg = base;
 }
 
-// Producer warp `pw` fills rows [pw*ROWS, (pw+1)*ROWS) of an edge tile of TE positions (ROWS = 16 or 32):
-//   h1[e][:] = Swish(P[dst_e] + Q[src_e])  ->  bf16 (hi[/lo]) K-major swizzled image(s) of TE rows (lo image at +img_bytes).
-// The Q-row gathers are issued 16 rows at a time before their first use (one 512-byte coalesced row per
-// load instruction, float4 per lane); the P row is reused while dst stays the same.
-template <int NSPLIT, bool FAST, int TE, int ROWS>
-__device__ __forceinline__ void produce_h1_rows(const float* __restrict__ pq, const int32_t* __restrict__ dstv,
-                                                const int32_t* __restrict__ srcv, int64_t n_edges, int64_t tile, int pw,
-                                                int lane, uint64_t* empty_bar, uint32_t empty_parity, unsigned char* img,
-                                                uint32_t img_bytes) {
-    static_assert(ROWS == 16 || ROWS == 32, "16 or 32 rows per producer warp");
-    const int64_t e0 = tile * TE + pw * ROWS;
-    int my_d = -1, my_s = -1;
-    if (lane < ROWS && e0 + lane < n_edges) {
-        my_d = dstv[e0 + lane];
-        my_s = srcv[e0 + lane];
-    }
-    // byte offset of this lane's 4 channels inside a row of the swizzled image (row & 7 == r & 7 as pw*ROWS % 8 == 0)
-    const uint32_t lane_blk = (uint32_t)(lane >> 4) * ((uint32_t)TE * 128u) + (uint32_t)(lane & 1) * 8u;
-    const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
-    int prev_d = __shfl_sync(0xffffffffu, my_d, 0);
-    float4 p = *reinterpret_cast<const float4*>(pq + (int64_t)(prev_d < 0 ? 0 : prev_d) * (2 * TCH) + lane * 4);
-#pragma unroll 1
-    for (int r0 = 0; r0 < ROWS; r0 += 16) {
-        float4 q[16];
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int sidx = __shfl_sync(0xffffffffu, my_s, r0 + r);
-            q[r] = *reinterpret_cast<const float4*>(pq + (int64_t)(sidx < 0 ? 0 : sidx) * (2 * TCH) + TCH + lane * 4);
-        }
-        if (r0 == 0) umma::mbar_wait(empty_bar, empty_parity);
-#pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int d = __shfl_sync(0xffffffffu, my_d, r0 + r);
-            if (d != prev_d) {
-                if (d >= 0) p = *reinterpret_cast<const float4*>(pq + (int64_t)d * (2 * TCH) + lane * 4);
-                prev_d = d;
-            }
-            float4 h;
-            h.x = swish_tc<FAST>(p.x + q[r].x);
-            h.y = swish_tc<FAST>(p.y + q[r].y);
-            h.z = swish_tc<FAST>(p.z + q[r].z);
-            h.w = swish_tc<FAST>(p.w + q[r].w);
-            if (d < 0) h = make_float4(0.f, 0.f, 0.f, 0.f);
-            const uint32_t off = lane_blk + (uint32_t)(pw * ROWS + r0 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
-            if (NSPLIT == 1) {
-                *reinterpret_cast<uint2*>(img + off) = make_uint2(umma::pack_bf16(h.x, h.y), umma::pack_bf16(h.z, h.w));
-            } else {
-                uint2 hi, lo;
-                split2_bf16(h.x, h.y, hi.x, lo.x);
-                split2_bf16(h.z, h.w, hi.y, lo.y);
-                *reinterpret_cast<uint2*>(img + off) = hi;
-                *reinterpret_cast<uint2*>(img + img_bytes + off) = lo;
-            }
-        }
-    }
-}
-
 // ==================================================================================================
 // Forward
 // ==================================================================================================
@@ -942,79 +885,6 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
         const uint64_t z_m = umma::desc_sw128(umma::smem_u32(dz_img), 128 * 128, 1024);     // DZt[n][e], MN-major (K = n)
         constexpr uint32_t WT = TILE_BYTES >> 4, HS = (NSPLIT * BW_HB) >> 4, HT = BW_HB >> 4, ZS = (NSPLIT * BW_ZB) >> 4,
                            ZT = BW_ZB >> 4;
-#ifdef MGB_BW_EVLOOP
-        // Event loop: MMA2/MMA3 of the oldest tile whose DZt is ready, else MMA1 of the next tile whose h1 is ready.
-        // (A fixed order would chain MMA3(t-1) -> producers(t+1) -> MMA1(t+1) -> MMA3(t): the two stages of h1 make
-        // the producers of tile t+1 wait for MMA3 of tile t-1.)
-        int i1 = 0, i2 = 0;
-        uint32_t idle = 0;
-#pragma unroll 1
-        while (i2 < nt) {
-            bool did = false;
-            if (i2 < i1) {
-                const int it = i2, s = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                const int grp = it / D3_GROUP, buf = grp & 1;
-                const bool first_in_group = (it % D3_GROUP) == 0;
-                const bool last = it == nt - 1;
-                if (umma::mbar_try(&dz_full[s], ph) && umma::mbar_try(&d2_empty[s], ph ^ 1) &&
-                    (!first_in_group || umma::mbar_try(&d3_empty[buf], ((grp >> 1) & 1) ^ 1))) {
-                    umma::tc_fence_after();
-                    TL(1, it, 1);
-                    if (umma::elect_one()) {
-                        const uint64_t hb = h_m + (uint64_t)(s * HS), zk = z_k + (uint64_t)(s * ZS), zm = z_m + (uint64_t)(s * ZS);
-                        const uint32_t d2 = tm_d2 + (uint32_t)(s * BTE), d3 = tm_d3 + (uint32_t)(buf * 128);
-#pragma unroll
-                        for (int term = 0; term < NTERM; ++term) {
-                            const uint64_t wa = w_m + (term == 2 ? WT : 0), zz = zm + (term == 1 ? ZT : 0);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)     // K = n: 16 rows = 2048 bytes per step
-                                umma::mma_bf16(d2, wa + (uint64_t)(k * 128), zz + (uint64_t)(k * 128), id_2, (term | k) ? 1u : 0u);
-                        }
-                        umma::mma_commit(&d2_full[s]);
-#pragma unroll
-                        for (int term = 0; term < NTERM; ++term) {
-                            const uint64_t za = zk + (term == 2 ? ZT : 0), hh = hb + (term == 1 ? HT : 0);
-#pragma unroll
-                            for (int k = 0; k < BTE / 16; ++k)     // K = e
-                                umma::mma_bf16(d3, za + (uint64_t)(k * 2), hh + (uint64_t)(k * 128), id_3, (term | k) ? 1u : (first_in_group ? 0u : 1u));
-                        }
-                        umma::mma_commit(&h_empty[s]);
-                        umma::mma_commit(&dz_empty[s]);
-                        if ((it % D3_GROUP) == D3_GROUP - 1 || last) umma::mma_commit(&d3_full[buf]);
-                    }
-                    __syncwarp();
-                    ++i2;
-                    did = true;
-                }
-            }
-            if (i1 < nt && i1 < i2 + 2) {
-                const int it1 = i1, s1 = it1 & 1;
-                if (umma::mbar_try(&h_full[s1], (it1 >> 1) & 1) && umma::mbar_try(&d1_empty[s1], ((it1 >> 1) & 1) ^ 1)) {
-                    umma::tc_fence_after();
-                    TL(1, it1, 0);
-                    if (umma::elect_one()) {
-                        const uint64_t hb = h_k + (uint64_t)(s1 * HS);
-                        const uint32_t d = tm_d1 + (uint32_t)(s1 * BTE);
-#pragma unroll
-                        for (int term = 0; term < NTERM; ++term) {
-                            const uint64_t wa = w_k + (term == 2 ? WT : 0), hh = hb + (term == 1 ? HT : 0);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                umma::mma_bf16(d, wa + (uint64_t)((k >> 2) * (128 * 128 >> 4) + (k & 3) * 2),
-                                               hh + (uint64_t)((k >> 2) * (BTE * 128 >> 4) + (k & 3) * 2), id_1, (term | k) ? 1u : 0u);
-                        }
-                        umma::mma_commit(&d1_full[s1]);
-                    }
-                    __syncwarp();
-                    ++i1;
-                    did = true;
-                }
-            }
-            if (did) idle = 0;
-            else if (++idle > (1u << 24)) __trap();      // bounded like every wait here: a protocol bug must not hang the GPU
-        }
-#else
         // MMA1 of tile it+1 is issued before MMA2/MMA3 of tile it: the tensor pipe works on the next tile while
         // epilogue 1 runs on this one
 #pragma unroll 1
@@ -1076,7 +946,6 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             __syncwarp();
             TL(1, it, 2);
         }
-#endif
     } else if (warp == BW_META_WARP) {
         umma::reg_dec<40>();
         for (int it = 0; it < nt; ++it) {
