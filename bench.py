@@ -401,6 +401,9 @@ def run_ours(args, rank, world, local_rank):
                     "kernel_ms": bwd_ms, "kernel_share_of_step": bt / total_ms if total_ms > 0 else None,
                     "executed_tflops": 3 * EXEC_FLOP_PER_EDGE_FWD * E / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0,
                     "edge_fwd_kernel_ms": fwd_ms,
+                    # other floors of the same kernel: fp32-accurate Swish costs 6 transcendental ops per
+                    # edge-channel in the backward kernel (4 in the forward one) on a 16-lane/clk/SM MUFU pipe
+                    "mufu_floor_ms": (6 if args.precision != "bf16" else 3) * E * 128 / (16 * 148 * 1.965e9) * 1e3,
                     "edge_fwd_algorithmic_tflops": FLOP_PER_EDGE_FWD * E / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0,
                     "note": {"fp32": "fp32 FFMA path (1e-5 contract) measured against the bf16 tensor peak",
                              "fp32_tc": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (1e-5 contract)",
