@@ -125,11 +125,14 @@ int mgb_gnn_layer_bwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
 int mgb_transpose(const float* in, int rows, int cols, float* out, void* stream);
 int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* wt, const float* bias,
                    int act, const float* residual, float* y, float* y_pre, void* stream);
-/* The same Linear on the tensor cores (tcgen05, bf16 hi/lo split: 1e-5 contract; or plain bf16: 1e-2), for
- * in_features 128 or 256 and out_features <= 256 (mgb_linear_tc_packed_floats returns 0 for anything else).
- * packed = swizzled bf16 images of W [out, in] (row stride ldw), built once per weight version by mgb_linear_tc_pack. */
+/* The same Linear on the tensor cores (tcgen05), for in_features 128 or 256 and out_features <= 256
+ * (mgb_linear_tc_packed_floats returns 0 for anything else).  precision: 1 bf16 hi/lo split (16 significant bits),
+ * 2 plain bf16 (1e-2 contract), 3 fp16 hi/lo split (22 significant bits; inputs and weights must be O(1), |x| < 65504).
+ * packed = swizzled 16-bit images of W [out, in] (row stride ldw) in the format of `precision`, built once per weight
+ * version by mgb_linear_tc_pack. */
 size_t mgb_linear_tc_packed_floats(int in_features, int out_features);
-int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, float* packed, void* stream);
+int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, int precision, float* packed,
+                       void* stream);
 int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* packed,
                       const float* bias, int act, const float* residual, float* y, float* y_pre, int precision,
                       void* stream);

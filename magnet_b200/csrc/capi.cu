@@ -128,13 +128,28 @@ size_t mgb_linear_tc_packed_floats(int in_features, int out_features) {
     return (size_t)nk * nm * 2 * 128 * 128 / 2;       // per tile: two bf16 images (hi | lo) of 128 x 128
 }
 
-int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, float* packed, void* stream) {
+int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, int precision, float* packed, void* stream) {
     int nk, nm;
     MGB_REQUIRE(linear_tc_shape(in_features, out_features, &nk, &nm), "linear_tc_pack: unsupported shape %d -> %d", in_features, out_features);
     for (int m = 0; m < nm; ++m)
         for (int kc = 0; kc < nk; ++kc)
-            MGB_TRY(pack_weight_tile(W, ldw, out_features, in_features, m * 128, kc * 128, packed + (size_t)(m * nk + kc) * 128 * 128, STREAM(stream)));
+            MGB_TRY(pack_weight_tile(W, ldw, out_features, in_features, m * 128, kc * 128, packed + (size_t)(m * nk + kc) * 128 * 128, STREAM(stream), precision == 3));
     return MGB_OK;
+}
+
+// fp16 range guard of the fp16-split Linear: a host-mapped flag the producers raise when they meet |x| >= 32768.  It is
+// checked (without synchronising) at the start of every later call, so an out-of-range input surfaces as an error on one
+// of the next calls instead of silently turning into infinities.
+static int* f16_range_flag(int** dev_ptr) {
+    static int* host = nullptr;
+    static int* dev = nullptr;
+    if (!host) {
+        if (cudaHostAlloc((void**)&host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { host = nullptr; return nullptr; }
+        *host = 0;
+        if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess) dev = nullptr;
+    }
+    if (dev_ptr) *dev_ptr = dev;
+    return host;
 }
 
 int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* packed, const float* bias,
@@ -142,8 +157,17 @@ int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_fea
     int nk, nm;
     MGB_REQUIRE(linear_tc_shape(in_features, out_features, &nk, &nm), "linear_tc_fwd: unsupported shape %d -> %d", in_features, out_features);
     MGB_REQUIRE(act >= 0 && act <= 2, "linear_tc_fwd: unknown activation %d", act);
-    MGB_REQUIRE(precision == 1 || precision == 2, "linear_tc_fwd: precision must be 1 (bf16 hi/lo split) or 2 (bf16)");
+    MGB_REQUIRE(precision >= 1 && precision <= 3, "linear_tc_fwd: precision must be 1 (bf16 hi/lo split), 2 (bf16) or 3 (fp16 hi/lo split)");
     LinTcArgs a{};
+    if (precision == 3) {
+        int* dev_flag = nullptr;
+        volatile int* host_flag = f16_range_flag(&dev_flag);
+        if (host_flag && *host_flag) {
+            *host_flag = 0;
+            MGB_REQUIRE(false, "linear_tc_fwd: an earlier fp16-split Linear met |x| >= 32768 (fp16 range); use the fp32 path (set_linear_tc(False)) for this data");
+        }
+        a.range_flag = dev_flag;
+    }
     for (int kc = 0; kc < nk; ++kc) { a.src[kc] = x + kc * 128; a.ld[kc] = in_features; }
     a.nk = nk; a.nm = nm;
     for (int m = 0; m < nm; ++m)

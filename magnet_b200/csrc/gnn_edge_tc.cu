@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
             const int ms = it % META_STAGES;
             const TileMeta* M = metas + ms;
             umma::mbar_wait(&mfull[ms], (it / META_STAGES) & 1);
-            umma::mbar_wait(&tfull[acc], aph);
+            umma::mbar_wait_relaxed<64>(&tfull[acc], aph);
             umma::tc_fence_after();
             float sum = 0.f;
 #pragma unroll 1
@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             const uint32_t emw = M->endmask[half], fmw = M->flushmask[half];
             float* dz_tile = a.dz1 + (tile * BTE + pos0) * TCH + n;     // dz1 is padded to whole tiles: no bounds checks
             if ((warp & 3) == 0) TL(3 + half, it, 0);
-            umma::mbar_wait(&d2_full[s], ph);
+            umma::mbar_wait_relaxed<64>(&d2_full[s], ph);
             umma::tc_fence_after();
             if ((warp & 3) == 0) TL(3 + half, it, 1);
 #pragma unroll 1

@@ -111,6 +111,7 @@ struct LinTcArgs {
     const void* wimg;                               // weight tiles (hi|lo images), 64 KB each
     int nm, a_trans; int tile_of[2][2];             // tile index used by (output block m, chunk kc)
     const float* bias; int act;
+    int* range_flag;                                // fp16 split only: set to 1 by a producer that meets |x| >= 32768 (host-mapped)
     int n_out;                                      // valid output columns (0 = all 128*nm): the rest is neither biased nor stored
     const float* residual; int ldr; int res_blocks;   // residual added to output block m if bit m of res_blocks is set (0 = all blocks)
     float* y; int ldy; float* y_pre; int ldyp;
@@ -130,7 +131,7 @@ struct WgradTcArgs {
 struct WgradTcOut {          // destination of accumulator (y, x): dw[n*lddw + k], n < n_valid, k < k_valid
     float* dw; int lddw; int n_valid, k_valid; int accumulate;
 };
-int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s);
+int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s, int f16 = 0);
 int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s);
 size_t wgrad_tc_workspace(int64_t rows);
 int launch_wgrad_tc(int precision, WgradTcArgs a, const WgradTcOut* outs /*[ny][nx + tail]*/, void* ws, size_t ws_bytes,

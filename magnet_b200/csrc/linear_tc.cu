@@ -33,20 +33,27 @@ __device__ __forceinline__ void prefetch_rows16(const float* base, int64_t ld, i
 
 // W [rows_total][ld] fp32, tile = W[r0:r0+128, c0:c0+128] (zero outside) -> swizzled bf16 images hi | lo
 __global__ void pack_weight_tile_kernel(const float* __restrict__ W, int ld, int n_rows, int n_cols, int r0, int c0,
-                                        unsigned char* __restrict__ img) {
+                                        unsigned char* __restrict__ img, int f16) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 128 * 128) return;
     const int r = idx >> 7, c = idx & 127;
     const float v = (r0 + r < n_rows && c0 + c < n_cols) ? W[(int64_t)(r0 + r) * ld + c0 + c] : 0.f;
-    __nv_bfloat16 hi, lo;
-    umma::split_bf16(v, hi, lo);
     const uint32_t off = umma::tile_off(128, r, c);
-    *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
-    *reinterpret_cast<__nv_bfloat16*>(img + TILE_BYTES + off) = lo;
+    if (f16) {
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        *reinterpret_cast<__half*>(img + off) = hi;
+        *reinterpret_cast<__half*>(img + TILE_BYTES + off) = lo;
+    } else {
+        __nv_bfloat16 hi, lo;
+        umma::split_bf16(v, hi, lo);
+        *reinterpret_cast<__nv_bfloat16*>(img + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(img + TILE_BYTES + off) = lo;
+    }
 }
 
-int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s) {
-    pack_weight_tile_kernel<<<64, 256, 0, s>>>(W, ld, n_rows, n_cols, r0, c0, (unsigned char*)img);
+int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s, int f16) {
+    pack_weight_tile_kernel<<<64, 256, 0, s>>>(W, ld, n_rows, n_cols, r0, c0, (unsigned char*)img, f16);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }
@@ -57,7 +64,9 @@ constexpr size_t LINEAR_TC_SMEM = 1024 + (size_t)4 * TILE_BYTES + (size_t)2 * TI
 
 // All role loops are kept small on purpose: the three roles of a CTA run at the same time and share the SM's
 // 32 KB instruction cache (a fully unrolled version of this kernel was 100 KB of SASS and fetch-bound).
-template <int NSPLIT, bool FAST>
+// F16: operands split into two fp16 values instead of two bf16 values (22 instead of 16 significant bits at the same
+// cost; needs |x| < 65504 and O(1) data: used for the forward Linears of the MLPs, whose inputs are normalised)
+template <int NSPLIT, bool FAST, bool F16 = false>
 __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArgs a) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = umma::smem_u32(smem_raw);
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
         // =========================== MMA issue ====================================================
         if (lane == 0) load_w2_image(w_img, (const unsigned char*)a.wimg, (uint32_t)(n_wtiles * 2 * TILE_BYTES), wbar);   // global images always hold hi|lo
         umma::mbar_wait(wbar, 0);
-        const uint32_t idesc = umma::idesc_bf16(128, 128, a.a_trans, 0);
+        const uint32_t idesc = F16 ? umma::idesc_f16(128, 128, a.a_trans, 0) : umma::idesc_bf16(128, 128, a.a_trans, 0);
         // descriptors of k-step 0; a k-step only moves the start-address field (bytes >> 4)
         const uint64_t w_d = a.a_trans ? umma::desc_sw128(umma::smem_u32(w_img), 128 * 128, 1024) : umma::desc_sw128(umma::smem_u32(w_img), 16, 1024);
         const uint64_t b_d0 = umma::desc_sw128(umma::smem_u32(b_stage(0)), 16, 1024);
@@ -227,7 +236,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                         const uint64_t wd = w_d + (uint64_t)((uint32_t)a.tile_of[m][kc] * 2 * TB);
 #pragma unroll
                         for (int term = 0; term < (NSPLIT == 1 ? 1 : 3); ++term) {
-                            const uint64_t wa = wd + (term == 2 ? TB : 0), bb = bd + (term == 1 ? TB : 0);
+                            // bf16: hi*hi, hi*lo, lo*hi.  fp16: the small terms first (lo*hi, hi*lo, hi*hi), so that the
+                            // tensor core's truncating fp32 accumulation only rounds the eight big steps at full magnitude
+                            const bool w_lo = F16 ? term == 0 : term == 2, b_lo = term == 1;
+                            const uint64_t wa = wd + (w_lo ? TB : 0), bb = bd + (b_lo ? TB : 0);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 const uint32_t koff_k = (uint32_t)((k >> 2) * (128 * 128 >> 4) + (k & 3) * 2), koff_m = (uint32_t)(k * 128);
@@ -335,8 +347,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                         hl[r].x = umma::pack_bf16(h.x, h.y);
                         hl[r].y = umma::pack_bf16(h.z, h.w);
                     } else {
-                        split2_bf16(h.x, h.y, hl[r].x, hl[r].z);
-                        split2_bf16(h.z, h.w, hl[r].y, hl[r].w);
+                        if (F16) {
+                            // fp16 tops out at 65504: report values beyond half of that instead of producing infinities
+                            if (fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))) >= 32768.f && a.range_flag) *a.range_flag = 1;
+                            split2_f16(h.x, h.y, hl[r].x, hl[r].z);
+                            split2_f16(h.z, h.w, hl[r].y, hl[r].w);
+                        } else {
+                            split2_bf16(h.x, h.y, hl[r].x, hl[r].z);
+                            split2_bf16(h.z, h.w, hl[r].y, hl[r].w);
+                        }
                     }
                 }
                 umma::mbar_wait(&empty[s], ((sc / bstages) & 1) ^ 1);
@@ -368,6 +387,9 @@ int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s) {
     if (precision == 2) {
         MGB_CUDA(cudaFuncSetAttribute(linear_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINEAR_TC_SMEM));
         linear_tc_kernel<1, true><<<grid, LT_THREADS, LINEAR_TC_SMEM, s>>>(a);
+    } else if (precision == 3) {
+        MGB_CUDA(cudaFuncSetAttribute(linear_tc_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINEAR_TC_SMEM));
+        linear_tc_kernel<2, false, true><<<grid, LT_THREADS, LINEAR_TC_SMEM, s>>>(a);
     } else {
         MGB_CUDA(cudaFuncSetAttribute(linear_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LINEAR_TC_SMEM));
         linear_tc_kernel<2, false><<<grid, LT_THREADS, LINEAR_TC_SMEM, s>>>(a);

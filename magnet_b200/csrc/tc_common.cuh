@@ -43,6 +43,16 @@ __device__ __forceinline__ void split2_bf16(float a, float b, uint32_t& hi, uint
     lo = umma::pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
+// the same split into two fp16 values: 22 significant bits (|x - hi - lo| <= 2^-22 |x| while lo stays a normal number,
+// i.e. for |x| >~ 0.03; an absolute 3e-8 below that); |x| must stay below 65504
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 __device__ __forceinline__ void load_w2_image(unsigned char* w_img, const unsigned char* src, uint32_t bytes, uint64_t* wbar) {
     // one bulk async copy (TMA engine; no tensor map is needed for a pre-swizzled image)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(wbar)), "r"(bytes) : "memory");

@@ -12,6 +12,7 @@
 // Tiles must be 1024-byte aligned in the shared window.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace mgb {
@@ -183,6 +184,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// same with fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // shared-memory matrix descriptor, SWIZZLE_128B, descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

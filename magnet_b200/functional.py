@@ -137,7 +137,8 @@ class LinearActFn(torch.autograd.Function):
         res = _lib.f32c(residual).reshape(rows, fout) if residual is not None else None
         if packed is not None:      # tensor-core path (bf16 hi/lo split or bf16): weight images prepared by linear_act
             _lib.check(L.mgb_linear_tc_fwd(_lib.ptr(x2), rows, fin, fout, _lib.ptr(packed), _lib.ptr(bc), act, _lib.ptr(res),
-                                           _lib.ptr(y), _lib.ptr(y_pre), PRECISIONS[_precision], _lib.stream()), "linear_tc_fwd")
+                                           _lib.ptr(y), _lib.ptr(y_pre), 2 if _precision == "bf16" else _LINEAR_TC_PRECISION,
+                                           _lib.stream()), "linear_tc_fwd")
         else:
             wt = _empty((fin, fout), x2)
             _lib.check(L.mgb_transpose(_lib.ptr(Wc), fout, fin, _lib.ptr(wt), _lib.stream()), "transpose")
@@ -165,12 +166,14 @@ class LinearActFn(torch.autograd.Function):
         return (dx.reshape(ctx.shape) if dx is not None else None), dW, db, None, dres, None
 
 
-# The 128-wide Linears of MLP / Encoder / Decoder / projector (models/backbones/mlp.py) can run on the tensor cores too
-# (mgb_linear_tc_fwd, bf16 hi/lo split).  Each Linear is then within ~6e-6 of the reference, but MAgNet chains ~50 of
-# them and ends in an ill-conditioned 128 -> 1 projector, where that error is amplified to ~1e-4: outside the 1e-5
-# contract on predictions.  The exact fp32 path therefore stays the default; this switch is for throughput runs that
-# accept the looser bound (bench.py reports both and says which is which).
-_linear_tc = False
+# The 128-wide Linears of MLP / Encoder / Decoder / projector (models/backbones/mlp.py) run on the tensor cores
+# (mgb_linear_tc_fwd) with both operands split into two fp16 values (22 significant bits, small terms accumulated first):
+# measured 2.6e-7 per Linear against fp64 (the fp32 FFMA GEMM: 2.9e-7) and 3.9e-6 on MAgNet's ill-conditioned final
+# `hr_points` (FFMA: 3.0e-6) — inside the 1e-5 contract, 2.3x faster decode and rollout.  fp16 limits the inputs to
+# |x| < 32768 (raised as an error by the kernel) and is tuned for O(1) activations, which is what these MLPs see behind
+# their LayerNorms; set_linear_tc(False) restores the exact fp32 GEMM.  The backward pass of these Linears is fp32 FFMA.
+_linear_tc = True
+_LINEAR_TC_PRECISION = 3      # fp16 hi/lo split (include/magnet_b200.h); the per-edge kernels keep the bf16 split
 
 
 def set_linear_tc(on: bool) -> bool:
@@ -193,13 +196,14 @@ def _tc_weight_images(W: torch.Tensor):
         return None
     owner = W._base if W._base is not None else W
     cache = owner.__dict__.setdefault("_mgb_tc_images", {})
-    key = (W.storage_offset(), fout, fin, W.stride(0), owner.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    prec = 2 if _precision == "bf16" else _LINEAR_TC_PRECISION
+    key = (W.storage_offset(), fout, fin, W.stride(0), owner.data_ptr(), prec, torch.cuda.current_stream().cuda_stream)
     hit = cache.get(key)
     if hit is not None and hit[0] == owner._version:
         return hit[1]
     packed = torch.empty(n, dtype=torch.float32, device=W.device)
     Wd = W.detach()
-    _lib.check(L.mgb_linear_tc_pack(_lib.ptr(Wd), Wd.stride(0), fin, fout, _lib.ptr(packed), _lib.stream()), "linear_tc_pack")
+    _lib.check(L.mgb_linear_tc_pack(_lib.ptr(Wd), Wd.stride(0), fin, fout, prec, _lib.ptr(packed), _lib.stream()), "linear_tc_pack")
     cache[key] = (owner._version, packed)
     return packed
 

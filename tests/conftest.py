@@ -39,3 +39,13 @@ def golden():
     def load(name):
         return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
     return load
+
+
+def rows_off(a: torch.Tensor, b: torch.Tensor, tol: float) -> int:
+    """Number of rows of a whose error against b exceeds tol (relative to the scale of b).  Gradients of ReLU networks
+    are compared with this: a pre-activation within rounding distance of the kink flips the mask of ANY fp32 forward pass
+    (the reference's included), which changes a handful of gradient rows by O(1) and leaves all others within tol."""
+    a = a.detach().double().cpu().reshape(-1, a.shape[-1])
+    b = b.detach().double().cpu().reshape(-1, b.shape[-1])
+    scale = max(float(b.abs().max()), 1e-30)
+    return int(((a - b).abs().amax(1) > tol * scale).sum())

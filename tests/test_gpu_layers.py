@@ -55,7 +55,7 @@ def test_linear_act_fwd_bwd(rows, fin, fout, act):
 @pytest.mark.parametrize("rows,fin,fout,act", [(777, 128, 128, "relu"), (129, 128, 10, "none"), (2048, 128, 1, "none"),
                                                (1000, 256, 128, "swish"), (300, 128, 256, "none")])
 def test_linear_act_tensor_core_path(rows, fin, fout, act):
-    """Opt-in tcgen05 Linear (bf16 hi/lo split): same call, same results within the 1e-5 contract of a single Linear."""
+    """tcgen05 Linear (fp16 hi/lo split, the default for 128/256-wide inputs): same call, fp32-grade results."""
     g = S._gen(rows + 1)
     x = torch.randn(rows, fin, generator=g).to(DEV)
     W = (torch.randn(fout, fin, generator=g) / fin ** 0.5).to(DEV)
@@ -71,7 +71,31 @@ def test_linear_act_tensor_core_path(rows, fin, fout, act):
         MF.set_linear_tc(old)
     z = torch.nn.functional.linear(x.double().cpu(), W.double().cpu(), b.double().cpu())
     z = {"swish": lambda v: v * torch.sigmoid(v), "relu": torch.relu, "none": lambda v: v}[act](z) + res.double().cpu()
-    assert rel_err(y, z) < TOL and torch.equal(y, y2)
+    assert rel_err(y, z) < 1e-6 and torch.equal(y, y2)
+
+
+def test_linear_act_tensor_core_range_guard():
+    """fp16 tops out at 65504: an input beyond 32768 is reported by the next call instead of turning into infinities quietly."""
+    x = torch.full((256, 128), 1.0, device=DEV)
+    x[3, 5] = 1e5
+    W = torch.eye(128, device=DEV)
+    b = torch.zeros(128, device=DEV)
+    old = MF.set_linear_tc(True)
+    try:
+        with torch.no_grad():
+            MF.linear_act(x, W, b, "none")
+            torch.cuda.synchronize()
+            with pytest.raises(RuntimeError, match="fp16 range"):
+                MF.linear_act(torch.ones(256, 128, device=DEV), W, b, "none")
+            y = MF.linear_act(torch.ones(256, 128, device=DEV), W, b, "none")       # the flag is cleared by the report
+            assert torch.equal(y, torch.ones(256, 128, device=DEV))
+    finally:
+        MF.set_linear_tc(old)
+    with torch.no_grad():
+        MF.set_linear_tc(False)
+        y = MF.linear_act(x, W, b, "none")                                           # the fp32 GEMM takes any magnitude
+        MF.set_linear_tc(old)
+    assert float(y[3, 5]) == 1e5
 
 
 def test_layernorm_fwd_bwd():
