@@ -120,33 +120,40 @@ class GNNLayerFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # row-wise Linear (+activation, +residual) and LayerNorm
 # --------------------------------------------------------------------------------------------
+def _linear_forward(x, W, b, act: int, residual, packed, want_pre: bool):
+    """The forward kernels of LinearActFn; also called directly (no autograd node) when nothing requires a gradient."""
+    _lib.require_cuda(x, W)
+    L = _lib.lib()
+    shape = x.shape
+    x2 = _lib.f32c(x).reshape(-1, shape[-1])
+    bc = _lib.f32c(b.detach())
+    rows, fin = x2.shape
+    fout = W.shape[0]
+    y = _empty((rows, fout), x2)
+    y_pre = _empty((rows, fout), x2) if (act != 0 and want_pre) else None    # inference skips the copy
+    res = _lib.f32c(residual).reshape(rows, fout) if residual is not None else None
+    if packed is not None:      # tensor-core path (fp16 hi/lo split, or bf16 in the bf16 mode): weight images from linear_act
+        _lib.check(L.mgb_linear_tc_fwd(_lib.ptr(x2), rows, fin, fout, _lib.ptr(packed), _lib.ptr(bc), act, _lib.ptr(res),
+                                       _lib.ptr(y), _lib.ptr(y_pre), 2 if _precision == "bf16" else _LINEAR_TC_PRECISION,
+                                       _lib.stream()), "linear_tc_fwd")
+    else:
+        Wc = _lib.f32c(W.detach())
+        wt = _empty((fin, fout), x2)
+        _lib.check(L.mgb_transpose(_lib.ptr(Wc), fout, fin, _lib.ptr(wt), _lib.stream()), "transpose")
+        _lib.check(L.mgb_linear_fwd(_lib.ptr(x2), rows, fin, fout, _lib.ptr(wt), _lib.ptr(bc), act, _lib.ptr(res),
+                                    _lib.ptr(y), _lib.ptr(y_pre), _lib.stream()), "linear_fwd")
+    return y.reshape(*shape[:-1], fout), x2, y_pre
+
+
 class LinearActFn(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual) — nn.Linear followed by Swish/ReLU (models/backbones/mlp.py:24-27)."""
 
     @staticmethod
     def forward(ctx, x, W, b, act: int, residual: Optional[torch.Tensor], packed=None):
-        _lib.require_cuda(x, W)
-        L = _lib.lib()
-        shape = x.shape
-        x2 = _lib.f32c(x).reshape(-1, shape[-1])
-        Wc, bc = _lib.f32c(W.detach()), _lib.f32c(b.detach())
-        rows, fin = x2.shape
-        fout = Wc.shape[0]
-        y = _empty((rows, fout), x2)
-        y_pre = _empty((rows, fout), x2) if (act != 0 and any(ctx.needs_input_grad)) else None    # inference skips the copy
-        res = _lib.f32c(residual).reshape(rows, fout) if residual is not None else None
-        if packed is not None:      # tensor-core path (bf16 hi/lo split or bf16): weight images prepared by linear_act
-            _lib.check(L.mgb_linear_tc_fwd(_lib.ptr(x2), rows, fin, fout, _lib.ptr(packed), _lib.ptr(bc), act, _lib.ptr(res),
-                                           _lib.ptr(y), _lib.ptr(y_pre), 2 if _precision == "bf16" else _LINEAR_TC_PRECISION,
-                                           _lib.stream()), "linear_tc_fwd")
-        else:
-            wt = _empty((fin, fout), x2)
-            _lib.check(L.mgb_transpose(_lib.ptr(Wc), fout, fin, _lib.ptr(wt), _lib.stream()), "transpose")
-            _lib.check(L.mgb_linear_fwd(_lib.ptr(x2), rows, fin, fout, _lib.ptr(wt), _lib.ptr(bc), act, _lib.ptr(res),
-                                        _lib.ptr(y), _lib.ptr(y_pre), _lib.stream()), "linear_fwd")
-        ctx.save_for_backward(x2, Wc, y_pre)
-        ctx.act, ctx.shape, ctx.has_res = act, shape, residual is not None
-        return y.reshape(*shape[:-1], fout)
+        y, x2, y_pre = _linear_forward(x, W, b, act, residual, packed, any(ctx.needs_input_grad))
+        ctx.save_for_backward(x2, _lib.f32c(W.detach()), y_pre)
+        ctx.act, ctx.shape, ctx.has_res = act, x.shape, residual is not None
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -209,7 +216,25 @@ def _tc_weight_images(W: torch.Tensor):
 
 
 def linear_act(x, W, b, act: str = "none", residual=None):
-    return LinearActFn.apply(x, W, b, ACT[act], residual, _tc_weight_images(W))
+    packed = _tc_weight_images(W)
+    if not torch.is_grad_enabled() or not (x.requires_grad or W.requires_grad or b.requires_grad or
+                                           (residual is not None and residual.requires_grad)):
+        return _linear_forward(x, W, b, ACT[act], residual, packed, False)[0]      # rollout / decode: no autograd node
+    return LinearActFn.apply(x, W, b, ACT[act], residual, packed)
+
+
+def _layernorm_forward(x, gamma, beta):
+    _lib.require_cuda(x, gamma)
+    L = _lib.lib()
+    shape = x.shape
+    x2 = _lib.f32c(x).reshape(-1, shape[-1])
+    g, b = _lib.f32c(gamma.detach()), _lib.f32c(beta.detach())
+    rows, cols = x2.shape
+    y = _empty((rows, cols), x2)
+    stats = _empty((max(rows, 1), 2), x2)
+    _lib.check(L.mgb_layernorm_fwd(_lib.ptr(x2), _lib.ptr(g), _lib.ptr(b), rows, cols, _lib.ptr(y), _lib.ptr(stats),
+                                   _lib.stream()), "layernorm_fwd")
+    return y.reshape(shape), x2, g, stats
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -217,19 +242,10 @@ class LayerNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta):
-        _lib.require_cuda(x, gamma)
-        L = _lib.lib()
-        shape = x.shape
-        x2 = _lib.f32c(x).reshape(-1, shape[-1])
-        g, b = _lib.f32c(gamma.detach()), _lib.f32c(beta.detach())
-        rows, cols = x2.shape
-        y = _empty((rows, cols), x2)
-        stats = _empty((max(rows, 1), 2), x2)
-        _lib.check(L.mgb_layernorm_fwd(_lib.ptr(x2), _lib.ptr(g), _lib.ptr(b), rows, cols, _lib.ptr(y), _lib.ptr(stats),
-                                       _lib.stream()), "layernorm_fwd")
+        y, x2, g, stats = _layernorm_forward(x, gamma, beta)
         ctx.save_for_backward(x2, g, stats)
-        ctx.shape = shape
-        return y.reshape(shape)
+        ctx.shape = x.shape
+        return y
 
     @staticmethod
     def backward(ctx, dy):
@@ -247,7 +263,13 @@ class LayerNormFn(torch.autograd.Function):
         return dx.reshape(ctx.shape), dg, db
 
 
+def _no_grad_needed(*tensors) -> bool:
+    return not torch.is_grad_enabled() or not any(t is not None and t.requires_grad for t in tensors)
+
+
 def layer_norm(x, gamma, beta):
+    if _no_grad_needed(x, gamma, beta):
+        return _layernorm_forward(x, gamma, beta)[0]         # rollout / decode: no autograd node
     return LayerNormFn.apply(x, gamma, beta)
 
 
@@ -281,7 +303,7 @@ class EdgeCombineFn(torch.autograd.Function):
     applied to cat([x_i, x_j, e_features]) (models/magnet_gnn.py:79-82)."""
 
     @staticmethod
-    def forward(ctx, p, q, r, edge_index, plan: AggregationPlan, act: int):
+    def run(p, q, r, edge_index, act: int):
         _lib.require_cuda(p, q, r, edge_index)
         L = _lib.lib()
         p, q, r = _lib.f32c(p), _lib.f32c(q), _lib.f32c(r)
@@ -290,6 +312,11 @@ class EdgeCombineFn(torch.autograd.Function):
         out = _empty((E, 128), p)
         _lib.check(L.mgb_edge_combine_fwd(_lib.ptr(p), _lib.ptr(q), _lib.ptr(r), _lib.ptr(ei), E, act, _lib.ptr(out),
                                           _lib.stream()), "edge_combine_fwd")
+        return out
+
+    @staticmethod
+    def forward(ctx, p, q, r, edge_index, plan: AggregationPlan, act: int):
+        out = EdgeCombineFn.run(p, q, r, edge_index, act)
         ctx.save_for_backward(out)
         ctx.plan, ctx.act, ctx.n = plan, act, p.shape[0]
         return out
@@ -312,6 +339,8 @@ class EdgeCombineFn(torch.autograd.Function):
 
 
 def edge_combine(p, q, r, edge_index, plan, act: str = "none"):
+    if _no_grad_needed(p, q, r):
+        return EdgeCombineFn.run(p, q, r, edge_index, ACT[act])
     return EdgeCombineFn.apply(p, q, r, edge_index, plan, ACT[act])
 
 
@@ -341,6 +370,8 @@ class ScatterMeanFn(torch.autograd.Function):
 
 
 def scatter_mean(m, edge_index, plan):
+    if _no_grad_needed(m):
+        return _segment_sum(_lib.f32c(m), 128, plan.rowptr, plan.perm, plan.n_nodes, True)
     return ScatterMeanFn.apply(m, edge_index, plan)
 
 
