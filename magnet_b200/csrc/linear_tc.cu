@@ -134,7 +134,12 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                 const float bias = (a.bias && col_ok) ? a.bias[col] : 0.f;
                 float wt[LT_TAIL];
 #pragma unroll
-                for (int t = 0; t < LT_TAIL; ++t) wt[t] = (t < a.kt && col_ok) ? a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st] : 0.f;
+                for (int t = 0; t < LT_TAIL; ++t) wt[t] = 0.f;
+                if (a.kt > 0 && col_ok) {
+#pragma unroll
+                    for (int t = 0; t < LT_TAIL; ++t)
+                        if (t < a.kt) wt[t] = a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st];
+                }
                 const bool last_m = m == a.nm - 1;
                 // residual values two chunks ahead of the chunk being processed (4-byte loads, one coalesced 128-byte
                 // line per warp and row: their latency must not sit between two chunks)
@@ -142,19 +147,25 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                 const int rlim = nr - hf * 64;
                 float rn1[8], rn2[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    rn1[i] = (rp && i < rlim) ? rp[(int64_t)i * a.ldr] : 0.f;
-                    rn2[i] = (rp && 8 + i < rlim) ? rp[(int64_t)(8 + i) * a.ldr] : 0.f;
+                for (int i = 0; i < 8; ++i) { rn1[i] = 0.f; rn2[i] = 0.f; }
+                if (rp) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        rn1[i] = i < rlim ? rp[(int64_t)i * a.ldr] : 0.f;
+                        rn2[i] = 8 + i < rlim ? rp[(int64_t)(8 + i) * a.ldr] : 0.f;
+                    }
                 }
 #pragma unroll 1
                 for (int cb = 0; cb < 64; cb += 8) {
                     const int c0 = hf * 64 + cb;
                     float v[8], res[8];
+                    if (rp) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { res[i] = rn1[i]; rn1[i] = rn2[i]; }
-                    if (rp && cb + 16 < 64) {
+                        for (int i = 0; i < 8; ++i) { res[i] = rn1[i]; rn1[i] = rn2[i]; }
+                        if (cb + 16 < 64) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) rn2[i] = cb + 16 + i < rlim ? rp[(int64_t)(cb + 16 + i) * a.ldr] : 0.f;
+                            for (int i = 0; i < 8; ++i) rn2[i] = cb + 16 + i < rlim ? rp[(int64_t)(cb + 16 + i) * a.ldr] : 0.f;
+                        }
                     }
                     umma::tmem_ld8(tmem + (uint32_t)((acc * 2 + m) * 128) + lane_base + c0, v);
                     if (last_m && cb + 8 >= 64 && a.kt == 0) {
@@ -194,8 +205,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
+                    if (rp) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] += res[i];
+                        for (int i = 0; i < 8; ++i) v[i] += res[i];
+                    }
                     float* yo = a.y + row0 * a.ldy + col;
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
