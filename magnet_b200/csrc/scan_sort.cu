@@ -299,17 +299,32 @@ int radix_sort_pairs(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t*
 __global__ void segment_starts_kernel(const uint32_t* __restrict__ keys, int64_t n, int32_t* __restrict__ starts,
                                       int64_t n_keys) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n) return;
-    // position i closes the key range (prev, cur]: every key c in it starts at i
-    int64_t prev = (i == 0) ? -1 : (int64_t)keys[i - 1];
-    int64_t cur = (i == n) ? n_keys : (int64_t)keys[i];
+    if (i == 0 || i >= n) return;
+    // position i closes the key range (prev, cur]: every key c in it starts at i (gaps between two present keys are short)
+    const int64_t prev = (int64_t)keys[i - 1];
+    int64_t cur = (int64_t)keys[i];
     if (cur > n_keys) cur = n_keys;
     for (int64_t c = prev + 1; c <= cur; ++c) starts[c] = (int32_t)i;
 }
 
+// the two open ends — keys up to the first present key start at 0, keys past the last present key start at n — can
+// span most of a sparse key space (a kNN grid with millions of cells): one thread per key instead of one thread's loop
+__global__ void segment_ends_kernel(const uint32_t* __restrict__ keys, int64_t n, int32_t* __restrict__ starts, int64_t n_keys) {
+    const int64_t first = n > 0 ? (int64_t)keys[0] : n_keys;
+    const int64_t last = n > 0 ? (int64_t)keys[n - 1] : -1;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c <= n_keys; c += (int64_t)gridDim.x * blockDim.x) {
+        if (c <= first) starts[c] = 0;
+        else if (c > last) starts[c] = (int32_t)n;
+    }
+}
+
 int segment_starts(const uint32_t* sorted_keys, int64_t n, int32_t* starts, int64_t n_keys, cudaStream_t s) {
-    int64_t threads = n + 1;
-    segment_starts_kernel<<<(unsigned)ceil_div<int64_t>(threads, 256), 256, 0, s>>>(sorted_keys, n, starts, n_keys);
+    if (n > 1) {
+        segment_starts_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, s>>>(sorted_keys, n, starts, n_keys);
+        MGB_LAUNCH_CHECK();
+    }
+    const int64_t blocks = ceil_div<int64_t>(n_keys + 1, 256);
+    segment_ends_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, s>>>(sorted_keys, n, starts, n_keys);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }
