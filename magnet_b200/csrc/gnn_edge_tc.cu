@@ -1059,13 +1059,31 @@ size_t edge_bwd_tc_workspace(int64_t n_edges) {
            align_up((size_t)grid * 2 * TCH * sizeof(float)) + 1024;
 }
 
+// out[i] (+)= sum over the CTA partials.  Block = 32 outputs x 8 groups; group g sums the partials p = g, g+8, ... with four
+// independent loads in flight, then a fixed-order shared-memory reduction over the groups (deterministic).
 __global__ void __launch_bounds__(256)
 sum_partials_tc_kernel(const float* __restrict__ partial, int n_parts, int64_t count, float* __restrict__ out, int accumulate) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int p = 0; p < n_parts; ++p) s += partial[(int64_t)p * count + i];
-    out[i] = accumulate ? out[i] + s : s;
+    if (i < count) {
+        int p = g;
+        for (; p + 24 < n_parts; p += 32) {
+            const float v0 = partial[(int64_t)p * count + i], v1 = partial[(int64_t)(p + 8) * count + i];
+            const float v2 = partial[(int64_t)(p + 16) * count + i], v3 = partial[(int64_t)(p + 24) * count + i];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; p < n_parts; p += 8) s += partial[(int64_t)p * count + i];
+    }
+    red[g][lane] = s;
+    __syncthreads();
+    if (g == 0 && i < count) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += red[q][lane];
+        out[i] = accumulate ? out[i] + t : t;
+    }
 }
 
 int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv,
@@ -1099,9 +1117,9 @@ int launch_edge_bwd_tc(int precision, const float* pq, const int32_t* rowptr, co
         segment_fixup_tc_kernel<<<(unsigned)ceil_div<int64_t>(subtiles - 1, 8), 256, 0, s>>>(rowptr, dstv, n_edges, BW_FLUSH_TE, part_head, part_tail, dpq, 2 * TCH, 0);
         MGB_LAUNCH_CHECK();
     }
-    sum_partials_tc_kernel<<<ceil_div(TCH * TCH, 256), 256, 0, s>>>(dw2_part, grid, (int64_t)TCH * TCH, dW2, accumulate);
+    sum_partials_tc_kernel<<<TCH * TCH / 32, 256, 0, s>>>(dw2_part, grid, (int64_t)TCH * TCH, dW2, accumulate);
     MGB_LAUNCH_CHECK();
-    sum_partials_tc_kernel<<<1, 256, 0, s>>>(db2_part, 2 * grid, TCH, db2, accumulate);
+    sum_partials_tc_kernel<<<TCH / 32, 256, 0, s>>>(db2_part, 2 * grid, TCH, db2, accumulate);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }
