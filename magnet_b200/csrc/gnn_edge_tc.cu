@@ -251,6 +251,10 @@ __global__ void __launch_bounds__(FW_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
                 // segmented mean over the destination-sorted positions: one pass per stored sum (segment end or
                 // sub-tile end); positions past the end of the edge list carry Swish(bias) but belong to no segment
                 uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 31)) & 0xffu, todo = 0xffu;
+                if (fm == 0) {                   // the common case: no sum ends inside the chunk
+                    sum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                    continue;
+                }
                 while (fm) {
                     const uint32_t low = fm & (0u - fm);
                     const uint32_t upto = (low << 1) - 1u;
@@ -707,6 +711,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 for (int i = 0; i < 8; ++i) v[i] = swish_grad_tc<FAST>(v[i] + bias);
                 // dagg[dst]/deg is constant along a segment: one pass per segment that intersects the chunk (usually one)
                 uint32_t em = (emw >> cb) & 0xffu, todo = 0xffu;
+                if (em == 0) {                   // the common case: one segment covers the chunk
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] *= g;
+                } else
                 while (true) {
                     const uint32_t upto = em ? (((em & (0u - em)) << 1) - 1u) : 0xffu;
                     const uint32_t rng = todo & upto;
@@ -825,6 +833,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 // Positions past the end of the edge list carry D2 = 0 and belong to no segment: they store zeros
                 // into the padding of dz1 and add nothing to any sum.
                 uint32_t em = (emw >> cb) & 0xffu, todo = 0xffu;
+                if (em == 0) {                   // the common case: one segment covers the chunk
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] += pk;
+                } else
                 while (true) {
                     const uint32_t upto = em ? (((em & (0u - em)) << 1) - 1u) : 0xffu;
                     const uint32_t rng = todo & upto;
@@ -845,6 +857,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                 // segmented sum over the destination-sorted positions: one pass per stored sum (segment end or sub-tile end)
                 uint32_t fm = (fmw >> cb) & 0xffu;
                 todo = 0xffu;
+                if (fm == 0) {                   // the common case: no sum ends inside the chunk
+                    sum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                    continue;
+                }
                 while (fm) {
                     const uint32_t low = fm & (0u - fm);
                     const uint32_t upto = (low << 1) - 1u;
