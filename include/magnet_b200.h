@@ -141,6 +141,14 @@ size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features)
 int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features,
                    int out_features, const float* w, float* dx, float* dw, float* db, int accumulate_params,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * Flat-buffer Adam: torch.optim.Adam(lr, weight_decay) as configured by models/magnet_gnn.py:378-386 and
+ * models/mpnn_2d.py:205-213, one launch for all parameters of a model (param / grad / moments are flat fp32 buffers of
+ * n elements, 16-byte aligned).  step >= 1 counts this update; grad_scale multiplies the gradient first (1/world
+ * after a sum all-reduce); the StepLR schedule is the caller's `lr`.
+ * ------------------------------------------------------------------------------------------- */
+int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
 int mgb_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int cols, float* y,
                       float* stats /* [rows,2] mean,rstd */, void* stream);
 size_t mgb_layernorm_bwd_workspace(int64_t rows, int cols);

@@ -178,6 +178,11 @@ int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_fea
     return launch_linear_tc(precision, a, STREAM(stream));
 }
 
+int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
+                  double eps, double weight_decay, int64_t step, double grad_scale, void* stream) {
+    return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, STREAM(stream));
+}
+
 size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features) {
     return wgrad_workspace_bytes((int)rows, out_features, in_features) + 1024;
 }

@@ -141,6 +141,9 @@ int launch_tail_dgrad(const float* dy, int lddy, int ny, const float* pre, int l
 #ifdef MGB_TIMELINE
 int set_timeline_buffer(long long* p);
 #endif
+// optim.cu
+int adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+              double weight_decay, int64_t step, double grad_scale, cudaStream_t s);
 // umma_selftest.cu
 int umma_selftest(const float* a, const float* b, int a_mn, int b_mn, int lbo_mn, int sbo_mn, float* d, cudaStream_t s);
 

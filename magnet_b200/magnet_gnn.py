@@ -138,6 +138,10 @@ class MAgNetGNN(LightningModule):
         self.save_hyperparameters()
         self.lr = hparams.lr
         self.weight_decay = hparams.weight_decay
+        try:                                                   # not a reference hyper-parameter (see optim.py): absent in its configs
+            self.flat_adam = bool(hparams.flat_adam)
+        except (AttributeError, KeyError):
+            self.flat_adam = False
         self.factor = hparams.factor
         self.step_size = hparams.step_size
         self.loss = hparams.loss
@@ -249,7 +253,11 @@ class MAgNetGNN(LightningModule):
         return cat
 
     def configure_optimizers(self):
-        optimizer = torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
+        if getattr(self, "flat_adam", False):     # opt-in (hparams.flat_adam): same update, one launch, flat gradient buffer
+            from .optim import FlatAdam
+            optimizer = FlatAdam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
+        else:
+            optimizer = torch.optim.Adam(self.parameters(), lr=self.lr, weight_decay=self.weight_decay)
         scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=self.step_size, gamma=self.factor)
         return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler}}
 

@@ -1,0 +1,83 @@
+"""Flat-buffer Adam for the drop-in models.
+
+The reference trains with ``torch.optim.Adam(self.parameters(), lr, weight_decay)`` under ``StepLR``
+(models/magnet_gnn.py:378-386, models/mpnn_2d.py:205-213): ~150 parameter tensors, each with its own chain of
+element-wise launches per step.  ``FlatAdam`` keeps parameters, gradients and both moments in four flat fp32 buffers
+(the parameters / ``.grad`` of the model become views into them) and updates everything with ONE CUDA launch
+(``mgb_adam_step``); the flat gradient buffer is also what the training all-reduce sends (``allreduce_flat_gradient``), so
+no per-step concatenation or copy-back is needed.  It is a ``torch.optim.Optimizer``: ``torch.optim.lr_scheduler.StepLR``
+drives its ``lr`` exactly as it drives torch's Adam.
+"""
+from typing import Iterable
+
+import torch
+
+from . import _lib
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0):
+        params = [p for p in params if p.requires_grad]
+        if not params:
+            raise ValueError("FlatAdam got no trainable parameters")
+        dev = params[0].device
+        if dev.type != "cuda" or any(p.device != dev or p.dtype != torch.float32 for p in params):
+            raise RuntimeError("FlatAdam needs fp32 CUDA parameters on one device (magnet_b200 has no CPU fallback)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        # every tensor starts on a 16-byte boundary of the flat buffers (float4 accesses in the kernel and in the layers)
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros_like(self.flat_param)
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self._params, self._offs = params, offs
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.flat_param[o:o + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view                                   # the module's Parameter objects stay, their storage moves
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        self.steps = 0
+
+    @torch.no_grad()
+    def zero_grad(self, set_to_none: bool = False):           # the views must survive: always zero in place
+        self.flat_grad.zero_()
+        for p, o in zip(self._params, self._offs):
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+
+    @torch.no_grad()
+    def step(self, closure=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        g = self.param_groups[0]
+        for p, o in zip(self._params, self._offs):             # a gradient that autograd re-created (p.grad was None) is copied in
+            if p.grad is not None and p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                self.flat_grad[o:o + p.numel()].view_as(p).copy_(p.grad)
+                p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        self.steps += 1
+        with torch.cuda.device(self.flat_param.device):
+            _lib.check(_lib.lib().mgb_adam_step(_lib.ptr(self.flat_param), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg),
+                                                _lib.ptr(self.exp_avg_sq), self.flat_param.numel(), float(g["lr"]),
+                                                float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                                float(g["weight_decay"]), self.steps, float(grad_scale), _lib.stream()),
+                       "adam_step")
+        for p in self._params:                                  # the kernel wrote through raw pointers: tell the caches
+            torch._C._increment_version(p)                      # (packed weight copies are keyed on the version counter)
+        return loss
+
+
+def allreduce_flat_gradient(opt: FlatAdam, world: int = None) -> float:
+    """Sum the flat gradient buffer across ranks (one collective, no copies); returns the ``grad_scale`` to pass to
+    ``opt.step`` so that the update uses the mean over ranks."""
+    import torch.distributed as dist
+    world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+    if world > 1:
+        dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM)
+    return 1.0 / world

@@ -255,3 +255,54 @@ def test_mpnn_1d_golden(golden):
     with torch.no_grad():
         y = m.forward(graph, x[0, -1], b["t"][0, -1], b["t"][0][1] - b["t"][0][0])
     assert rel_err(y, c["y"]) < TOL
+
+
+@pytest.mark.parametrize("weight_decay", [0.0, 1e-2])
+def test_flat_adam_matches_torch_adam(weight_decay):
+    """FlatAdam (one launch over flat buffers) against torch.optim.Adam + StepLR as the reference configures them
+    (models/mpnn_2d.py:205-213), fed identical gradients: the update rule itself."""
+    from magnet_b200.optim import FlatAdam
+    g = S._gen(5)
+    shapes = [(128, 269), (128,), (7, 3), (1,), (128, 128), (5,)]
+    pa = [torch.nn.Parameter(torch.randn(sh, generator=g).to(DEV)) for sh in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.Adam(pa, lr=1e-3, weight_decay=weight_decay)
+    ob = FlatAdam(pb, lr=1e-3, weight_decay=weight_decay)
+    sa, sb = (torch.optim.lr_scheduler.StepLR(o, step_size=2, gamma=0.3) for o in (oa, ob))
+    for step in range(6):
+        grads = [torch.randn(sh, generator=g).to(DEV) * 10.0 ** (step - 3) for sh in shapes]
+        ob.zero_grad()
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad = gr.clone()
+            q.grad += gr                                  # accumulates into the flat buffer, as autograd does
+        oa.step(), ob.step()
+        sa.step(), sb.step()
+    for p, q in zip(pa, pb):
+        assert rel_err(q, p) < 1e-6
+        assert ob.flat_param.data_ptr() <= q.data_ptr() < ob.flat_param.data_ptr() + 4 * ob.flat_param.numel()
+
+
+def test_flat_adam_updates_reach_the_kernels():
+    """The step writes through raw pointers: the version counters must move so that the cached packed weights follow."""
+    from magnet_b200.optim import FlatAdam
+    g = S._gen(6)
+    B, N = 2, 300
+    pos = torch.rand(B * N, 2, generator=g).to(DEV)
+    batch = torch.arange(B).repeat_interleave(N).to(DEV)
+    ei = MG.radius_graph(pos, 0.12, batch, loop=False)
+    layer = GNN_Layer(128, 128, 128, 10, 1).to(DEV)
+    layer.load_state_dict(S.seeded_state_dict(_layer_shapes(10, 2), 11))
+    x = torch.randn(B * N, 128, generator=g).to(DEV)
+    u = torch.randn(B * N, 10, generator=g).to(DEV)
+    var = torch.rand(B * N, 1, generator=g).to(DEV)
+    opt = FlatAdam(layer.parameters(), lr=1e-2)
+    y0 = layer(x, u, pos, var, ei, batch)
+    opt.zero_grad()
+    (y0 * torch.randn(y0.shape, generator=g).to(DEV)).sum().backward()
+    opt.step()
+    with torch.no_grad():
+        y1 = layer(x, u, pos, var, ei, batch)
+        fresh = GNN_Layer(128, 128, 128, 10, 1).to(DEV)
+        fresh.load_state_dict(layer.state_dict())
+        y2 = fresh(x, u, pos, var, ei, batch)
+    assert not torch.equal(y0, y1) and torch.equal(y1, y2)
