@@ -48,17 +48,20 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The nvidia-smi process is started before the
+    warm-up (its start-up takes longer than a short timed region, more so on an 8-GPU box); samples are time-stamped on
+    arrival and only those between mark_start() and mark_end() are summarised."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0, self.t1 = None, None
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -68,7 +71,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_ready(self, timeout: float = 8.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up can outlast the warm-up)."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.02)
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
         if self.proc:
@@ -79,10 +94,12 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.06]
+        rows = inside
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -316,20 +333,23 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step(d["x"], d["u"], d["pos"], d["var"], d["gy"])
-    barrier()
-    # ---- device-resident timing -------------------------------------------------------------
-    L.mgb_profile_enable(1)
-    launches0 = L.mgb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        for _ in range(max(args.warmup, 3)):
+            step(d["x"], d["u"], d["pos"], d["var"], d["gy"])
         barrier()
+        # ---- device-resident timing -------------------------------------------------------------
+        L.mgb_profile_enable(1)
+        launches0 = L.mgb_launch_count()
+        clocks.wait_ready()
+        barrier()
+        clocks.mark_start()
         ev0.record()
         for _ in range(args.steps):
             step(d["x"], d["u"], d["pos"], d["var"], d["gy"])
         ev1.record()
         barrier()
+        clocks.mark_end()
     launches = (L.mgb_launch_count() - launches0) // max(args.steps, 1)
     L.mgb_profile_enable(0)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
