@@ -50,6 +50,32 @@ def test_cpu_tensors_fail_loudly():
         MG.radius_graph(torch.rand(10, 2), 0.1)
 
 
+def test_new_entry_points_reject_bad_arguments_without_gpu():
+    L = _lib.lib()
+    # tensor-core Linear: only 128/256 inputs and <= 256 outputs, at most two weight tiles
+    assert L.mgb_linear_tc_packed_floats(128, 128) == 128 * 128 and L.mgb_linear_tc_packed_floats(128, 1) == 128 * 128
+    assert L.mgb_linear_tc_packed_floats(256, 128) == 2 * 128 * 128 and L.mgb_linear_tc_packed_floats(128, 256) == 2 * 128 * 128
+    assert L.mgb_linear_tc_packed_floats(13, 128) == 0 and L.mgb_linear_tc_packed_floats(256, 256) == 0
+    rc = L.mgb_linear_tc_fwd(None, 10, 13, 128, None, None, 0, None, None, None, 3, None)
+    assert rc == -1 and "unsupported shape" in _lib.last_error()
+    rc = L.mgb_linear_tc_fwd(None, 10, 128, 128, None, None, 0, None, None, None, 7, None)
+    assert rc == -1 and "precision" in _lib.last_error()
+    # flat Adam: the step counter starts at 1
+    rc = L.mgb_adam_step(None, None, None, None, 16, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None)
+    assert rc == -1 and "step >= 1" in _lib.last_error()
+
+
+def test_flat_adam_and_linear_paths_have_no_cpu_fallback():
+    from magnet_b200 import functional as MF
+    from magnet_b200.optim import FlatAdam
+    with pytest.raises(RuntimeError, match="CUDA"):
+        FlatAdam([torch.nn.Parameter(torch.zeros(4))])
+    with pytest.raises(RuntimeError):
+        MF.linear_act(torch.zeros(4, 128), torch.zeros(128, 128), torch.zeros(128))
+    assert MF.set_linear_tc(False) in (True, False)
+    MF.set_linear_tc(True)
+
+
 def test_synthetic_is_deterministic_and_shaped_like_the_reference_batches():
     a = S.graph_batch(B=3, N=64, nt=20, seed=4)
     b = S.graph_batch(B=3, N=64, nt=20, seed=4)
