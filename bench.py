@@ -360,14 +360,16 @@ def run_ours(args, rank, world, local_rank):
         prof[name] = (t.value, c.value)
     # ---- end to end: pinned host inputs -> H2D -> 5 layers fwd+bwd -> D2H of the result checksum ----
     # Every step copies its own inputs from pinned host memory and reads its result back.  The copy of step k+1 is
-    # issued on a side stream before step k computes (double buffering), so the PCIe transfer overlaps the kernels;
-    # the first copy and every device->host read stay exposed.
+    # issued on a side stream before step k computes (double buffering), so the PCIe transfer overlaps the kernels; the
+    # result of every step is copied to pinned host memory inside the timed region (asynchronously: the host does not
+    # stall the pipeline on it; the closing barrier + synchronize waits for all of them).
     e2e_steps = max(1, args.steps)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
 
     dbuf = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
+    results = torch.zeros(e2e_steps, dtype=torch.float32).pin_memory()       # one value per step, read back asynchronously
     used = [None, None]          # event: the step that read buffer j has been enqueued and finished
 
     def upload(j):
@@ -394,9 +396,11 @@ def run_ours(args, rank, world, local_rank):
         out = step(dx["x"], dx["u"], dx["pos"], dx["var"], dx["gy"])
         used[j] = torch.cuda.Event()
         used[j].record(main_stream)
-        checksum = out.sum().item()                      # device -> host read of the step's result
+        results[i:i + 1].copy_(out.sum().reshape(1), non_blocking=True)      # device -> host read of the step's result
     ee1.record()
-    barrier()
+    barrier()                                            # every copy has landed before the clock is read
+    checksum = float(results.sum())
+    assert checksum == checksum, "e2e produced NaN"
     e2e_ms = torch.tensor([ee0.elapsed_time(ee1)], device=dev)
     edges = torch.tensor([float(E)], device=dev)
     extras = None
