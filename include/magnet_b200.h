@@ -136,6 +136,16 @@ int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_feature
 int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* packed,
                       const float* bias, int act, const float* residual, float* y, float* y_pre, int precision,
                       void* stream);
+/* A whole MLP of models/backbones/mlp.py:9-28 behind its first Linear — n_layers Linear(128, 128) + act, the last one
+ * Linear(128, n_out <= 128) without activation — in one launch, forward only (inference / rollout): activations stay in
+ * shared memory between the layers, arithmetic as mgb_linear_tc_fwd with precision 3.  x [rows, >=128] fp32 (row stride
+ * ldx, optional ReLU applied on load: in_act = 1), y [rows, n_out] (row stride ldy).  packed: filled layer by layer with
+ * mgb_mlp_chain_pack_layer (W_l [out, 128] row stride ldw, bias_l [out] or NULL). */
+size_t mgb_mlp_chain_packed_floats(int n_layers);
+int mgb_mlp_chain_pack_layer(const float* W, int ldw, int out_features, const float* bias, int layer, int n_layers,
+                             float* packed, void* stream);
+int mgb_mlp_chain_fwd(const float* x, int ldx, int64_t rows, int n_layers, const float* packed, int act, int in_act,
+                      int n_out, float* y, int ldy, void* stream);
 size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features);
 /* dx = (dy * act'(y_pre)) W;  dW (+)= (dy * act'(y_pre))^T x;  db (+)= colsum.  dx may be NULL. */
 int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features,

@@ -178,6 +178,41 @@ int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_fea
     return launch_linear_tc(precision, a, STREAM(stream));
 }
 
+// ---- a whole 128-wide MLP in one launch (mlp_chain_tc.cu): packed = [n_layers][hi | lo images] | [n_layers][128] biases
+size_t mgb_mlp_chain_packed_floats(int n_layers) {
+    if (n_layers < 1 || n_layers > 8) return 0;
+    return (size_t)n_layers * 128 * 128 + (size_t)n_layers * 128;
+}
+
+int mgb_mlp_chain_pack_layer(const float* W, int ldw, int out_features, const float* bias, int layer, int n_layers, float* packed,
+                             void* stream) {
+    MGB_REQUIRE(n_layers >= 1 && n_layers <= 8 && layer >= 0 && layer < n_layers, "mlp_chain_pack_layer: layer %d of %d", layer, n_layers);
+    MGB_REQUIRE(out_features >= 1 && out_features <= 128, "mlp_chain_pack_layer: 1 <= out_features <= 128 (got %d)", out_features);
+    MGB_TRY(pack_weight_tile(W, ldw, out_features, 128, 0, 0, packed + (size_t)layer * 128 * 128, STREAM(stream), 1));
+    float* b = packed + (size_t)n_layers * 128 * 128 + (size_t)layer * 128;
+    MGB_CUDA(cudaMemsetAsync(b, 0, 128 * sizeof(float), STREAM(stream)));
+    if (bias) MGB_CUDA(cudaMemcpyAsync(b, bias, (size_t)out_features * sizeof(float), cudaMemcpyDeviceToDevice, STREAM(stream)));
+    return MGB_OK;
+}
+
+int mgb_mlp_chain_fwd(const float* x, int ldx, int64_t rows, int n_layers, const float* packed, int act, int in_act, int n_out, float* y,
+                      int ldy, void* stream) {
+    MGB_REQUIRE(act >= 0 && act <= 2 && (in_act == 0 || in_act == 1), "mlp_chain_fwd: unknown activation");
+    MGB_REQUIRE(n_layers >= 1 && n_layers <= 8, "mlp_chain_fwd: 1..8 layers (got %d)", n_layers);
+    MlpChainArgs a{};
+    int* dev_flag = nullptr;
+    volatile int* host_flag = f16_range_flag(&dev_flag);
+    if (host_flag && *host_flag) {
+        *host_flag = 0;
+        MGB_REQUIRE(false, "mlp_chain_fwd: an earlier fp16-split Linear met |x| >= 32768 (fp16 range); use the fp32 path (set_linear_tc(False)) for this data");
+    }
+    a.range_flag = dev_flag;
+    a.x = x; a.ldx = ldx; a.rows = rows; a.n_layers = n_layers;
+    a.wimg = packed; a.bias = packed + (size_t)n_layers * 128 * 128;
+    a.act = act; a.in_act = in_act; a.n_out = n_out; a.y = y; a.ldy = ldy;
+    return launch_mlp_chain_tc(a, STREAM(stream));
+}
+
 int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
                   double eps, double weight_decay, int64_t step, double grad_scale, void* stream) {
     return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, STREAM(stream));

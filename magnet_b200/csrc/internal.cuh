@@ -141,6 +141,18 @@ int launch_tail_dgrad(const float* dy, int lddy, int ny, const float* pre, int l
 #ifdef MGB_TIMELINE
 int set_timeline_buffer(long long* p);
 #endif
+// mlp_chain_tc.cu (a whole 128-wide MLP in one launch, forward only)
+struct MlpChainArgs {
+    const float* x; int ldx; int64_t rows;
+    int n_layers;                    // Linear layers, all with 128 inputs; 128 outputs except the last (n_out <= 128)
+    const void* wimg;                // [n_layers][hi | lo] swizzled fp16 images of W_l [out, 128] (zero-padded rows), 64 KB each
+    const float* bias;               // [n_layers][128], zero-padded
+    int act;                         // activation after every layer but the last
+    int in_act;                      // activation applied to x on load (0 none, 1 ReLU)
+    int n_out; float* y; int ldy;
+    int* range_flag;                 // raised when an operand leaves the fp16 range
+};
+int launch_mlp_chain_tc(const MlpChainArgs& a, cudaStream_t s);
 // optim.cu
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
               double weight_decay, int64_t step, double grad_scale, cudaStream_t s);

@@ -215,6 +215,44 @@ def _tc_weight_images(W: torch.Tensor):
     return packed
 
 
+def mlp_chain(x, linears, act: str = "relu", in_act: str = "none", cache_owner=None):
+    """Inference forward of ``linears`` (nn.Linear modules: Linear(128,128) + act ... Linear(128, out <= 128)) in one launch
+    (mgb_mlp_chain_fwd): the activations never leave the SM between the layers.  Returns None when the shapes or the
+    current settings do not allow it (the caller then runs the layers one by one).  The packed weights are cached on
+    ``cache_owner`` (the MLP module), keyed on the version counters of its parameters."""
+    if not _linear_tc or _precision != "fp32_tc" or torch.is_grad_enabled() and any(p.requires_grad for l in linears for p in (l.weight, l.bias)):
+        return None
+    if x.shape[-1] != 128 or not x.is_cuda or x.dtype != torch.float32 or not (1 <= len(linears) <= 8):
+        return None
+    if any(l.in_features != 128 for l in linears) or any(l.out_features != 128 for l in linears[:-1]) or linears[-1].out_features > 128:
+        return None
+    L = _lib.lib()
+    nl = len(linears)
+    key = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version) for l in linears) + \
+        (torch.cuda.current_stream().cuda_stream,)
+    store = cache_owner.__dict__ if cache_owner is not None else None
+    hit = store.get("_mgb_chain") if store is not None else None
+    if hit is not None and hit[0] == key:
+        packed = hit[1]
+    else:
+        packed = torch.empty(L.mgb_mlp_chain_packed_floats(nl), dtype=torch.float32, device=x.device)
+        for i, l in enumerate(linears):
+            W, b = l.weight.detach(), l.bias.detach()
+            if W.stride(1) != 1:
+                W = W.contiguous()
+            _lib.check(L.mgb_mlp_chain_pack_layer(_lib.ptr(W), W.stride(0), l.out_features, _lib.ptr(b.contiguous()), i, nl,
+                                                  _lib.ptr(packed), _lib.stream()), "mlp_chain_pack_layer")
+        if store is not None:
+            store["_mgb_chain"] = (key, packed)
+    shape = x.shape
+    x2 = _lib.f32c(x).reshape(-1, 128)
+    n_out = linears[-1].out_features
+    y = _empty((x2.shape[0], n_out), x2)
+    _lib.check(L.mgb_mlp_chain_fwd(_lib.ptr(x2), 128, x2.shape[0], nl, _lib.ptr(packed), ACT[act], ACT[in_act], n_out, _lib.ptr(y),
+                                   n_out, _lib.stream()), "mlp_chain_fwd")
+    return y.reshape(*shape[:-1], n_out)
+
+
 def linear_act(x, W, b, act: str = "none", residual=None):
     packed = _tc_weight_images(W)
     if not torch.is_grad_enabled() or not (x.requires_grad or W.requires_grad or b.requires_grad or

@@ -46,7 +46,22 @@ class MLP(nn.Module):
             raise RuntimeError("magnet_b200 MLP kernels implement the reference's ReLU MLPs only")
         lin = self.linears()
         out = x
+        # inference: everything behind the first Linear in one launch (activations stay on the SM between the layers)
+        if not torch.is_grad_enabled() and len(lin) >= 2:
+            if first_preact is None and lin[0].in_features == 128:       # e.g. the projector: the first Linear joins the chain
+                y = MF.mlp_chain(x, lin, "relu", cache_owner=self)
+                if y is not None:
+                    return y
+            h = first_preact if first_preact is not None else MF.linear_act(x, lin[0].weight, lin[0].bias, "relu")
+            y = MF.mlp_chain(h, lin[1:], "relu", cache_owner=self)
+            if y is not None:
+                return y
+            out, start = h, 1
+        else:
+            start = 0
         for n, l in enumerate(lin):
+            if n < start:
+                continue
             last = n + 1 == len(lin)
             if n == 0 and first_preact is not None:      # already activated by the caller (fused into the gather)
                 out = first_preact

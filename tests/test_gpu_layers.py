@@ -74,6 +74,31 @@ def test_linear_act_tensor_core_path(rows, fin, fout, act):
     assert rel_err(y, z) < 1e-6 and torch.equal(y, y2)
 
 
+@pytest.mark.parametrize("rows,n_layers,n_out", [(1000, 5, 1), (129, 4, 128), (5, 1, 10), (2048, 4, 10), (257, 2, 128)])
+def test_mlp_chain_one_launch(rows, n_layers, n_out):
+    """A whole MLP (Linear(128,128)+ReLU ... Linear(128,n_out)) in one launch against an fp64 evaluation of the same layers;
+    odd tile counts leave the second tile slot of the last pair empty."""
+    g = S._gen(rows + n_layers)
+    lins = [torch.nn.Linear(128, 128 if i + 1 < n_layers else n_out).to(DEV) for i in range(n_layers)]
+    for l in lins:
+        l.weight.data = (torch.randn(l.weight.shape, generator=g) / 128 ** 0.5).to(DEV)
+        l.bias.data = (0.1 * torch.randn(l.bias.shape, generator=g)).to(DEV)
+    x = torch.randn(rows, 128, generator=g).to(DEV)
+    holder = torch.nn.Module()
+    with torch.no_grad():
+        y = MF.mlp_chain(x, lins, "relu", cache_owner=holder)
+        y2 = MF.mlp_chain(x, lins, "relu", cache_owner=holder)       # cached weight images
+        yr = MF.mlp_chain(-x, lins, "relu", in_act="relu")           # ReLU applied to the input on load
+    assert y is not None and y.shape == (rows, n_out) and torch.equal(y, y2)
+    z, zr = x.double().cpu(), torch.relu(-x.double().cpu())
+    for i, l in enumerate(lins):
+        W, b = l.weight.double().cpu(), l.bias.double().cpu()
+        z, zr = z @ W.T + b, zr @ W.T + b
+        if i + 1 < n_layers:
+            z, zr = torch.relu(z), torch.relu(zr)
+    assert rel_err(y, z) < 2e-6 and rel_err(yr, zr) < 2e-6
+
+
 def test_linear_act_tensor_core_range_guard():
     """fp16 tops out at 65504: an input beyond 32768 is reported by the next call instead of turning into infinities quietly."""
     x = torch.full((256, 128), 1.0, device=DEV)
