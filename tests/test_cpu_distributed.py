@@ -35,8 +35,15 @@ def _worker(rank, world, port, out_dir):
         per_sample = local["u"].reshape(local["u"].shape[0], -1).sum(1, keepdim=True)
         sizes = [D.shard_range(6, r, world)[1] - D.shard_range(6, r, world)[0] for r in range(world)]
         gathered = D.gather_samples(per_sample, sizes)
+        # the flat-buffer path of optim.FlatAdam: one collective on the buffer itself, the mean applied as grad_scale
+        from magnet_b200.optim import allreduce_flat_gradient
+
+        class _Flat:          # stands in for FlatAdam (which needs CUDA parameters): only .flat_grad is touched
+            flat_grad = torch.full((5,), float(rank + 1))
+        scale = allreduce_flat_gradient(_Flat, world)
         torch.save({"grads": [p.grad.clone() for p in model.parameters()], "frozen": [p.grad.clone() for p in frozen.parameters()],
-                    "gathered": gathered, "lo_hi": D.shard_range(6, rank, world)}, os.path.join(out_dir, f"r{rank}.pt"))
+                    "gathered": gathered, "lo_hi": D.shard_range(6, rank, world), "flat": _Flat.flat_grad.clone(), "scale": scale},
+                   os.path.join(out_dir, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -66,3 +73,4 @@ def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
     assert all(float(g.abs().max()) == 0.0 for g in r0["frozen"])
     want = batch["u"].reshape(6, -1).sum(1, keepdim=True)
     assert torch.equal(r0["gathered"], want) and torch.equal(r1["gathered"], want)
+    assert torch.equal(r0["flat"], torch.full((5,), 3.0)) and torch.equal(r1["flat"], r0["flat"]) and r0["scale"] == 0.5
