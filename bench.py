@@ -94,8 +94,14 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        inside = [r for t, r in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= t <= self.t1 + 0.06]
-        rows = inside
+        rows = []
+        if self.t0 is not None and self.t1 is not None and self.rows:
+            # a sample describes the 50 ms before it arrived: keep those whose window overlaps the timed region; a region
+            # shorter than one period keeps the sample that closes it
+            rows = [r for t, r in self.rows if self.t0 <= t <= self.t1 + 0.06]
+            if not rows:
+                after = [(t, r) for t, r in self.rows if t >= self.t0]
+                rows = [min(after, key=lambda tr: tr[0])[1]] if after else [self.rows[-1][1]]
         sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -350,6 +356,8 @@ def run_ours(args, rank, world, local_rank):
         ev1.record()
         barrier()
         clocks.mark_end()
+        if args.steps * 0.025 < 0.12:
+            time.sleep(0.12)          # a very short timed region: let the sample that covers it arrive before nvidia-smi is stopped
     launches = (L.mgb_launch_count() - launches0) // max(args.steps, 1)
     L.mgb_profile_enable(0)
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
