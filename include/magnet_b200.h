@@ -183,6 +183,25 @@ int mgb_segment_sum_rows(const float* rows, int cols, const int32_t* rowptr, con
                          float* out, int ld_out, void* stream);
 int mgb_gather_rows(const float* rows, const int64_t* index, const int32_t* rowptr, int64_t n_edges, float* out, void* stream);
 
+/* Fused edge function of InteractionNetwork (models/magnet_gnn.py:79-82 message, :54 aggr='mean'), forward:
+ *   agg[i] = mean_{e: edge_index[1][e] = i} LayerNorm(MLP5(cat[x_i, x_j, e_scale * e_features[e]]))
+ * in ONE launch: e_features rows are gathered through the aggregation plan, the five 128x128 contractions of edge_fn run
+ * as tcgen05 tiles whose activations stay in shared memory, LayerNorm and the per-destination mean (fixed order, no
+ * atomics) happen in the last epilogue.  Nothing of size [E,128] is written.
+ *   pq [N,256] = x [W0[:, :128] | W0[:, 128:256]]^T + [b0 | 0]  (first Linear factorised per node, mgb_linear_tc_fwd);
+ *   perm / rowptr / dst / src: plan of mgb_csr_plan (perm NULL: e_features already in aggregation order);
+ *   e_scale: the reference doubles e_features every layer and never updates them - layer l sees 2^l e_0;
+ *   packed: mgb_in_edge_packed_floats() floats; layer 0 = W0[:, 256:384] (ldw 384, bias NULL), layers 1..4 = the other
+ *   Linears of edge_fn with their biases, then the LayerNorm affine.  precision: 2 = bf16 operands (1e-2 contract),
+ *   otherwise fp16 hi/lo split (1e-5 contract).  agg [N,128] is written for every node (0 where no edge arrives). */
+size_t mgb_in_edge_packed_floats(void);
+int mgb_in_edge_pack_layer(const float* W, int ldw, const float* bias, int layer, int precision, float* packed, void* stream);
+int mgb_in_edge_pack_norm(const float* gamma, const float* beta, float* packed, void* stream);
+size_t mgb_in_edge_fwd_workspace(int64_t n_edges);
+int mgb_in_edge_fwd(const float* e_features, float e_scale, const int32_t* perm, const float* pq, const int32_t* rowptr,
+                    const int32_t* dst, const int32_t* src, int64_t n_nodes, int64_t n_edges, const float* packed, int precision,
+                    float* agg, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * INR decoder.  Replaces the body of MAgNetGNN.continuous_decoder (models/magnet_gnn.py:254-280) given the
  * neighbour table of mgb_knn (:247).  a [B*L,128] = lr_encoded proj_head.weight[:, :128]^T + proj_head.bias

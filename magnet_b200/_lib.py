@@ -101,3 +101,51 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+def ver(t: torch.Tensor) -> int:
+    """Version counter of a tensor for cache keys.  Inference tensors (created under ``torch.inference_mode()``, which
+    Lightning >= 1.8 uses for validate/test/predict) do not track one: they cannot be modified in place outside
+    inference mode either, so (data_ptr, shape, identity) identifies their contents and -1 stands in for the counter."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
+def on(t: torch.Tensor):
+    """Context manager: make the device of ``t`` current for the launches inside (kernels run on the current device's
+    current stream; tensors on another device than the current one would otherwise be launched against foreign pointers)."""
+    return torch.cuda.device(t.device)
+
+
+def same_device(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"magnet_b200: operands live on different devices ({dev} and {t.device})")
+
+
+def guard(fn):
+    """Decorator for the forward entry points: run ``fn`` with the device of its first CUDA tensor argument current, and
+    refuse operands spread over several devices (kernels launch on the current device's current stream)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise RuntimeError(f"magnet_b200.{fn.__name__}: operands live on different devices ({dev} and {a.device})")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped

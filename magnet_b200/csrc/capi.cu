@@ -213,6 +213,42 @@ int mgb_mlp_chain_fwd(const float* x, int ldx, int64_t rows, int n_layers, const
     return launch_mlp_chain_tc(a, STREAM(stream));
 }
 
+// ---- fused InteractionNetwork edge function (in_edge_tc.cu): packed = [5][hi | lo images] | [5][128] biases | gamma | beta
+size_t mgb_in_edge_packed_floats(void) { return (size_t)5 * 128 * 128 + 5 * 128 + 256; }
+
+int mgb_in_edge_pack_layer(const float* W, int ldw, const float* bias, int layer, int precision, float* packed, void* stream) {
+    MGB_REQUIRE(layer >= 0 && layer < 5, "in_edge_pack_layer: layer %d of 5", layer);
+    MGB_TRY(pack_weight_tile(W, ldw, 128, 128, 0, 0, packed + (size_t)layer * 128 * 128, STREAM(stream), precision == 2 ? 0 : 1));
+    float* b = packed + (size_t)5 * 128 * 128 + (size_t)layer * 128;
+    if (bias) MGB_CUDA(cudaMemcpyAsync(b, bias, 128 * sizeof(float), cudaMemcpyDeviceToDevice, STREAM(stream)));
+    else MGB_CUDA(cudaMemsetAsync(b, 0, 128 * sizeof(float), STREAM(stream)));
+    return MGB_OK;
+}
+
+int mgb_in_edge_pack_norm(const float* gamma, const float* beta, float* packed, void* stream) {
+    float* g = packed + (size_t)5 * 128 * 128 + 5 * 128;
+    MGB_CUDA(cudaMemcpyAsync(g, gamma, 128 * sizeof(float), cudaMemcpyDeviceToDevice, STREAM(stream)));
+    MGB_CUDA(cudaMemcpyAsync(g + 128, beta, 128 * sizeof(float), cudaMemcpyDeviceToDevice, STREAM(stream)));
+    return MGB_OK;
+}
+
+size_t mgb_in_edge_fwd_workspace(int64_t n_edges) { return in_edge_fwd_workspace(n_edges); }
+
+int mgb_in_edge_fwd(const float* e_features, float e_scale, const int32_t* perm, const float* pq, const int32_t* rowptr,
+                    const int32_t* dst, const int32_t* src, int64_t n_nodes, int64_t n_edges, const float* packed, int precision,
+                    float* agg, void* workspace, size_t workspace_bytes, void* stream) {
+    int* dev_flag = nullptr;
+    if (precision != 2) {
+        volatile int* host_flag = f16_range_flag(&dev_flag);
+        if (host_flag && *host_flag) {
+            *host_flag = 0;
+            MGB_REQUIRE(false, "in_edge_fwd: an earlier fp16-split kernel met |x| >= 32768 (fp16 range); use the fp32 path (set_linear_tc(False)) for this data");
+        }
+    }
+    return launch_in_edge_fwd(precision, e_features, e_scale, perm, pq, rowptr, dst, src, n_nodes, n_edges, packed, agg, dev_flag,
+                              workspace, workspace_bytes, STREAM(stream));
+}
+
 int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
                   double eps, double weight_decay, int64_t step, double grad_scale, void* stream) {
     return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, STREAM(stream));

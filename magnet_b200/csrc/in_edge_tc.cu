@@ -1,0 +1,470 @@
+// magnet_b200 — fused edge kernel of MAgNet's InteractionNetwork on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Reference: InteractionNetwork.message + aggregate (models/magnet_gnn.py:70-90, edge_fn :61-68, aggr='mean' :54):
+//     m_e   = LayerNorm(MLP5(cat[x_i, x_j, e_e]))        384 -> 128 -> 128 -> 128 -> 128 -> 128, ReLU between
+//     agg_i = mean_{e -> i} m_e                           at i = edge_index[1] (UNSORTED in MAgNetGNN graphs)
+// The first Linear is factorised: W0 [x_i, x_j, e] = P[i] + Q[j] + We e with P|Q = x [W0_i | W0_j]^T + [b0 | 0] computed per
+// NODE (linear_tc.cu); what remains per EDGE is a chain of five 128x128 contractions, which never leaves the SM here:
+//   producers   gather e_features rows through the aggregation plan (position -> COO edge id), scale by 2^l (the
+//               reference doubles e_features every layer and never updates them), split into fp16 hi | lo and
+//               write a K-major operand image (as mlp_chain_tc.cu)
+//   layer 0     D^T[n][e] = sum_k We[n][k] e[e][k];  epilogue (thread = channel n) adds P[dst_e][n] + Q[src_e][n], ReLU,
+//               writes the next operand IN PLACE as an MN-major image
+//   layers 1-3  as mlp_chain_tc.cu (bias, ReLU, MN-major image)
+//   layer 4     y = D + b4;  LayerNorm over the 128 channels of an edge = across the 128 epilogue threads: y goes through
+//               the (now free) operand tile as an fp32 [e][n] staging buffer, two threads per edge compute mean / rstd
+//               exactly (two-pass, values in registers), then every thread normalises its channel from TMEM and runs the
+//               segmented mean over the destination-sorted positions in registers (segmeta.cuh; no atomics, fixed order)
+// Two 128-edge tiles ping-pong between the MMA warp and the epilogue warps; one layer's weight images (64 KB) are
+// re-loaded from L2 per layer with one bulk async copy.  HBM sees e_features once (512 B per edge) and agg once.
+// NSPLIT = 2: operands split into two fp16 values, three MMA terms (1e-5 contract); NSPLIT = 1: plain bf16 (1e-2).
+#include "internal.cuh"
+#include "tc_common.cuh"
+#include "segmeta.cuh"
+
+namespace mgb {
+
+constexpr int IE_TE = 128;                       // edge positions per tile (MMA N)
+constexpr int IE_L = 5;                          // Linear layers of edge_fn
+constexpr int IE_EPI_WARPS = 8, IE_PROD_WARPS = 8;
+constexpr int IE_MMA_WARP = IE_EPI_WARPS, IE_META_WARP = IE_EPI_WARPS + 1, IE_PROD_WARP0 = IE_EPI_WARPS + 2;
+constexpr int IE_THREADS = (IE_PROD_WARP0 + IE_PROD_WARPS) * 32;      // 576
+constexpr int IE_FLUSH = 64;                     // positions per epilogue warp = granularity of the stored partial sums
+constexpr int IE_MSLOTS = 4;                     // metadata slots: (pair parity, tile of the pair)
+using IeMeta = TileMetaT<IE_TE>;
+constexpr size_t IN_EDGE_SMEM = 1024 + (size_t)2 * TILE_BYTES + (size_t)4 * TILE_BYTES + IE_MSLOTS * sizeof(IeMeta) +
+                                2 * IE_TE * sizeof(float2) + 256;
+
+struct InEdgeArgs {
+    const float* e;            // [E][128] edge features, COO order
+    float e_scale;             // 2^l
+    const int32_t* perm;       // [E] COO edge id of every aggregation-order position (NULL: identity)
+    const float* pq;           // [N][256]  P | Q
+    const int32_t* rowptr;     // plan
+    const int32_t* dstv;
+    const int32_t* srcv;
+    int64_t n_edges;
+    const void* wimg;          // [5][hi | lo] images of We, W1..W4
+    const float* bias;         // [5][128] (row 0 unused: b0 is folded into P)
+    const float* gamma;        // LayerNorm affine
+    const float* beta;
+    float* agg;                // [N][128], pre-zeroed
+    float* part_head;
+    float* part_tail;
+    int* range_flag;
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InEdgeArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = umma::smem_u32(smem_raw);
+    unsigned char* base = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    unsigned char* w_img = base;                                        // [hi|lo] of the current layer
+    unsigned char* x_img = base + (size_t)2 * TILE_BYTES;               // [tile 0|1][hi|lo]; fp32 staging in the last layer
+    IeMeta* metas = reinterpret_cast<IeMeta*>(x_img + (size_t)4 * TILE_BYTES);
+    float2* stats = reinterpret_cast<float2*>(metas + IE_MSLOTS);       // [2][128] mean, rstd of every edge of a tile
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * IE_TE);
+    uint64_t* x_full = bars;          // [2] producers -> MMA (layer 0 operand written)
+    uint64_t* x_empty = bars + 2;     // [2] last-layer epilogue -> producers
+    uint64_t* t_full = bars + 4;      // [2] MMA -> epilogue
+    uint64_t* x_ready = bars + 6;     // [2] hidden-layer epilogue -> MMA
+    uint64_t* w_bar = bars + 8;
+    uint64_t* w_free = bars + 9;
+    uint64_t* m_full = bars + 10;     // [IE_MSLOTS] meta warp -> epilogue
+    uint64_t* m_empty = bars + 10 + IE_MSLOTS;   // [IE_MSLOTS] epilogue -> meta warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * IE_MSLOTS);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_tiles = ceil_div<int64_t>(a.n_edges, IE_TE);
+    const int64_t n_pairs = (n_tiles + 1) / 2;
+    const int np = (int)((n_pairs - blockIdx.x + gridDim.x - 1) / gridDim.x);      // tile pairs of this CTA (>= 1)
+
+    if (tid == 0) {
+        for (int t = 0; t < 2; ++t) {
+            umma::mbar_init(&x_full[t], IE_PROD_WARPS * 32);
+            umma::mbar_init(&x_empty[t], IE_EPI_WARPS * 32);
+            umma::mbar_init(&t_full[t], 1);
+            umma::mbar_init(&x_ready[t], IE_EPI_WARPS * 32);
+        }
+        for (int s = 0; s < IE_MSLOTS; ++s) {
+            umma::mbar_init(&m_full[s], 32);
+            umma::mbar_init(&m_empty[s], IE_EPI_WARPS * 32);
+        }
+        umma::mbar_init(w_bar, 1);
+        umma::mbar_init(w_free, 1);
+        umma::fence_barrier_init();
+    }
+    if (warp == IE_MMA_WARP) umma::tmem_alloc(tmem_slot, 256);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < IE_EPI_WARPS) {
+        // =========================== epilogue: thread = output channel n; warps 0-3 positions 0-63, warps 4-7 64-127 ====
+        const int n = tid & 127, hf = warp >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float gamma = a.gamma[n], beta = a.beta[n];
+        const float* pqn = a.pq + n;
+        uint32_t tf[2] = {0, 0};        // completed phases of t_full[t]
+#pragma unroll 1
+        for (int it = 0; it < np; ++it) {
+            const int64_t pair = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+#pragma unroll 1
+            for (int l = 0; l < IE_L; ++l) {
+                const float bias = l ? a.bias[l * 128 + n] : 0.f;
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {
+                    if (pair * 2 + t >= n_tiles) continue;
+                    const int slot = (it & 1) * 2 + t;
+                    const IeMeta* M = metas + slot;
+                    unsigned char* xt = x_img + (size_t)t * 2 * TILE_BYTES;
+                    unsigned char* xrow = xt + n * 128;
+                    const uint32_t tacc = tmem + (uint32_t)(t * 128) + lane_base + (uint32_t)(hf * 64);
+                    if (l == 0) {
+                        // ---- layer 0: + P[dst] + Q[src], ReLU.  The Q values of the first 32 positions are requested before
+                        // the accumulator is waited for; P changes only at segment starts (warp-uniform branch).
+                        umma::mbar_wait(&m_full[slot], (it >> 1) & 1);
+                        float qv[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) qv[i] = pqn[M->qoff[hf * 64 + i]];
+                        umma::mbar_wait(&t_full[t], tf[t] & 1);
+                        ++tf[t];
+                        umma::tc_fence_after();
+                        int dprev = -2;
+                        float pv = 0.f;
+#pragma unroll 1
+                        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                            for (int cc = 0; cc < 4; ++cc) {
+                                const int c0 = hf * 64 + h * 32 + cc * 8;
+                                float v[8];
+                                umma::tmem_ld8(tacc + (uint32_t)(h * 32 + cc * 8), v);
+                                const int4 d0 = *reinterpret_cast<const int4*>(&M->dst[c0]);
+                                const int4 d1 = *reinterpret_cast<const int4*>(&M->dst[c0 + 4]);
+                                const int dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    if (dd[i] != dprev) {
+                                        dprev = dd[i];
+                                        pv = dd[i] >= 0 ? pqn[(int64_t)dd[i] * 256] : 0.f;
+                                    }
+                                    v[i] = dd[i] >= 0 ? fmaxf(v[i] + pv + qv[cc * 8 + i], 0.f) : 0.f;
+                                }
+                                if (NSPLIT == 2 &&
+                                    fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))) >= 32768.f &&
+                                    a.range_flag)
+                                    *a.range_flag = 1;
+                                const uint32_t off = (uint32_t)(c0 >> 6) * (128u * 128u) + (uint32_t)((((c0 & 63) >> 3) ^ (n & 7)) << 4);
+                                uint4 hi, lo;
+                                if (NSPLIT == 2) {
+                                    split2_f16(v[0], v[1], hi.x, lo.x);
+                                    split2_f16(v[2], v[3], hi.y, lo.y);
+                                    split2_f16(v[4], v[5], hi.z, lo.z);
+                                    split2_f16(v[6], v[7], hi.w, lo.w);
+                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
+                                    *reinterpret_cast<uint4*>(xrow + TILE_BYTES + off) = lo;
+                                } else {
+                                    hi.x = umma::pack_bf16(v[0], v[1]);
+                                    hi.y = umma::pack_bf16(v[2], v[3]);
+                                    hi.z = umma::pack_bf16(v[4], v[5]);
+                                    hi.w = umma::pack_bf16(v[6], v[7]);
+                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
+                                }
+                            }
+                            if (h == 0) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) qv[i] = pqn[M->qoff[hf * 64 + 32 + i]];
+                            }
+                        }
+                        umma::fence_async_smem();
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(&x_ready[t]);
+                        continue;
+                    }
+                    umma::mbar_wait(&t_full[t], tf[t] & 1);
+                    ++tf[t];
+                    umma::tc_fence_after();
+                    if (l < IE_L - 1) {
+                        // ---- hidden layers: bias, ReLU, next operand in place (MN-major image [n][e])
+#pragma unroll 1
+                        for (int cb = 0; cb < 64; cb += 8) {
+                            const int c0 = hf * 64 + cb;
+                            float v[8];
+                            umma::tmem_ld8(tacc + (uint32_t)cb, v);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + bias, 0.f);
+                            if (NSPLIT == 2 &&
+                                fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))) >= 32768.f &&
+                                a.range_flag)
+                                *a.range_flag = 1;
+                            const uint32_t off = (uint32_t)(c0 >> 6) * (128u * 128u) + (uint32_t)((((c0 & 63) >> 3) ^ (n & 7)) << 4);
+                            uint4 hi, lo;
+                            if (NSPLIT == 2) {
+                                split2_f16(v[0], v[1], hi.x, lo.x);
+                                split2_f16(v[2], v[3], hi.y, lo.y);
+                                split2_f16(v[4], v[5], hi.z, lo.z);
+                                split2_f16(v[6], v[7], hi.w, lo.w);
+                                *reinterpret_cast<uint4*>(xrow + off) = hi;
+                                *reinterpret_cast<uint4*>(xrow + TILE_BYTES + off) = lo;
+                            } else {
+                                hi.x = umma::pack_bf16(v[0], v[1]);
+                                hi.y = umma::pack_bf16(v[2], v[3]);
+                                hi.z = umma::pack_bf16(v[4], v[5]);
+                                hi.w = umma::pack_bf16(v[6], v[7]);
+                                *reinterpret_cast<uint4*>(xrow + off) = hi;
+                            }
+                        }
+                        umma::fence_async_smem();
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(&x_ready[t]);
+                        continue;
+                    }
+                    // ---- last layer: y = D + b4 -> LayerNorm over channels -> segmented mean over positions
+                    // pass 1: y[n][e] -> staging [e][n] fp32 (16-byte chunks of a row permuted by the row index: every
+                    // access pattern below is bank-conflict free).  The operand tile is free: all MMAs that read it are done.
+#pragma unroll 1
+                    for (int cb = 0; cb < 64; cb += 8) {
+                        const int c0 = hf * 64 + cb;
+                        float v[8];
+                        umma::tmem_ld8(tacc + (uint32_t)cb, v);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int e = c0 + i;
+                            *reinterpret_cast<float*>(xt + e * 512 + ((((n >> 2) ^ (e & 31))) << 4) + (n & 3) * 4) = v[i] + bias;
+                        }
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
+                    // pass 2: two threads per edge (64 channels each), exact two-pass mean / variance
+                    {
+                        const int j = tid & 127;
+                        const int e = hf * 64 + (j >> 1), part = j & 1;
+                        const unsigned char* row = xt + e * 512;
+                        float4 y[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int chunk = part * 16 + (i ^ (part << 2));
+                            y[i] = *reinterpret_cast<const float4*>(row + ((chunk ^ (e & 31)) << 4));
+                        }
+                        float s = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        const float mean = s * (1.0f / 128.0f);
+                        float q = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float dx = y[i].x - mean, dy = y[i].y - mean, dz = y[i].z - mean, dw = y[i].w - mean;
+                            q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                        }
+                        q += __shfl_xor_sync(0xffffffffu, q, 1);
+                        if (part == 0) stats[t * IE_TE + e] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / 128.0f) + 1e-5f));
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
+                    // pass 3: normalise this thread's channel (accumulator re-read from TMEM) and reduce per destination
+                    {
+                        float sum = 0.f;
+                        const float2* st = stats + t * IE_TE;
+#pragma unroll 1
+                        for (int cb = 0; cb < 64; cb += 8) {
+                            const int c0 = hf * 64 + cb;
+                            float v[8];
+                            umma::tmem_ld8(tacc + (uint32_t)cb, v);
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) {
+                                const float4 mr = *reinterpret_cast<const float4*>(st + c0 + i);     // mean, rstd of two edges
+                                v[i] = fmaf(((v[i] + bias) - mr.x) * mr.y, gamma, beta);
+                                v[i + 1] = fmaf(((v[i + 1] + bias) - mr.z) * mr.w, gamma, beta);
+                            }
+                            uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 31)) & 0xffu, todo = 0xffu;
+                            if (fm == 0) {                   // the common case: no stored sum ends inside the chunk
+                                sum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                                continue;
+                            }
+                            while (fm) {
+                                const uint32_t low = fm & (0u - fm);
+                                const uint32_t upto = (low << 1) - 1u;
+                                const uint32_t rng = todo & upto;
+                                float part = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (rng & (1u << i)) part += v[i];
+                                const int pos = c0 + (31 - __clz(low));
+                                M->out[pos][n] = (sum + part) * M->scale[pos];
+                                sum = 0.f;
+                                todo &= ~upto;
+                                fm &= fm - 1;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                if (todo & (1u << i)) sum += v[i];
+                        }
+                    }
+                    umma::tc_fence_before();
+                    umma::mbar_arrive(&x_empty[t]);
+                    umma::mbar_arrive(&m_empty[slot]);
+                }
+            }
+        }
+    } else if (warp == IE_MMA_WARP) {
+        // =========================== MMA issue + weight loads =======================================
+        const uint32_t id_k = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 0) : umma::idesc_bf16(128, 128, 0, 0);   // layer 0: B K-major
+        const uint32_t id_m = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 1) : umma::idesc_bf16(128, 128, 0, 1);   // layers >= 1: B MN-major
+        const uint64_t w_d = umma::desc_sw128(umma::smem_u32(w_img), 16, 1024);
+        const uint64_t xk_d = umma::desc_sw128(umma::smem_u32(x_img), 16, 1024);
+        const uint64_t xm_d = umma::desc_sw128(umma::smem_u32(x_img), 128 * 128, 1024);
+        constexpr uint32_t TB = TILE_BYTES >> 4;
+        uint32_t wl = 0;                 // weight loads issued so far
+        uint32_t xf[2] = {0, 0}, xr[2] = {0, 0};
+#pragma unroll 1
+        for (int it = 0; it < np; ++it) {
+            const int64_t pair = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+#pragma unroll 1
+            for (int l = 0; l < IE_L; ++l) {
+                if (wl > 0) umma::mbar_wait(w_free, (wl - 1) & 1);          // the MMAs of the previous layer are done with w_img
+                if (lane == 0) load_w2_image(w_img, (const unsigned char*)a.wimg + (size_t)l * 2 * TILE_BYTES, NSPLIT * TILE_BYTES, w_bar);
+                umma::mbar_wait(w_bar, wl & 1);
+                ++wl;
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {
+                    if (pair * 2 + t >= n_tiles) continue;
+                    if (l == 0) { umma::mbar_wait(&x_full[t], xf[t] & 1); ++xf[t]; }
+                    else { umma::mbar_wait(&x_ready[t], xr[t] & 1); ++xr[t]; }
+                    umma::tc_fence_after();
+                    if (umma::elect_one()) {
+                        const uint32_t d = tmem + (uint32_t)(t * 128);
+                        const uint64_t xd = (l == 0 ? xk_d : xm_d) + (uint64_t)((uint32_t)t * 2 * TB);
+#pragma unroll
+                        for (int term = 0; term < (NSPLIT == 2 ? 3 : 1); ++term) {      // small terms first: lo*hi, hi*lo, hi*hi
+                            const uint64_t wa = w_d + ((NSPLIT == 2 && term == 0) ? TB : 0), xb = xd + ((NSPLIT == 2 && term == 1) ? TB : 0);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const uint32_t koff_k = (uint32_t)((k >> 2) * (128 * 128 >> 4) + (k & 3) * 2), koff_m = (uint32_t)(k * 128);
+                                umma::mma_bf16(d, wa + (uint64_t)koff_k, xb + (uint64_t)(l == 0 ? koff_k : koff_m), l == 0 ? id_k : id_m,
+                                               (term | k) ? 1u : 0u);
+                            }
+                        }
+                        umma::mma_commit(&t_full[t]);
+                    }
+                    __syncwarp();
+                }
+                if (umma::elect_one()) umma::mma_commit(w_free);
+                __syncwarp();
+            }
+        }
+    } else if (warp == IE_META_WARP) {
+        // =========================== segment metadata, one pair ahead ===============================
+#pragma unroll 1
+        for (int it = 0; it < np; ++it) {
+            const int64_t pair = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                if (pair * 2 + t >= n_tiles) continue;
+                const int slot = (it & 1) * 2 + t;
+                umma::mbar_wait_relaxed(&m_empty[slot], ((it >> 1) & 1) ^ 1);
+                build_tile_meta(metas + slot, a.rowptr, a.dstv, a.srcv, a.n_edges, pair * 2 + t, lane, a.agg, SEG_H, true, a.part_head,
+                                a.part_tail, IE_FLUSH);
+                umma::mbar_arrive(&m_full[slot]);
+            }
+        }
+    } else {
+        // =========================== producers: 16 rows per warp (layer-0 operand) ==================
+        const int pw = warp - IE_PROD_WARP0;
+        const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
+        const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
+        const float* src = a.e + lane * 4;
+        const float sc = a.e_scale;
+        uint32_t xe[2] = {0, 0};
+#pragma unroll 1
+        for (int it = 0; it < np; ++it) {
+            const int64_t pair = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const int64_t tile = pair * 2 + t;
+                if (tile >= n_tiles) continue;
+                const int64_t p0 = tile * IE_TE + pw * 16;
+                int64_t mine = -1;
+                if (lane < 16 && p0 + lane < a.n_edges) mine = a.perm ? (int64_t)a.perm[p0 + lane] : p0 + lane;
+                float4 x[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const int64_t c = __shfl_sync(0xffffffffu, mine, r);
+                    x[r] = *reinterpret_cast<const float4*>(src + (c < 0 ? 0 : c) * 128);
+                    if (c < 0) x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                uint4 hl[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    float4 h = x[r];
+                    h.x *= sc; h.y *= sc; h.z *= sc; h.w *= sc;
+                    if (NSPLIT == 2) {
+                        if (fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))) >= 32768.f && a.range_flag) *a.range_flag = 1;
+                        split2_f16(h.x, h.y, hl[r].x, hl[r].z);
+                        split2_f16(h.z, h.w, hl[r].y, hl[r].w);
+                    } else {
+                        hl[r].x = umma::pack_bf16(h.x, h.y);
+                        hl[r].y = umma::pack_bf16(h.z, h.w);
+                    }
+                }
+                umma::mbar_wait(&x_empty[t], (xe[t] & 1) ^ 1);
+                ++xe[t];
+                unsigned char* img = x_img + (size_t)t * 2 * TILE_BYTES;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
+                    *reinterpret_cast<uint2*>(img + off) = make_uint2(hl[r].x, hl[r].y);
+                    if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = make_uint2(hl[r].z, hl[r].w);
+                }
+                umma::fence_async_smem();
+                umma::mbar_arrive(&x_full[t]);
+            }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == IE_MMA_WARP) umma::tmem_dealloc(tmem, 256);
+}
+
+size_t in_edge_fwd_workspace(int64_t n_edges) {
+    const int64_t sub = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, IE_FLUSH);
+    return 2 * align_up((size_t)sub * SEG_H * sizeof(float)) + 512;
+}
+
+// precision: 2 = plain bf16 (1e-2 contract), anything else = fp16 hi/lo split (1e-5 contract)
+int launch_in_edge_fwd(int precision, const float* e, float e_scale, const int32_t* perm, const float* pq, const int32_t* rowptr,
+                       const int32_t* dstv, const int32_t* srcv, int64_t n_nodes, int64_t n_edges, const float* packed, float* agg,
+                       int* range_flag, void* ws_ptr, size_t ws_bytes, cudaStream_t s) {
+    MGB_REQUIRE(n_edges >= 0 && n_edges < ((int64_t)1 << 31) && n_nodes >= 0 && n_nodes < ((int64_t)1 << 23) * 256,
+                "in_edge_fwd: sizes out of range");
+    MGB_REQUIRE(((uintptr_t)e % 16) == 0 && ((uintptr_t)pq % 16) == 0, "in_edge_fwd: e / pq must be 16-byte aligned");
+    if (n_nodes > 0) MGB_CUDA(cudaMemsetAsync(agg, 0, (size_t)n_nodes * SEG_H * sizeof(float), s));
+    if (n_edges <= 0) return MGB_OK;
+    const int64_t sub = ceil_div<int64_t>(n_edges, IE_FLUSH);
+    Workspace ws(ws_ptr, ws_bytes);
+    float* part_head = ws.take<float>((size_t)sub * SEG_H);
+    float* part_tail = ws.take<float>((size_t)sub * SEG_H);
+    MGB_WS_CHECK(ws);
+    InEdgeArgs a{};
+    a.e = e; a.e_scale = e_scale; a.perm = perm; a.pq = pq; a.rowptr = rowptr; a.dstv = dstv; a.srcv = srcv; a.n_edges = n_edges;
+    a.wimg = packed;
+    a.bias = packed + (size_t)IE_L * 128 * 128;
+    a.gamma = a.bias + IE_L * 128;
+    a.beta = a.gamma + 128;
+    a.agg = agg; a.part_head = part_head; a.part_tail = part_tail; a.range_flag = range_flag;
+    const int64_t pairs = (ceil_div<int64_t>(n_edges, IE_TE) + 1) / 2;
+    const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
+    {
+        ProfScope prof(PROF_IN_EDGE_FWD, s);
+        if (precision == 2) {
+            MGB_CUDA(cudaFuncSetAttribute(in_edge_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IN_EDGE_SMEM));
+            in_edge_fwd_tc_kernel<1><<<grid, IE_THREADS, IN_EDGE_SMEM, s>>>(a);
+        } else {
+            MGB_CUDA(cudaFuncSetAttribute(in_edge_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IN_EDGE_SMEM));
+            in_edge_fwd_tc_kernel<2><<<grid, IE_THREADS, IN_EDGE_SMEM, s>>>(a);
+        }
+    }
+    MGB_LAUNCH_CHECK();
+    return launch_segment_fixup(rowptr, dstv, n_edges, IE_FLUSH, part_head, part_tail, agg, SEG_H, 1, s);
+}
+
+}  // namespace mgb

@@ -39,6 +39,7 @@ def _empty(shape, ref):
 # --------------------------------------------------------------------------------------------
 # GNN_Layer (models/mpnn_2d.py:27-90)
 # --------------------------------------------------------------------------------------------
+@_lib.guard
 def pack_gnn_layer(W1, b1, W2, W3, W4, tw: int, dp: int, nv: int) -> torch.Tensor:
     """Packed / transposed / bf16-imaged copies of a layer's weights for the kernels (the nn.Parameters stay the
     canonical [out, in] fp32 tensors).  GNN_Layer caches the result per module, keyed on the parameters' version counters."""
@@ -67,6 +68,8 @@ class GNNLayerFn(torch.autograd.Function):
             raise RuntimeError("aggregation plan was built for a different node count")
         if packed is None:
             packed = pack_gnn_layer(W1, b1, W2, W3, W4, tw, dp, nv)
+        if W4.shape != (128, 128) or b2.shape != (128,) or b3.shape != (128,) or b4.shape != (128,):
+            raise RuntimeError(f"GNN_Layer kernels need out_features = 128; got W4 {tuple(W4.shape)}")
         prec = PRECISIONS[_precision]
         y = _empty((N, H), x)
         pq = _empty((N, 2 * H), x)
@@ -74,13 +77,15 @@ class GNNLayerFn(torch.autograd.Function):
         y1_pre = _empty((N, H), x)
         y2_pre = _empty((N, H), x)
         rstd = _empty((max(seg.n_graphs, 1), H), x)
-        ws = _lib.workspace(L.mgb_gnn_layer_fwd_workspace(N, plan.n_edges, seg.n_graphs, seg.max_nodes), x.device)
-        _lib.check(L.mgb_gnn_layer_fwd(N, plan.n_edges, tw, dp, nv, seg.n_graphs, seg.max_nodes, _lib.ptr(x), _lib.ptr(u),
-                                       _lib.ptr(pos), _lib.ptr(var), _lib.ptr(plan.rowptr), _lib.ptr(plan.dst),
-                                       _lib.ptr(plan.src), _lib.ptr(seg.gptr), _lib.ptr(packed), _lib.ptr(b2),
-                                       _lib.ptr(b3), _lib.ptr(b4), _lib.ptr(y), _lib.ptr(pq), _lib.ptr(agg),
-                                       _lib.ptr(y1_pre), _lib.ptr(y2_pre), _lib.ptr(rstd), prec, _lib.ptr(ws), ws.numel(),
-                                       _lib.stream()), "gnn_layer_fwd")
+        _lib.same_device(x, u, pos, var, W1, plan.rowptr, seg.gptr)
+        with _lib.on(x):
+            ws = _lib.workspace(L.mgb_gnn_layer_fwd_workspace(N, plan.n_edges, seg.n_graphs, seg.max_nodes), x.device)
+            _lib.check(L.mgb_gnn_layer_fwd(N, plan.n_edges, tw, dp, nv, seg.n_graphs, seg.max_nodes, _lib.ptr(x), _lib.ptr(u),
+                                           _lib.ptr(pos), _lib.ptr(var), _lib.ptr(plan.rowptr), _lib.ptr(plan.dst),
+                                           _lib.ptr(plan.src), _lib.ptr(seg.gptr), _lib.ptr(packed), _lib.ptr(b2),
+                                           _lib.ptr(b3), _lib.ptr(b4), _lib.ptr(y), _lib.ptr(pq), _lib.ptr(agg),
+                                           _lib.ptr(y1_pre), _lib.ptr(y2_pre), _lib.ptr(rstd), prec, _lib.ptr(ws), ws.numel(),
+                                           _lib.stream()), "gnn_layer_fwd")
         ctx.save_for_backward(x, u, pos, var, y, pq, agg, y1_pre, y2_pre, rstd, packed, W1, W2, b2, W3, W4)
         ctx.plan, ctx.seg = plan, seg
         ctx.dims = (N, tw, dp, nv)
@@ -120,6 +125,7 @@ class GNNLayerFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------
 # row-wise Linear (+activation, +residual) and LayerNorm
 # --------------------------------------------------------------------------------------------
+@_lib.guard
 def _linear_forward(x, W, b, act: int, residual, packed, want_pre: bool):
     """The forward kernels of LinearActFn; also called directly (no autograd node) when nothing requires a gradient."""
     _lib.require_cuda(x, W)
@@ -190,10 +196,11 @@ def set_linear_tc(on: bool) -> bool:
     return old
 
 
-def _tc_weight_images(W: torch.Tensor):
-    """Swizzled bf16 (hi | lo) images of W for the tensor-core Linear, or None when the shape is not covered.  Cached on
-    the owning parameter object (W may be a column slice of it), keyed on the slice and the parameter's version
-    counter: an optimizer step or load_state_dict rebuilds them, a rollout reuses them."""
+def _tc_weight_images(W: torch.Tensor, owner: Optional[torch.Tensor] = None):
+    """Swizzled 16-bit (hi | lo) images of W for the tensor-core Linear, or None when the shape is not covered.  Cached on
+    the owning parameter object (``owner``; W may be a column slice of it — a slice taken under torch.inference_mode()
+    has neither ``_base`` nor a version counter, so callers that slice pass the parameter explicitly), keyed on the slice
+    and the parameter's version counter: an optimizer step or load_state_dict rebuilds them, a rollout reuses them."""
     if not _linear_tc or _precision == "fp32" or W.dim() != 2 or W.stride(1) != 1 or W.dtype != torch.float32 or not W.is_cuda:
         return None
     L = _lib.lib()
@@ -201,20 +208,24 @@ def _tc_weight_images(W: torch.Tensor):
     n = L.mgb_linear_tc_packed_floats(fin, fout)
     if n == 0:
         return None
-    owner = W._base if W._base is not None else W
+    if owner is None:
+        owner = W._base if W._base is not None else W
     cache = owner.__dict__.setdefault("_mgb_tc_images", {})
     prec = 2 if _precision == "bf16" else _LINEAR_TC_PRECISION
     key = (W.storage_offset(), fout, fin, W.stride(0), owner.data_ptr(), prec, torch.cuda.current_stream().cuda_stream)
     hit = cache.get(key)
-    if hit is not None and hit[0] == owner._version:
+    version = _lib.ver(owner)
+    if hit is not None and hit[0] == version:
         return hit[1]
     packed = torch.empty(n, dtype=torch.float32, device=W.device)
     Wd = W.detach()
-    _lib.check(L.mgb_linear_tc_pack(_lib.ptr(Wd), Wd.stride(0), fin, fout, prec, _lib.ptr(packed), _lib.stream()), "linear_tc_pack")
-    cache[key] = (owner._version, packed)
+    with _lib.on(W):
+        _lib.check(L.mgb_linear_tc_pack(_lib.ptr(Wd), Wd.stride(0), fin, fout, prec, _lib.ptr(packed), _lib.stream()), "linear_tc_pack")
+    cache[key] = (version, packed)
     return packed
 
 
+@_lib.guard
 def mlp_chain(x, linears, act: str = "relu", in_act: str = "none", cache_owner=None):
     """Inference forward of ``linears`` (nn.Linear modules: Linear(128,128) + act ... Linear(128, out <= 128)) in one launch
     (mgb_mlp_chain_fwd): the activations never leave the SM between the layers.  Returns None when the shapes or the
@@ -228,7 +239,7 @@ def mlp_chain(x, linears, act: str = "relu", in_act: str = "none", cache_owner=N
         return None
     L = _lib.lib()
     nl = len(linears)
-    key = tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version) for l in linears) + \
+    key = tuple((l.weight.data_ptr(), _lib.ver(l.weight), l.bias.data_ptr(), _lib.ver(l.bias)) for l in linears) + \
         (torch.cuda.current_stream().cuda_stream,)
     store = cache_owner.__dict__ if cache_owner is not None else None
     hit = store.get("_mgb_chain") if store is not None else None
@@ -253,14 +264,16 @@ def mlp_chain(x, linears, act: str = "relu", in_act: str = "none", cache_owner=N
     return y.reshape(*shape[:-1], n_out)
 
 
-def linear_act(x, W, b, act: str = "none", residual=None):
-    packed = _tc_weight_images(W)
+def linear_act(x, W, b, act: str = "none", residual=None, owner=None):
+    """``owner``: the nn.Parameter ``W`` is a column slice of (keeps the weight-image cache valid under inference_mode)."""
+    packed = _tc_weight_images(W, owner)
     if not torch.is_grad_enabled() or not (x.requires_grad or W.requires_grad or b.requires_grad or
                                            (residual is not None and residual.requires_grad)):
         return _linear_forward(x, W, b, ACT[act], residual, packed, False)[0]      # rollout / decode: no autograd node
     return LinearActFn.apply(x, W, b, ACT[act], residual, packed)
 
 
+@_lib.guard
 def _layernorm_forward(x, gamma, beta):
     _lib.require_cuda(x, gamma)
     L = _lib.lib()
@@ -311,6 +324,7 @@ def layer_norm(x, gamma, beta):
     return LayerNormFn.apply(x, gamma, beta)
 
 
+@_lib.guard
 def instance_norm(x: torch.Tensor, seg: GraphSegments) -> torch.Tensor:
     """Forward-only PyG InstanceNorm (tests / inference helper)."""
     L = _lib.lib()
@@ -326,6 +340,7 @@ def instance_norm(x: torch.Tensor, seg: GraphSegments) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # InteractionNetwork glue (models/magnet_gnn.py:70-90) and the INR decoder (:224-283)
 # --------------------------------------------------------------------------------------------
+@_lib.guard
 def _segment_sum(rows, cols, rowptr, idx, n_nodes, mean, out=None, ld_out=None):
     L = _lib.lib()
     if out is None:
@@ -341,12 +356,16 @@ class EdgeCombineFn(torch.autograd.Function):
     applied to cat([x_i, x_j, e_features]) (models/magnet_gnn.py:79-82)."""
 
     @staticmethod
+    @_lib.guard
     def run(p, q, r, edge_index, act: int):
         _lib.require_cuda(p, q, r, edge_index)
         L = _lib.lib()
         p, q, r = _lib.f32c(p), _lib.f32c(q), _lib.f32c(r)
         ei = edge_index.contiguous()
         E = ei.shape[1]
+        if p.shape[1] != 128 or q.shape != p.shape or r.shape != (E, 128):
+            raise RuntimeError("edge_combine kernels are built for hidden width 128: got p "
+                               f"{tuple(p.shape)}, q {tuple(q.shape)}, r {tuple(r.shape)} for {E} edges")
         out = _empty((E, 128), p)
         _lib.check(L.mgb_edge_combine_fwd(_lib.ptr(p), _lib.ptr(q), _lib.ptr(r), _lib.ptr(ei), E, act, _lib.ptr(out),
                                           _lib.stream()), "edge_combine_fwd")
@@ -408,9 +427,82 @@ class ScatterMeanFn(torch.autograd.Function):
 
 
 def scatter_mean(m, edge_index, plan):
+    if m.shape[-1] != 128 or m.shape[0] != plan.n_edges:
+        raise RuntimeError(f"scatter_mean kernels are built for [E, 128] messages; got {tuple(m.shape)} for {plan.n_edges} edges")
     if _no_grad_needed(m):
         return _segment_sum(_lib.f32c(m), 128, plan.rowptr, plan.perm, plan.n_nodes, True)
     return ScatterMeanFn.apply(m, edge_index, plan)
+
+
+# --------------------------------------------------------------------------------------------
+# fused InteractionNetwork edge function (csrc/in_edge_tc.cu): gather + edge_fn MLP + LayerNorm + mean in one launch
+# --------------------------------------------------------------------------------------------
+def params_key(params):
+    """Cache key for kernel-side copies of parameters: storage identity + version counters + arithmetic + stream."""
+    return tuple((p.data_ptr(), _lib.ver(p)) for p in params) + (_precision, _linear_tc, torch.cuda.current_stream().cuda_stream)
+
+
+def in_edge_fusable(x, e_features, linears) -> bool:
+    """The fused kernel covers the reference configuration (hidden 128, mlp_layers 4) on the tensor-core arithmetic,
+    forward only (rollout / decode: nothing requires a gradient)."""
+    return (_linear_tc and _precision != "fp32" and x.is_cuda and x.dtype == torch.float32 and e_features.dtype == torch.float32
+            and x.dim() == 2 and x.shape[1] == 128 and e_features.dim() == 2 and e_features.shape[1] == 128 and len(linears) == 5
+            and linears[0].in_features == 384 and all(l.out_features == 128 for l in linears)
+            and all(l.in_features == 128 for l in linears[1:])
+            and _no_grad_needed(x, e_features, *[p for l in linears for p in (l.weight, l.bias)]))
+
+
+@_lib.guard
+def in_edge_pack(x_like, linears, norm):
+    """Kernel-side copies for in_edge_fused: (pq weight images, pq bias, packed edge_fn images + biases + LayerNorm affine)."""
+    L = _lib.lib()
+    dev = x_like.device
+    lin_prec = 2 if _precision == "bf16" else _LINEAR_TC_PRECISION
+    W0 = linears[0].weight.detach()
+    if W0.stride(1) != 1:
+        W0 = W0.contiguous()
+    b0 = linears[0].bias.detach()
+    w_pq = torch.cat([W0[:, :128], W0[:, 128:256]], dim=0).contiguous()                  # [256, 128]: rows of P, then of Q
+    b_pq = torch.cat([b0, torch.zeros_like(b0)]).contiguous()
+    pq_img = torch.empty(L.mgb_linear_tc_packed_floats(128, 256), dtype=torch.float32, device=dev)
+    _lib.check(L.mgb_linear_tc_pack(_lib.ptr(w_pq), 128, 128, 256, lin_prec, _lib.ptr(pq_img), _lib.stream()), "linear_tc_pack")
+    packed = torch.empty(L.mgb_in_edge_packed_floats(), dtype=torch.float32, device=dev)
+    eprec = 2 if _precision == "bf16" else 3
+    _lib.check(L.mgb_in_edge_pack_layer(ctypes_offset(W0, 256), W0.stride(0), None, 0, eprec, _lib.ptr(packed), _lib.stream()),
+               "in_edge_pack_layer")
+    for i, l in enumerate(linears[1:], start=1):
+        W = l.weight.detach().contiguous()
+        b = l.bias.detach().contiguous()
+        _lib.check(L.mgb_in_edge_pack_layer(_lib.ptr(W), 128, _lib.ptr(b), i, eprec, _lib.ptr(packed), _lib.stream()),
+                   "in_edge_pack_layer")
+    g, bt = norm.weight.detach().contiguous(), norm.bias.detach().contiguous()
+    _lib.check(L.mgb_in_edge_pack_norm(_lib.ptr(g), _lib.ptr(bt), _lib.ptr(packed), _lib.stream()), "in_edge_pack_norm")
+    return pq_img, b_pq, packed
+
+
+@_lib.guard
+def in_edge_fused(x, e_features, e_scale: float, plan: AggregationPlan, packs):
+    """agg [N,128] = mean over edge_index[1] of LayerNorm(edge_fn(cat[x_i, x_j, e_scale * e_features])) — one node-level
+    Linear for P | Q plus ONE fused edge launch (mgb_in_edge_fwd); no [E,128] intermediate exists."""
+    _lib.require_cuda(x, e_features)
+    L = _lib.lib()
+    pq_img, b_pq, packed = packs
+    x = _lib.f32c(x)
+    e = _lib.f32c(e_features)
+    N, E = x.shape[0], plan.n_edges
+    if plan.n_nodes != N or e.shape[0] != E:
+        raise RuntimeError(f"in_edge_fused: plan is for {plan.n_nodes} nodes / {plan.n_edges} edges, got x {tuple(x.shape)}, "
+                           f"e_features {tuple(e.shape)}")
+    lin_prec = 2 if _precision == "bf16" else _LINEAR_TC_PRECISION
+    pq = _empty((N, 256), x)
+    _lib.check(L.mgb_linear_tc_fwd(_lib.ptr(x), N, 128, 256, _lib.ptr(pq_img), _lib.ptr(b_pq), 0, None, _lib.ptr(pq), None,
+                                   lin_prec, _lib.stream()), "linear_tc_fwd")
+    agg = _empty((N, 128), x)
+    ws = _lib.workspace(L.mgb_in_edge_fwd_workspace(E), x.device)
+    _lib.check(L.mgb_in_edge_fwd(_lib.ptr(e), float(e_scale), _lib.ptr(plan.perm), _lib.ptr(pq), _lib.ptr(plan.rowptr),
+                                 _lib.ptr(plan.dst), _lib.ptr(plan.src), N, E, _lib.ptr(packed), 2 if _precision == "bf16" else 3,
+                                 _lib.ptr(agg), _lib.ptr(ws), ws.numel(), _lib.stream()), "in_edge_fwd")
+    return agg
 
 
 INTERP = {"area": 0, "knn": 1, "sph": 2}
@@ -428,6 +520,9 @@ class InrBlendFn(torch.autograd.Function):
         a, xlr, lr_coords, hr_coords, t = (_lib.f32c(v) for v in (a, xlr, lr_coords, hr_coords, t))
         wpc = _lib.f32c(wp.detach())
         Q, k = idx.shape
+        if a.shape[1] != 128 or wpc.shape != (128, 128 + d + 2):
+            raise RuntimeError("inr_decode kernels are built for latent_dim = n_chan = 128: got a "
+                               f"{tuple(a.shape)}, proj_head.weight {tuple(wpc.shape)} (d = {d})")
         z = _empty((Q, T, 128), a)
         ldw = wpc.shape[1]
         wsmall = ctypes_offset(wpc, 128)
@@ -471,6 +566,7 @@ def ctypes_offset(t: torch.Tensor, n_elems: int):
     return ctypes.c_void_p(t.data_ptr() + n_elems * t.element_size())
 
 
+@_lib.guard
 def inr_decode(xlr, lr_encoded, lr_coords, hr_coords, t, wp, bp, B, L_, nq, k, interpolation, *, idx=None):
     """continuous_decoder (models/magnet_gnn.py:224-283): xlr [B,T,L], lr_encoded [B*L,C], lr_coords [B*L,d],
     hr_coords [B*nq,d], t [B,>=T] -> z [B*nq, T, n_chan]."""
@@ -481,5 +577,8 @@ def inr_decode(xlr, lr_encoded, lr_coords, hr_coords, t, wp, bp, B, L_, nq, k, i
         ptr_x = MG.uniform_ptr(B, L_, xlr.device)
         ptr_y = MG.uniform_ptr(B, nq, xlr.device)
         idx = MG.knn_indices(lr_coords, hr_coords, k, ptr_x, ptr_y)
-    a = linear_act(lr_encoded, wp[:, :128], bp, "none")
+    if lr_encoded.shape[-1] != 128 or wp.shape != (128, 128 + d + 2):
+        raise RuntimeError("inr_decode kernels are built for latent_dim = n_chan = 128: got lr_encoded "
+                           f"{tuple(lr_encoded.shape)}, proj_head.weight {tuple(wp.shape)} (d = {d})")
+    a = linear_act(lr_encoded, wp[:, :128], bp, "none", owner=wp)
     return InrBlendFn.apply(a, xlr, wp, lr_coords, hr_coords, t, idx, (nq, L_, T, d, INTERP[interpolation]))

@@ -168,7 +168,7 @@ def build_plan(edge_index: torch.Tensor, n_nodes: int) -> AggregationPlan:
 
 
 def plan_for(edge_index: torch.Tensor, n_nodes: int) -> AggregationPlan:
-    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), int(n_nodes), edge_index.device.index)
+    key = (edge_index.data_ptr(), _lib.ver(edge_index), tuple(edge_index.shape), int(n_nodes), edge_index.device.index)
     hit = _PLAN_CACHE.get(key)
     if hit is not None and hit[0]() is edge_index:
         _PLAN_CACHE.move_to_end(key)
@@ -195,7 +195,7 @@ _SEG_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 def segments_for(batch: torch.Tensor, n_nodes: int) -> GraphSegments:
     """Cached conversion of a sorted `batch` vector (models/mpnn_2d.py:237,249) to offsets."""
     import weakref
-    key = (batch.data_ptr(), batch._version, batch.numel(), batch.device.index)
+    key = (batch.data_ptr(), _lib.ver(batch), batch.numel(), batch.device.index)
     hit = _SEG_CACHE.get(key)
     if hit is not None and hit[0]() is batch:
         _SEG_CACHE.move_to_end(key)

@@ -15,6 +15,7 @@ from torch import nn
 
 from . import functional as MF
 from . import graph as MG
+from . import _lib
 from ._compat import LightningModule
 
 _ACT = {"relu": nn.ReLU(), "tanh": nn.Tanh(), "gelu": nn.GELU()}
@@ -99,22 +100,39 @@ class InteractionNetwork(nn.Module):
         self.edge_fn = nn.Sequential(MLP(node_in + node_in + edge_in, [mlp_hidden] * mlp_layers, edge_out),
                                      nn.LayerNorm(edge_out))
 
-    def forward(self, x, edge_index, e_features, *, plan=None):
+    def forward(self, x, edge_index, e_features, *, plan=None, e_scale: float = 1.0, return_e: bool = True):
+        """``e_scale`` / ``return_e`` (keyword-only, used by Processor): the reference hands every layer 2x the edge features
+        of the previous one and never updates them (quirk F3), so a stack passes e_0 with e_scale = 2^l instead of
+        materialising the doubled tensor per layer."""
         n = x.shape[0]
         if plan is None:
             plan = MG.plan_for(edge_index, n)
         h = self.node_in
-        first = self.edge_fn[0].layers[0]
-        W, b = first.weight, first.bias
-        # first Linear factorised over its three inputs: W [x_i, x_j, e] = P[dst] + Q[src] + R
-        p = MF.linear_act(x, W[:, :h], b, "none")
-        q = MF.linear_act(x, W[:, h:2 * h], torch.zeros_like(b), "none")
-        r = MF.linear_act(e_features, W[:, 2 * h:], torch.zeros_like(b), "none")
-        h0 = MF.edge_combine(p, q, r, edge_index, plan, "relu")      # ReLU of the first Linear, fused into the gather
-        m = _mlp_ln(self.edge_fn, None, first_preact=h0)
-        agg = MF.scatter_mean(m, edge_index, plan)
+        lin = self.edge_fn[0].linears()
+        if MF.in_edge_fusable(x, e_features, lin) and self.edge_fn[0].activation == "relu":
+            # rollout / decode: P | Q per node + ONE fused edge launch (gather, 5-layer MLP, LayerNorm, mean)
+            params = [p for l in lin for p in (l.weight, l.bias)] + [self.edge_fn[1].weight, self.edge_fn[1].bias]
+            key = MF.params_key(params)
+            if getattr(self, "_fused_key", None) != key:
+                self._fused_packs = MF.in_edge_pack(x, lin, self.edge_fn[1])
+                self._fused_key = key
+            agg = MF.in_edge_fused(x, e_features, e_scale, plan, self._fused_packs)
+        else:
+            first = lin[0]
+            W, b = first.weight, first.bias
+            e_in = e_features if e_scale == 1.0 else e_features * e_scale
+            # first Linear factorised over its three inputs: W [x_i, x_j, e] = P[dst] + Q[src] + R
+            p = MF.linear_act(x, W[:, :h], b, "none", owner=W)
+            q = MF.linear_act(x, W[:, h:2 * h], torch.zeros_like(b), "none", owner=W)
+            r = MF.linear_act(e_in, W[:, 2 * h:], torch.zeros_like(b), "none", owner=W)
+            h0 = MF.edge_combine(p, q, r, edge_index, plan, "relu")      # ReLU of the first Linear, fused into the gather
+            m = _mlp_ln(self.edge_fn, None, first_preact=h0)
+            agg = MF.scatter_mean(m, edge_index, plan)
         x_new = _mlp_ln(self.node_fn, torch.cat([agg, x], dim=-1))
-        return x_new + x, e_features + e_features
+        if not return_e:
+            return x_new + x, None
+        e_out = e_features + e_features if e_scale == 1.0 else e_features * (2.0 * e_scale)
+        return x_new + x, e_out
 
 
 class Processor(nn.Module):
@@ -126,12 +144,14 @@ class Processor(nn.Module):
             InteractionNetwork(node_in, node_out, edge_in, edge_out, mlp_num_layers, mlp_hidden_dim)
             for _ in range(num_message_passing_steps)])
 
-    def forward(self, x, edge_index, e_features, *, plan=None):
+    def forward(self, x, edge_index, e_features, *, plan=None, need_e: bool = True):
         if plan is None:
             plan = MG.plan_for(edge_index, x.shape[0])
+        scale = 1.0
         for gnn in self.gnn_stacks:
-            x, e_features = gnn(x, edge_index, e_features, plan=plan)
-        return x, e_features
+            x, _ = gnn(x, edge_index, e_features, plan=plan, e_scale=scale, return_e=False)
+            scale *= 2.0           # exact in fp32: 2^l e_0 is bit-identical to l doublings
+        return x, (e_features * scale if need_e else None)
 
 
 class Decoder(nn.Module):
@@ -176,6 +196,11 @@ class MAgNetGNN(LightningModule):
         except (AttributeError, KeyError):
             self.dim = 2
         d, ts, ld = self.dim, self.time_slice, self.latent_dim
+        if not (self.latent_dim == self.mlp_hidden == self.n_chan == 128):
+            raise RuntimeError("magnet_b200 kernels are built for latent_dim = mlp_hidden = n_chan = 128 (every reference "
+                               f"config); got {self.latent_dim}, {self.mlp_hidden}, {self.n_chan}")
+        if d not in (1, 2):
+            raise RuntimeError(f"magnet_b200 supports 1-D and 2-D meshes (hparams.dim), got {d}")
         self.criterion = {"l1": nn.L1Loss(), "l2": nn.MSELoss(), "smooth_l1": nn.SmoothL1Loss()}[self.loss]
         self.mse_criterion = nn.MSELoss()
         self.mae_criterion = nn.L1Loss()
@@ -196,7 +221,7 @@ class MAgNetGNN(LightningModule):
     # ---- graph -------------------------------------------------------------------------
     def _edges(self, x_flat: torch.Tensor, key_tensor: torch.Tensor, B: int, N: int):
         """radius graph (r = hparams.radius, loop=True) + plan, cached on the coordinate tensor."""
-        key = (key_tensor.data_ptr(), key_tensor._version, tuple(key_tensor.shape), B, N, float(self.radius))
+        key = (key_tensor.data_ptr(), _lib.ver(key_tensor), tuple(key_tensor.shape), B, N, float(self.radius))
         hit = self._graph_cache.get(key)
         if hit is not None and hit[0]() is key_tensor:
             return hit[1]
@@ -239,7 +264,7 @@ class MAgNetGNN(LightningModule):
         u = x_lr.permute(0, 3, 1, 2).reshape(B, L, -1)
         nf, ei, ef, plan = self._build_graph(u, lr_coords, t[:, :T], return_plan=True)
         nf, ef = self.encoder(nf, ei, ef)
-        lr_encoded, _ = self.processor(nf, ei, ef, plan=plan)
+        lr_encoded, _ = self.processor(nf, ei, ef, plan=plan, need_e=False)
 
         z = self.continuous_decoder(x_lr, lr_encoded, lr_coords, hr_coords, t)
         hr_points = self.projector(z).reshape(B, N, -1)
@@ -248,7 +273,7 @@ class MAgNetGNN(LightningModule):
         all_feats = torch.cat([u, hr_points], dim=1)
         nf, ei, ef, plan = self._build_graph(all_feats, all_coords, t[:, :T], return_plan=True)
         nf, ef = self._encoder(nf, ei, ef)
-        nf, _ = self._processor(nf, ei, ef, plan=plan)
+        nf, _ = self._processor(nf, ei, ef, plan=plan, need_e=False)
         ret = self._decoder(nf).reshape(B, L + N, -1)
 
         last_values = torch.cat([x_lr[:, -1].permute(0, 2, 1), hr_last], dim=1)            # [B, L+N, 1]
@@ -259,7 +284,7 @@ class MAgNetGNN(LightningModule):
 
     def _all_coords(self, lr_coords, hr_coords):
         """cat([lr, hr]) cached on the input tensors so the stage-3 graph is built once per mesh."""
-        key = (lr_coords.data_ptr(), lr_coords._version, hr_coords.data_ptr(), hr_coords._version)
+        key = (lr_coords.data_ptr(), _lib.ver(lr_coords), hr_coords.data_ptr(), _lib.ver(hr_coords))
         hit = getattr(self, "_coords_cache", None)
         if hit is not None and hit[0] == key and hit[1]() is lr_coords and hit[2]() is hr_coords:
             return hit[3]

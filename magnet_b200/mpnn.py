@@ -16,6 +16,7 @@ import torch.nn.functional as F
 
 from . import functional as MF
 from . import graph as MG
+from . import _lib
 from ._compat import Data, LightningModule
 
 
@@ -66,7 +67,7 @@ class GNN_Layer(nn.Module):
         # (optimizer steps and load_state_dict bump the version counters); the module keeps its parameters alive, so
         # (data_ptr, version) identifies their contents
         ws = (m1.weight, m1.bias, m2.weight, u1.weight, u2.weight)
-        key = tuple((w.data_ptr(), w._version) for w in ws) + (u.shape[1], pos.shape[1], variables.shape[1],
+        key = tuple((w.data_ptr(), _lib.ver(w)) for w in ws) + (u.shape[1], pos.shape[1], variables.shape[1],
                                                                torch.cuda.current_stream().cuda_stream)
         if self._pack_key != key:
             f32 = [w.detach().float().contiguous() for w in ws]
@@ -133,7 +134,7 @@ class _MPNNBase(LightningModule):
 
     def _mesh_graph(self, x: torch.Tensor, B: int, nx: int):
         """edge_index / batch / positions for B copies of sample 0's mesh (models/mpnn_2d.py:235), cached."""
-        key = (x.data_ptr(), x._version, tuple(x.shape), B, self.n)
+        key = (x.data_ptr(), _lib.ver(x), tuple(x.shape), B, self.n)
         hit = self._graph_cache.get(key)
         if hit is not None and hit[0]() is x:      # same tensor object, unmodified: same mesh
             return hit[1]
