@@ -8,8 +8,9 @@
 //   producers   gather e_features rows through the aggregation plan (position -> COO edge id), scale by 2^l (the
 //               reference doubles e_features every layer and never updates them), split into fp16 hi | lo and
 //               write a K-major operand image (as mlp_chain_tc.cu)
-//   layer 0     D^T[n][e] = sum_k We[n][k] e[e][k];  epilogue (thread = channel n) adds P[dst_e][n] + Q[src_e][n], ReLU,
-//               writes the next operand IN PLACE as an MN-major image
+//               and initialise the accumulator with P[dst_e][n] + Q[src_e][n] (tcgen05.st, thread = channel n)
+//   layer 0     D^T[n][e] += sum_k We[n][k] e[e][k];  epilogue (thread = channel n): ReLU, next operand written IN PLACE
+//               as an MN-major image
 //   layers 1-3  as mlp_chain_tc.cu (bias, ReLU, MN-major image)
 //   layer 4     y = D + b4;  LayerNorm over the 128 channels of an edge = across the 128 epilogue threads: y goes through
 //               the (now free) operand tile as an fp32 [e][n] staging buffer, two threads per edge compute mean / rstd
@@ -54,6 +55,16 @@ struct InEdgeArgs {
     int* range_flag;
 };
 
+#ifdef MGB_TIMELINE
+__device__ long long* g_ie_timeline = nullptr;      // [role 0..3][pair 0..3][layer 0..4][tile 0..1][event 0..3]
+#define IETL(role, it_, l_, t_, ev) do { if (blockIdx.x == 0 && (it_) < 4 && (threadIdx.x & 31) == 0 && g_ie_timeline) g_ie_timeline[((((role) * 4 + (it_)) * 5 + (l_)) * 2 + (t_)) * 4 + (ev)] = clock64(); } while (0)
+int set_ie_timeline_buffer(long long* p) {
+    return cudaMemcpyToSymbol(g_ie_timeline, &p, sizeof(p)) == cudaSuccess ? MGB_OK : MGB_ERR_CUDA;
+}
+#else
+#define IETL(role, it_, l_, t_, ev) do { } while (0)
+#endif
+
 template <int NSPLIT>
 __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InEdgeArgs a) {
     extern __shared__ unsigned char smem_raw[];
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
         umma::mbar_init(w_free, 1);
         umma::fence_barrier_init();
     }
-    if (warp == IE_MMA_WARP) umma::tmem_alloc(tmem_slot, 256);
+    if (warp == IE_MMA_WARP) umma::tmem_alloc(tmem_slot, 512);      // 4 accumulators: (pair parity, tile of the pair)
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
@@ -105,7 +116,6 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
         const int n = tid & 127, hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float gamma = a.gamma[n], beta = a.beta[n];
-        const float* pqn = a.pq + n;
         uint32_t tf[2] = {0, 0};        // completed phases of t_full[t]
 #pragma unroll 1
         for (int it = 0; it < np; ++it) {
@@ -120,107 +130,56 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                     const IeMeta* M = metas + slot;
                     unsigned char* xt = x_img + (size_t)t * 2 * TILE_BYTES;
                     unsigned char* xrow = xt + n * 128;
-                    const uint32_t tacc = tmem + (uint32_t)(t * 128) + lane_base + (uint32_t)(hf * 64);
-                    if (l == 0) {
-                        // ---- layer 0: + P[dst] + Q[src], ReLU.  The Q values of the first 32 positions are requested before
-                        // the accumulator is waited for; P changes only at segment starts (warp-uniform branch).
-                        umma::mbar_wait(&m_full[slot], (it >> 1) & 1);
-                        float qv[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) qv[i] = pqn[M->qoff[hf * 64 + i]];
-                        umma::mbar_wait(&t_full[t], tf[t] & 1);
-                        ++tf[t];
-                        umma::tc_fence_after();
-                        int dprev = -2;
-                        float pv = 0.f;
-#pragma unroll 1
-                        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                            for (int cc = 0; cc < 4; ++cc) {
-                                const int c0 = hf * 64 + h * 32 + cc * 8;
-                                float v[8];
-                                umma::tmem_ld8(tacc + (uint32_t)(h * 32 + cc * 8), v);
-                                const int4 d0 = *reinterpret_cast<const int4*>(&M->dst[c0]);
-                                const int4 d1 = *reinterpret_cast<const int4*>(&M->dst[c0 + 4]);
-                                const int dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    if (dd[i] != dprev) {
-                                        dprev = dd[i];
-                                        pv = dd[i] >= 0 ? pqn[(int64_t)dd[i] * 256] : 0.f;
-                                    }
-                                    v[i] = dd[i] >= 0 ? fmaxf(v[i] + pv + qv[cc * 8 + i], 0.f) : 0.f;
-                                }
-                                if (NSPLIT == 2 &&
-                                    fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))) >= 32768.f &&
-                                    a.range_flag)
-                                    *a.range_flag = 1;
-                                const uint32_t off = (uint32_t)(c0 >> 6) * (128u * 128u) + (uint32_t)((((c0 & 63) >> 3) ^ (n & 7)) << 4);
-                                uint4 hi, lo;
-                                if (NSPLIT == 2) {
-                                    split2_f16(v[0], v[1], hi.x, lo.x);
-                                    split2_f16(v[2], v[3], hi.y, lo.y);
-                                    split2_f16(v[4], v[5], hi.z, lo.z);
-                                    split2_f16(v[6], v[7], hi.w, lo.w);
-                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
-                                    *reinterpret_cast<uint4*>(xrow + TILE_BYTES + off) = lo;
-                                } else {
-                                    hi.x = umma::pack_bf16(v[0], v[1]);
-                                    hi.y = umma::pack_bf16(v[2], v[3]);
-                                    hi.z = umma::pack_bf16(v[4], v[5]);
-                                    hi.w = umma::pack_bf16(v[6], v[7]);
-                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
-                                }
-                            }
-                            if (h == 0) {
-#pragma unroll
-                                for (int i = 0; i < 32; ++i) qv[i] = pqn[M->qoff[hf * 64 + 32 + i]];
-                            }
-                        }
-                        umma::fence_async_smem();
-                        umma::tc_fence_before();
-                        umma::mbar_arrive(&x_ready[t]);
-                        continue;
-                    }
+                    const uint32_t tacc = tmem + (uint32_t)(slot * 128) + lane_base + (uint32_t)(hf * 64);
                     umma::mbar_wait(&t_full[t], tf[t] & 1);
                     ++tf[t];
                     umma::tc_fence_after();
+                    if (warp == 0 || warp == 4) IETL(1 + hf, it, l, t, 0);
                     if (l < IE_L - 1) {
-                        // ---- hidden layers: bias, ReLU, next operand in place (MN-major image [n][e])
+                        // ---- layers 0-3: bias, ReLU, next operand in place (MN-major image [n][e]); layer 0's accumulator was
+                        // initialised with P[dst] + Q[src] by the producers (b0 is folded into P)
+                        float vmax = 0.f;
 #pragma unroll 1
-                        for (int cb = 0; cb < 64; cb += 8) {
+                        for (int cb = 0; cb < 64; cb += 16) {
                             const int c0 = hf * 64 + cb;
-                            float v[8];
-                            umma::tmem_ld8(tacc + (uint32_t)cb, v);
+                            float v[16];
+                            umma::tmem_ld16(tacc + (uint32_t)cb, v);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + bias, 0.f);
-                            if (NSPLIT == 2 &&
-                                fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]))) >= 32768.f &&
-                                a.range_flag)
-                                *a.range_flag = 1;
-                            const uint32_t off = (uint32_t)(c0 >> 6) * (128u * 128u) + (uint32_t)((((c0 & 63) >> 3) ^ (n & 7)) << 4);
-                            uint4 hi, lo;
+                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias, 0.f);
                             if (NSPLIT == 2) {
-                                split2_f16(v[0], v[1], hi.x, lo.x);
-                                split2_f16(v[2], v[3], hi.y, lo.y);
-                                split2_f16(v[4], v[5], hi.z, lo.z);
-                                split2_f16(v[6], v[7], hi.w, lo.w);
-                                *reinterpret_cast<uint4*>(xrow + off) = hi;
-                                *reinterpret_cast<uint4*>(xrow + TILE_BYTES + off) = lo;
-                            } else {
-                                hi.x = umma::pack_bf16(v[0], v[1]);
-                                hi.y = umma::pack_bf16(v[2], v[3]);
-                                hi.z = umma::pack_bf16(v[4], v[5]);
-                                hi.w = umma::pack_bf16(v[6], v[7]);
-                                *reinterpret_cast<uint4*>(xrow + off) = hi;
+#pragma unroll
+                                for (int i = 0; i < 16; i += 2) vmax = fmaxf(vmax, fmaxf(v[i], v[i + 1]));
+                            }
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const int cg = c0 + g * 8;
+                                const uint32_t off = (uint32_t)(cg >> 6) * (128u * 128u) + (uint32_t)((((cg & 63) >> 3) ^ (n & 7)) << 4);
+                                uint4 hi, lo;
+                                if (NSPLIT == 2) {
+                                    split2_f16(v[g * 8 + 0], v[g * 8 + 1], hi.x, lo.x);
+                                    split2_f16(v[g * 8 + 2], v[g * 8 + 3], hi.y, lo.y);
+                                    split2_f16(v[g * 8 + 4], v[g * 8 + 5], hi.z, lo.z);
+                                    split2_f16(v[g * 8 + 6], v[g * 8 + 7], hi.w, lo.w);
+                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
+                                    *reinterpret_cast<uint4*>(xrow + TILE_BYTES + off) = lo;
+                                } else {
+                                    hi.x = umma::pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                                    hi.y = umma::pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                                    hi.z = umma::pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                                    hi.w = umma::pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
+                                }
                             }
                         }
+                        if (NSPLIT == 2 && vmax >= 32768.f && a.range_flag) *a.range_flag = 1;
                         umma::fence_async_smem();
                         umma::tc_fence_before();
                         umma::mbar_arrive(&x_ready[t]);
+                        if (warp == 0 || warp == 4) IETL(1 + hf, it, l, t, 1);
                         continue;
                     }
                     // ---- last layer: y = D + b4 -> LayerNorm over channels -> segmented mean over positions
+                    umma::mbar_wait(&m_full[slot], (it >> 1) & 1);
                     // pass 1: y[n][e] -> staging [e][n] fp32 (16-byte chunks of a row permuted by the row index: every
                     // access pattern below is bank-conflict free).  The operand tile is free: all MMAs that read it are done.
 #pragma unroll 1
@@ -303,6 +262,7 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                     umma::tc_fence_before();
                     umma::mbar_arrive(&x_empty[t]);
                     umma::mbar_arrive(&m_empty[slot]);
+                    if (warp == 0 || warp == 4) IETL(1 + hf, it, l, t, 1);
                 }
             }
         }
@@ -323,16 +283,19 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
             for (int l = 0; l < IE_L; ++l) {
                 if (wl > 0) umma::mbar_wait(w_free, (wl - 1) & 1);          // the MMAs of the previous layer are done with w_img
                 if (lane == 0) load_w2_image(w_img, (const unsigned char*)a.wimg + (size_t)l * 2 * TILE_BYTES, NSPLIT * TILE_BYTES, w_bar);
+                IETL(0, it, l, 0, 3);
                 umma::mbar_wait(w_bar, wl & 1);
                 ++wl;
+                IETL(0, it, l, 0, 0);
 #pragma unroll 1
                 for (int t = 0; t < 2; ++t) {
                     if (pair * 2 + t >= n_tiles) continue;
                     if (l == 0) { umma::mbar_wait(&x_full[t], xf[t] & 1); ++xf[t]; }
                     else { umma::mbar_wait(&x_ready[t], xr[t] & 1); ++xr[t]; }
                     umma::tc_fence_after();
+                    IETL(0, it, l, t, 1);
                     if (umma::elect_one()) {
-                        const uint32_t d = tmem + (uint32_t)(t * 128);
+                        const uint32_t d = tmem + (uint32_t)(((it & 1) * 2 + t) * 128);
                         const uint64_t xd = (l == 0 ? xk_d : xm_d) + (uint64_t)((uint32_t)t * 2 * TB);
 #pragma unroll
                         for (int term = 0; term < (NSPLIT == 2 ? 3 : 1); ++term) {      // small terms first: lo*hi, hi*lo, hi*hi
@@ -341,12 +304,13 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                             for (int k = 0; k < 8; ++k) {
                                 const uint32_t koff_k = (uint32_t)((k >> 2) * (128 * 128 >> 4) + (k & 3) * 2), koff_m = (uint32_t)(k * 128);
                                 umma::mma_bf16(d, wa + (uint64_t)koff_k, xb + (uint64_t)(l == 0 ? koff_k : koff_m), l == 0 ? id_k : id_m,
-                                               (term | k) ? 1u : 0u);
+                                               (l == 0 || (term | k)) ? 1u : 0u);
                             }
                         }
                         umma::mma_commit(&t_full[t]);
                     }
                     __syncwarp();
+                    IETL(0, it, l, t, 2);
                 }
                 if (umma::elect_one()) umma::mma_commit(w_free);
                 __syncwarp();
@@ -361,27 +325,58 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
             for (int t = 0; t < 2; ++t) {
                 if (pair * 2 + t >= n_tiles) continue;
                 const int slot = (it & 1) * 2 + t;
-                umma::mbar_wait_relaxed(&m_empty[slot], ((it >> 1) & 1) ^ 1);
+                umma::mbar_wait_relaxed<1000>(&m_empty[slot], ((it >> 1) & 1) ^ 1);
                 build_tile_meta(metas + slot, a.rowptr, a.dstv, a.srcv, a.n_edges, pair * 2 + t, lane, a.agg, SEG_H, true, a.part_head,
                                 a.part_tail, IE_FLUSH);
                 umma::mbar_arrive(&m_full[slot]);
             }
         }
     } else {
-        // =========================== producers: 16 rows per warp (layer-0 operand) ==================
+        // =========================== producers: layer-0 operand + accumulator initialisation ========
+        // (a) 16 e_features rows per warp -> fp16 hi | lo K-major image (gathered and converted BEFORE the tile slot is
+        //     waited for);  (b) D^T[n][e] := P[dst_e][n] + Q[src_e][n] written straight into the accumulator with tcgen05.st
+        //     (thread = channel n of the warp's TMEM lane quadrant, 64 positions per warp), so that layer 0's MMAs add
+        //     We e on top and its epilogue is the plain bias-free ReLU — the gathers never sit on the epilogue's path.
         const int pw = warp - IE_PROD_WARP0;
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
         const float* src = a.e + lane * 4;
         const float sc = a.e_scale;
+        const int quad = warp & 3, chalf = pw >> 2;            // TMEM lane quadrant of this warp, its half of the positions
+        const float* pqn = a.pq + quad * 32 + lane;
         uint32_t xe[2] = {0, 0};
 #pragma unroll 1
         for (int it = 0; it < np; ++it) {
             const int64_t pair = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            // (b) first, for both tiles of the pair: their accumulators were drained two pairs ago, so they are initialised
+            // while the previous pair is still in flight — the gathers are off every critical path
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
                 const int64_t tile = pair * 2 + t;
                 if (tile >= n_tiles) continue;
+                const int64_t c0 = tile * IE_TE + chalf * 64;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t p = c0 + h * 32 + lane;
+                    // positions past the end of the edge list read node 0 (finite values in columns that belong to no segment);
+                    // no select behind the loads: all 32 stay in flight
+                    const uint32_t dl = p < a.n_edges ? (uint32_t)a.dstv[p] : 0u;
+                    const uint32_t sl = p < a.n_edges ? (uint32_t)a.srcv[p] : 0u;
+                    float acc[32], pv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = pqn[(size_t)__shfl_sync(0xffffffffu, sl, i) * 256 + 128];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) pv[i] = pqn[(size_t)__shfl_sync(0xffffffffu, dl, i) * 256];      // repeat along a segment: L1 hits
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] += pv[i];
+                    umma::tmem_st32(tmem + (uint32_t)(((it & 1) * 2 + t) * 128) + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 64 + h * 32), acc);
+                }
+            }
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const int64_t tile = pair * 2 + t;
+                if (tile >= n_tiles) continue;
+                // (a) e_features rows -> registers -> images once the tile slot is free
                 const int64_t p0 = tile * IE_TE + pw * 16;
                 int64_t mine = -1;
                 if (lane < 16 && p0 + lane < a.n_edges) mine = a.perm ? (int64_t)a.perm[p0 + lane] : p0 + lane;
@@ -406,8 +401,11 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                         hl[r].y = umma::pack_bf16(h.z, h.w);
                     }
                 }
-                umma::mbar_wait(&x_empty[t], (xe[t] & 1) ^ 1);
+                if (pw == 0) IETL(3, it, 0, t, 0);
+                umma::mbar_wait_relaxed<500>(&x_empty[t], (xe[t] & 1) ^ 1);
                 ++xe[t];
+                if (pw == 0) IETL(3, it, 0, t, 1);
+                umma::tc_fence_after();            // orders the NEXT tile's tcgen05.st behind the epilogue's accumulator reads
                 unsigned char* img = x_img + (size_t)t * 2 * TILE_BYTES;
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
@@ -416,13 +414,15 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                     if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = make_uint2(hl[r].z, hl[r].w);
                 }
                 umma::fence_async_smem();
+                umma::tc_fence_before();
                 umma::mbar_arrive(&x_full[t]);
+                if (pw == 0) IETL(3, it, 0, t, 2);
             }
         }
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == IE_MMA_WARP) umma::tmem_dealloc(tmem, 256);
+    if (warp == IE_MMA_WARP) umma::tmem_dealloc(tmem, 512);
 }
 
 size_t in_edge_fwd_workspace(int64_t n_edges) {

@@ -140,6 +140,7 @@ int launch_tail_dgrad(const float* dy, int lddy, int ny, const float* pre, int l
                       int wt_st, int kt, int64_t rows, float* out, int ldo, cudaStream_t s);
 #ifdef MGB_TIMELINE
 int set_timeline_buffer(long long* p);
+int set_ie_timeline_buffer(long long* p);
 #endif
 // mlp_chain_tc.cu (a whole 128-wide MLP in one launch, forward only)
 struct MlpChainArgs {

@@ -72,6 +72,49 @@ class FlatAdam(torch.optim.Optimizer):
             torch._C._increment_version(p)                      # (packed weight copies are keyed on the version counter)
         return loss
 
+    # ---- checkpoints: the layout of torch.optim.Adam (per-parameter "step" / "exp_avg" / "exp_avg_sq"), so that a
+    # Lightning checkpoint written with FlatAdam resumes under torch's Adam and vice versa.
+    # Semantics note: parameters that receive no gradient are updated as if their gradient were zero (the flat gradient
+    # buffer is zeroed, never None); torch's Adam skips such parameters entirely.  The two agree unless weight_decay != 0
+    # or the parameter still carries momentum from earlier steps.  Every parameter of the drop-in models receives a
+    # gradient in every training step.
+    def state_dict(self):
+        state = {}
+        for i, (p, o) in enumerate(zip(self._params, self._offs)):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.steps)),
+                        "exp_avg": self.exp_avg[o:o + n].view_as(p).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + n].view_as(p).clone()}
+        groups = []
+        for g in self.param_groups:
+            g2 = {k: v for k, v in g.items() if k != "params"}
+            g2["params"] = list(range(len(self._params)))
+            groups.append(g2)
+        return {"state": state, "param_groups": groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self._params):
+            raise ValueError("FlatAdam.load_state_dict: the checkpoint holds a different parameter list")
+        for k, v in groups[0].items():
+            if k != "params" and k in self.param_groups[0]:
+                self.param_groups[0][k] = v
+        state = state_dict["state"]
+        steps = 0
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, (p, o) in enumerate(zip(self._params, self._offs)):
+            st = state.get(i, state.get(str(i)))
+            if st is None:                      # torch's Adam has no state for a parameter that never received a gradient
+                continue
+            n = p.numel()
+            self.exp_avg[o:o + n].view_as(p).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + n].view_as(p).copy_(st["exp_avg_sq"])
+            steps = max(steps, int(float(st["step"])))
+        self.steps = steps
+        # the flat views of parameters / gradients stay as they are (load_state_dict of the MODULE copies into them)
+
 
 def allreduce_flat_gradient(opt: FlatAdam, world: int = None) -> float:
     """Sum the flat gradient buffer across ranks (one collective, no copies); returns the ``grad_scale`` to pass to

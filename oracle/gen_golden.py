@@ -184,8 +184,99 @@ def gen_magnet(ref):
     torch.save(out, os.path.join(OUT, "magnet_gnn.pt"))
 
 
+def _digest(t: torch.Tensor) -> str:
+    import hashlib
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+def _sub(t: torch.Tensor, dim: int, stride: int) -> torch.Tensor:
+    return t.index_select(dim, torch.arange(0, t.shape[dim], stride)).contiguous()
+
+
+def _reference_1d(ref):
+    """The checked-in reference model is 2-D only (`time_slice+3`, `time_slice+2`, `latent_dim+4`).  The 1-D
+    oracle is the SAME file with exactly these three widths parametrised (d = 1: +2, +1, +3), patched in memory — nothing
+    of the reference is copied into this repository."""
+    import types
+    path = os.path.join(rl.REFERENCE_ROOT, "models", "magnet_gnn.py")
+    src = open(path).read()
+    for old, new in (("node_in=self.time_slice+3", "node_in=self.time_slice+2"),
+                     ("edge_in=self.time_slice+2", "edge_in=self.time_slice+1"),
+                     ("nn.Linear(self.latent_dim+4, self.n_chan)", "nn.Linear(self.latent_dim+3, self.n_chan)")):
+        assert src.count(old) == 2 if "node_in" in old or "edge_in" in old else src.count(old) == 1, (old, src.count(old))
+        src = src.replace(old, new)
+    mod = types.ModuleType("models.magnet_gnn_1d")
+    mod.__file__ = path
+    exec(compile(src, path, "exec"), mod.__dict__)
+    return mod
+
+
+def gen_magnet_shapes(ref):
+    """MAgNet[GNN] at BASELINE's own shapes: C3 training shape (B=32, L=Nq=256, concentrated, r=0.08),
+    one test-resolution-256 sample (L=Nq=32,768), and C1 (1-D E1: nx=50 -> L=25, Nq=25, time_slice 25, batch 16).
+    Large tensors are stored as strided subsets plus SHA-256 digests / sums (fixtures stay small)."""
+    out = {}
+    hp = rl.magnet_gnn_hparams()
+    # ---- C3, training shape ---------------------------------------------------------------------------------------
+    m = ref.magnet_gnn.MAgNetGNN(hp).eval()
+    _load_seeded(m, 41)
+    b = S.implicit_batch(B=32, L=256, Nq=256, nt=50, d=2, kind="concentrated", seed=41)
+    inp, hr_last, tt = b["lr_frames"][:, :10], b["hr_points"][:, 9], b["t"][:, :20]
+    with torch.no_grad():
+        u = inp.permute(0, 3, 1, 2).reshape(32, 256, -1)
+        _, ei1, _ = m._build_graph(u, b["coords_lr"], tt[:, :10])
+        out_hr, out_lr, hr_points = m.forward(inp, b["coords_lr"], b["coords_hr"], tt, hr_last)
+        allc = torch.cat([b["coords_lr"], b["coords_hr"]], 1)
+        allf = torch.cat([u, hr_points.permute(0, 2, 1, 3).reshape(32, 256, -1)], 1)
+        _, ei3, _ = m._build_graph(allf, allc, tt[:, :10])
+        m.validation_step(b, 0)
+    out["c3_train"] = dict(seed=41, hparams=dict(hp), batch_args=dict(B=32, L=256, Nq=256, nt=50, d=2, kind="concentrated", seed=41),
+                           ei1_sha=_digest(ei1), ei1_edges=ei1.shape[1], ei3_sha=_digest(ei3), ei3_edges=ei3.shape[1],
+                           out_hr=out_hr, out_lr=out_lr, hr_points=hr_points, val_loss=m.logged["val_loss"],
+                           val_mae_loss=m.logged["val_mae_loss"])
+    print("c3_train", ei1.shape, ei3.shape, float(m.logged["val_loss"]))
+    # ---- C3, one sample at test resolution 256 (L = Nq = 32,768) -------------------------------------------------
+    b = S.implicit_batch(B=1, L=32768, Nq=32768, nt=20, d=2, kind="concentrated", seed=42)
+    inp, hr_last, tt = b["lr_frames"][:, :10], b["hr_points"][:, 9], b["t"][:, :20]
+    with torch.no_grad():
+        u = inp.permute(0, 3, 1, 2).reshape(1, 32768, -1)
+        _, ei1, _ = m._build_graph(u, b["coords_lr"], tt[:, :10])
+        out_hr, out_lr, hr_points = m.forward(inp, b["coords_lr"], b["coords_hr"], tt, hr_last)
+    out["c3_res256"] = dict(seed=41, hparams=dict(hp), batch_args=dict(B=1, L=32768, Nq=32768, nt=20, d=2, kind="concentrated", seed=42),
+                            ei1_sha=_digest(ei1), ei1_edges=ei1.shape[1], stride=16,
+                            out_hr=_sub(out_hr, 2, 16), out_lr=_sub(out_lr, 2, 16), hr_points=_sub(hr_points, 2, 16),
+                            sums={k: (float(v.double().sum()), float(v.double().abs().sum()), float(v.abs().max()))
+                                  for k, v in (("out_hr", out_hr), ("out_lr", out_lr), ("hr_points", hr_points))})
+    print("c3_res256", ei1.shape, out["c3_res256"]["sums"])
+    # ---- C1: 1-D E1 shape (reference file with the three hard-coded widths parametrised, F8) ----------------------
+    hp1 = rl.magnet_gnn_hparams(time_slice=25, radius=0.3)
+    ref1 = _reference_1d(ref)
+    m1 = ref1.MAgNetGNN(hp1).eval()
+    _load_seeded(m1, 43)
+    b1 = S.implicit_batch(B=16, L=25, Nq=25, nt=250, d=1, kind="uniform", seed=43)
+    inp, hr_last, tt = b1["lr_frames"][:, :25], b1["hr_points"][:, 24], b1["t"][:, :50]
+    with torch.no_grad():
+        u = inp.permute(0, 3, 1, 2).reshape(16, 25, -1)
+        nf, ei, ef = m1._build_graph(u, b1["coords_lr"], tt[:, :25])
+        out_hr, out_lr, hr_points = m1.forward(inp, b1["coords_lr"], b1["coords_hr"], tt, hr_last)
+        m1.validation_step(b1, 0)
+    out["c1_1d"] = dict(seed=43, hparams=dict(hp1, dim=1), batch_args=dict(B=16, L=25, Nq=25, nt=250, d=1, kind="uniform", seed=43),
+                        edge_index=ei, node_features=nf, edge_features=ef, out_hr=out_hr, out_lr=out_lr, hr_points=hr_points,
+                        val_loss=m1.logged["val_loss"])
+    m1.train()
+    loss = m1.training_step(b1, 0)
+    loss.backward()
+    out["c1_1d"]["train_loss"] = loss.detach()
+    out["c1_1d"]["grad_norms"] = {k: p.grad.norm() for k, p in m1.named_parameters()}
+    print("c1_1d", ei.shape, float(m1.logged["val_loss"]), float(loss))
+    torch.save(out, os.path.join(OUT, "magnet_shapes.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "shapes":
+        gen_magnet_shapes(rl.load())
+        return
     ref = rl.load()
     torch.manual_seed(0)
     gen_radius(ref)
@@ -193,6 +284,7 @@ def main():
     gen_gnn_layer(ref)
     gen_mpnn(ref)
     gen_magnet(ref)
+    gen_magnet_shapes(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -11,6 +11,7 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("MAGNET_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # bytecode of the same files (oracle/stage_ref.py)
 _STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "thirdparty")
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -19,20 +20,31 @@ def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "mpnn_2d.py"))
 
 
-def load():
-    """Returns a namespace with the reference modules: .mpnn, .mpnn_2d, .magnet_gnn, .mlp."""
-    if not available():
-        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
-    for p in (_REPO, _STUBS, REFERENCE_ROOT):
+def staged() -> bool:
+    """oracle/_ref/ holds the byte-compiled reference files (travels to the GPU box, where /root/reference does not exist)."""
+    return os.path.isfile(os.path.join(STAGED_ROOT, "models", "mpnn_2d.pyc"))
+
+
+def load(prefer_staged: bool = False):
+    """Returns a namespace with the reference modules: .mpnn, .mpnn_2d, .magnet_gnn, .mlp (+ .root, .kind).
+    Source tree when present (this container), else the staged bytecode of the very same files (GPU box)."""
+    if available() and not (prefer_staged and staged()):
+        root = REFERENCE_ROOT
+    elif staged():
+        root = STAGED_ROOT
+    else:
+        raise RuntimeError(f"reference not found: neither {REFERENCE_ROOT} nor staged bytecode under {STAGED_ROOT} "
+                           "(python -m oracle.stage_ref)")
+    for p in (_REPO, _STUBS, root):
         if p not in sys.path:
-            sys.path.insert(0, p) if p != REFERENCE_ROOT else sys.path.append(p)
-    ns = types.SimpleNamespace()
+            sys.path.insert(0, p) if p != root else sys.path.append(p)
+    ns = types.SimpleNamespace(root=root, kind="source" if root == REFERENCE_ROOT else "bytecode")
     ns.mlp = importlib.import_module("models.backbones.mlp")
     ns.mpnn = importlib.import_module("models.mpnn")
     ns.mpnn_2d = importlib.import_module("models.mpnn_2d")
     ns.magnet_gnn = importlib.import_module("models.magnet_gnn")
     for m in (ns.mpnn, ns.mpnn_2d, ns.magnet_gnn):
-        assert m.__file__.startswith(REFERENCE_ROOT), m.__file__
+        assert m.__file__.startswith(root), m.__file__
     return ns
 
 

@@ -331,3 +331,54 @@ def test_flat_adam_updates_reach_the_kernels():
         fresh.load_state_dict(layer.state_dict())
         y2 = fresh(x, u, pos, var, ei, batch)
     assert not torch.equal(y0, y1) and torch.equal(y1, y2)
+
+
+def test_flat_adam_checkpoint_interchanges_with_torch_adam():
+    """state_dict / load_state_dict use torch.optim.Adam's per-parameter layout: a run resumed from a
+    checkpoint continues bit-for-bit like the uninterrupted run, and a torch-Adam checkpoint loads into FlatAdam."""
+    from magnet_b200.optim import FlatAdam
+    g = S._gen(15)
+    shapes = [(128, 128), (128,), (9, 5), (3,)]
+    base = [torch.randn(sh, generator=g).to(DEV) for sh in shapes]
+    grads = [[torch.randn(sh, generator=g).to(DEV) for sh in shapes] for _ in range(6)]
+
+    def feed(opt, params, gs):
+        opt.zero_grad()
+        for p, gr in zip(params, gs):
+            if p.grad is None:
+                p.grad = gr.clone()
+            else:
+                p.grad += gr
+        opt.step()
+
+    pa = [torch.nn.Parameter(b.clone()) for b in base]
+    oa = FlatAdam(pa, lr=1e-3, weight_decay=1e-2)
+    for k in range(6):
+        feed(oa, pa, grads[k])
+    # interrupted run: 3 steps, checkpoint, fresh optimizer + parameters, 3 more steps
+    pb = [torch.nn.Parameter(b.clone()) for b in base]
+    ob = FlatAdam(pb, lr=1e-3, weight_decay=1e-2)
+    for k in range(3):
+        feed(ob, pb, grads[k])
+    ck_opt, ck_par = ob.state_dict(), [p.detach().clone() for p in pb]
+    assert set(ck_opt) == {"state", "param_groups"} and set(ck_opt["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+    pc = [torch.nn.Parameter(b.clone()) for b in ck_par]
+    oc = FlatAdam(pc, lr=1e-3, weight_decay=1e-2)
+    oc.load_state_dict(ck_opt)
+    for k in range(3, 6):
+        feed(oc, pc, grads[k])
+    for p, q in zip(pa, pc):
+        assert torch.equal(p, q)
+    # the same checkpoint drives torch's Adam to the same parameters (update rule parity is test_flat_adam_matches_torch_adam)
+    pd = [torch.nn.Parameter(b.clone()) for b in ck_par]
+    od = torch.optim.Adam(pd, lr=1e-3, weight_decay=1e-2)
+    od.load_state_dict(ck_opt)
+    for k in range(3, 6):
+        feed(od, pd, grads[k])
+    for p, q in zip(pa, pd):
+        assert rel_err(q, p) < 1e-6
+    # and torch's checkpoint loads into FlatAdam
+    pe = [torch.nn.Parameter(b.clone()) for b in ck_par]
+    oe = FlatAdam(pe, lr=1e-3, weight_decay=1e-2)
+    oe.load_state_dict(od.state_dict())
+    assert oe.steps == 6
