@@ -34,7 +34,7 @@ constexpr int IE_FLUSH = 64;                     // positions per epilogue warp 
 constexpr int IE_MSLOTS = 4;                     // metadata slots: (pair parity, tile of the pair)
 using IeMeta = TileMetaT<IE_TE>;
 constexpr size_t IN_EDGE_SMEM = 1024 + (size_t)2 * TILE_BYTES + (size_t)4 * TILE_BYTES + IE_MSLOTS * sizeof(IeMeta) +
-                                2 * IE_TE * sizeof(float2) + 256;
+                                4 * IE_TE * sizeof(float2) + 256;
 
 struct InEdgeArgs {
     const float* e;            // [E][128] edge features, COO order
@@ -55,6 +55,48 @@ struct InEdgeArgs {
     int* range_flag;
 };
 
+// Last-layer phase B for one thread (= channel n of TMEM lane quadrant n / 32) and the 64 positions [hf*64, hf*64+64) of a
+// tile: m = LayerNorm(y) from the accumulator (re-read) and the per-edge statistics, then the segmented mean over the
+// destination-sorted positions — one pass per stored sum, warp-uniform control flow, no atomics (segmeta.cuh).
+__device__ __forceinline__ void ie_norm_reduce(uint32_t tacc, const IeMeta* M, const float2* st, int hf, int n, float bias, float gamma,
+                                               float beta) {
+    float sum = 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < 64; cb += 8) {
+        const int c0 = hf * 64 + cb;
+        float v[8];
+        umma::tmem_ld8(tacc + (uint32_t)cb, v);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            const float4 mr = *reinterpret_cast<const float4*>(st + c0 + i);     // mean, rstd of two edges
+            v[i] = fmaf(((v[i] + bias) - mr.x) * mr.y, gamma, beta);
+            v[i + 1] = fmaf(((v[i + 1] + bias) - mr.z) * mr.w, gamma, beta);
+        }
+        uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 31)) & 0xffu, todo = 0xffu;
+        if (fm == 0) {                   // the common case: no stored sum ends inside the chunk
+            sum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+            continue;
+        }
+        while (fm) {
+            const uint32_t low = fm & (0u - fm);
+            const uint32_t upto = (low << 1) - 1u;
+            const uint32_t rng = todo & upto;
+            float part = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (rng & (1u << i)) part += v[i];
+            const int pos = c0 + (31 - __clz(low));
+            M->out[pos][n] = (sum + part) * M->scale[pos];
+            sum = 0.f;
+            todo &= ~upto;
+            fm &= fm - 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (todo & (1u << i)) sum += v[i];
+    }
+}
+
 #ifdef MGB_TIMELINE
 __device__ long long* g_ie_timeline = nullptr;      // [role 0..3][pair 0..3][layer 0..4][tile 0..1][event 0..3]
 #define IETL(role, it_, l_, t_, ev) do { if (blockIdx.x == 0 && (it_) < 4 && (threadIdx.x & 31) == 0 && g_ie_timeline) g_ie_timeline[((((role) * 4 + (it_)) * 5 + (l_)) * 2 + (t_)) * 4 + (ev)] = clock64(); } while (0)
@@ -73,10 +115,10 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
     unsigned char* w_img = base;                                        // [hi|lo] of the current layer
     unsigned char* x_img = base + (size_t)2 * TILE_BYTES;               // [tile 0|1][hi|lo]; fp32 staging in the last layer
     IeMeta* metas = reinterpret_cast<IeMeta*>(x_img + (size_t)4 * TILE_BYTES);
-    float2* stats = reinterpret_cast<float2*>(metas + IE_MSLOTS);       // [2][128] mean, rstd of every edge of a tile
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * IE_TE);
+    float2* stats = reinterpret_cast<float2*>(metas + IE_MSLOTS);       // [pair parity][tile][128] mean, rstd of every edge
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 4 * IE_TE);
     uint64_t* x_full = bars;          // [2] producers -> MMA (layer 0 operand written)
-    uint64_t* x_empty = bars + 2;     // [2] last-layer epilogue -> producers
+    // (the tile slots go back to the producers through hardware barriers 3 and 4: a waiting producer issues nothing)
     uint64_t* t_full = bars + 4;      // [2] MMA -> epilogue
     uint64_t* x_ready = bars + 6;     // [2] hidden-layer epilogue -> MMA
     uint64_t* w_bar = bars + 8;
@@ -93,7 +135,6 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
     if (tid == 0) {
         for (int t = 0; t < 2; ++t) {
             umma::mbar_init(&x_full[t], IE_PROD_WARPS * 32);
-            umma::mbar_init(&x_empty[t], IE_EPI_WARPS * 32);
             umma::mbar_init(&t_full[t], 1);
             umma::mbar_init(&x_ready[t], IE_EPI_WARPS * 32);
         }
@@ -121,149 +162,127 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
         for (int it = 0; it < np; ++it) {
             const int64_t pair = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
 #pragma unroll 1
-            for (int l = 0; l < IE_L; ++l) {
+            for (int l = 0; l < IE_L - 1; ++l) {
+                // ---- layers 0-3: bias, ReLU, next operand in place (MN-major image [n][e]); layer 0's accumulator was
+                // initialised with P[dst] + Q[src] by the producers (b0 is folded into P)
                 const float bias = l ? a.bias[l * 128 + n] : 0.f;
 #pragma unroll 1
                 for (int t = 0; t < 2; ++t) {
                     if (pair * 2 + t >= n_tiles) continue;
-                    const int slot = (it & 1) * 2 + t;
-                    const IeMeta* M = metas + slot;
-                    unsigned char* xt = x_img + (size_t)t * 2 * TILE_BYTES;
-                    unsigned char* xrow = xt + n * 128;
-                    const uint32_t tacc = tmem + (uint32_t)(slot * 128) + lane_base + (uint32_t)(hf * 64);
+                    unsigned char* xrow = x_img + (size_t)t * 2 * TILE_BYTES + n * 128;
+                    const uint32_t tacc = tmem + (uint32_t)(((it & 1) * 2 + t) * 128) + lane_base + (uint32_t)(hf * 64);
                     umma::mbar_wait(&t_full[t], tf[t] & 1);
                     ++tf[t];
                     umma::tc_fence_after();
                     if (warp == 0 || warp == 4) IETL(1 + hf, it, l, t, 0);
-                    if (l < IE_L - 1) {
-                        // ---- layers 0-3: bias, ReLU, next operand in place (MN-major image [n][e]); layer 0's accumulator was
-                        // initialised with P[dst] + Q[src] by the producers (b0 is folded into P)
-                        float vmax = 0.f;
+                    float vmax = 0.f;
 #pragma unroll 1
-                        for (int cb = 0; cb < 64; cb += 16) {
-                            const int c0 = hf * 64 + cb;
-                            float v[16];
-                            umma::tmem_ld16(tacc + (uint32_t)cb, v);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias, 0.f);
-                            if (NSPLIT == 2) {
-#pragma unroll
-                                for (int i = 0; i < 16; i += 2) vmax = fmaxf(vmax, fmaxf(v[i], v[i + 1]));
-                            }
-#pragma unroll
-                            for (int g = 0; g < 2; ++g) {
-                                const int cg = c0 + g * 8;
-                                const uint32_t off = (uint32_t)(cg >> 6) * (128u * 128u) + (uint32_t)((((cg & 63) >> 3) ^ (n & 7)) << 4);
-                                uint4 hi, lo;
-                                if (NSPLIT == 2) {
-                                    split2_f16(v[g * 8 + 0], v[g * 8 + 1], hi.x, lo.x);
-                                    split2_f16(v[g * 8 + 2], v[g * 8 + 3], hi.y, lo.y);
-                                    split2_f16(v[g * 8 + 4], v[g * 8 + 5], hi.z, lo.z);
-                                    split2_f16(v[g * 8 + 6], v[g * 8 + 7], hi.w, lo.w);
-                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
-                                    *reinterpret_cast<uint4*>(xrow + TILE_BYTES + off) = lo;
-                                } else {
-                                    hi.x = umma::pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                                    hi.y = umma::pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                                    hi.z = umma::pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                                    hi.w = umma::pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                                    *reinterpret_cast<uint4*>(xrow + off) = hi;
-                                }
-                            }
-                        }
-                        if (NSPLIT == 2 && vmax >= 32768.f && a.range_flag) *a.range_flag = 1;
-                        umma::fence_async_smem();
-                        umma::tc_fence_before();
-                        umma::mbar_arrive(&x_ready[t]);
-                        if (warp == 0 || warp == 4) IETL(1 + hf, it, l, t, 1);
-                        continue;
-                    }
-                    // ---- last layer: y = D + b4 -> LayerNorm over channels -> segmented mean over positions
-                    umma::mbar_wait(&m_full[slot], (it >> 1) & 1);
-                    // pass 1: y[n][e] -> staging [e][n] fp32 (16-byte chunks of a row permuted by the row index: every
-                    // access pattern below is bank-conflict free).  The operand tile is free: all MMAs that read it are done.
-#pragma unroll 1
-                    for (int cb = 0; cb < 64; cb += 8) {
+                    for (int cb = 0; cb < 64; cb += 32) {
                         const int c0 = hf * 64 + cb;
-                        float v[8];
-                        umma::tmem_ld8(tacc + (uint32_t)cb, v);
+                        float v[32];
+                        umma::tmem_ld32(tacc + (uint32_t)cb, v);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int e = c0 + i;
-                            *reinterpret_cast<float*>(xt + e * 512 + ((((n >> 2) ^ (e & 31))) << 4) + (n & 3) * 4) = v[i] + bias;
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i] + bias, 0.f);
+                        if (NSPLIT == 2) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) vmax = fmaxf(vmax, fmaxf(v[i], v[i + 1]));
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int cg = c0 + g * 8;
+                            const uint32_t off = (uint32_t)(cg >> 6) * (128u * 128u) + (uint32_t)((((cg & 63) >> 3) ^ (n & 7)) << 4);
+                            uint4 hi, lo;
+                            if (NSPLIT == 2) {
+                                split2_f16(v[g * 8 + 0], v[g * 8 + 1], hi.x, lo.x);
+                                split2_f16(v[g * 8 + 2], v[g * 8 + 3], hi.y, lo.y);
+                                split2_f16(v[g * 8 + 4], v[g * 8 + 5], hi.z, lo.z);
+                                split2_f16(v[g * 8 + 6], v[g * 8 + 7], hi.w, lo.w);
+                                *reinterpret_cast<uint4*>(xrow + off) = hi;
+                                *reinterpret_cast<uint4*>(xrow + TILE_BYTES + off) = lo;
+                            } else {
+                                hi.x = umma::pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
+                                hi.y = umma::pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
+                                hi.z = umma::pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
+                                hi.w = umma::pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
+                                *reinterpret_cast<uint4*>(xrow + off) = hi;
+                            }
                         }
                     }
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
-                    // pass 2: two threads per edge (64 channels each), exact two-pass mean / variance
-                    {
-                        const int j = tid & 127;
-                        const int e = hf * 64 + (j >> 1), part = j & 1;
-                        const unsigned char* row = xt + e * 512;
-                        float4 y[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int chunk = part * 16 + (i ^ (part << 2));
-                            y[i] = *reinterpret_cast<const float4*>(row + ((chunk ^ (e & 31)) << 4));
-                        }
-                        float s = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
-                        s += __shfl_xor_sync(0xffffffffu, s, 1);
-                        const float mean = s * (1.0f / 128.0f);
-                        float q = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float dx = y[i].x - mean, dy = y[i].y - mean, dz = y[i].z - mean, dw = y[i].w - mean;
-                            q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-                        }
-                        q += __shfl_xor_sync(0xffffffffu, q, 1);
-                        if (part == 0) stats[t * IE_TE + e] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / 128.0f) + 1e-5f));
-                    }
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
-                    // pass 3: normalise this thread's channel (accumulator re-read from TMEM) and reduce per destination
-                    {
-                        float sum = 0.f;
-                        const float2* st = stats + t * IE_TE;
-#pragma unroll 1
-                        for (int cb = 0; cb < 64; cb += 8) {
-                            const int c0 = hf * 64 + cb;
-                            float v[8];
-                            umma::tmem_ld8(tacc + (uint32_t)cb, v);
-#pragma unroll
-                            for (int i = 0; i < 8; i += 2) {
-                                const float4 mr = *reinterpret_cast<const float4*>(st + c0 + i);     // mean, rstd of two edges
-                                v[i] = fmaf(((v[i] + bias) - mr.x) * mr.y, gamma, beta);
-                                v[i + 1] = fmaf(((v[i + 1] + bias) - mr.z) * mr.w, gamma, beta);
-                            }
-                            uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 31)) & 0xffu, todo = 0xffu;
-                            if (fm == 0) {                   // the common case: no stored sum ends inside the chunk
-                                sum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-                                continue;
-                            }
-                            while (fm) {
-                                const uint32_t low = fm & (0u - fm);
-                                const uint32_t upto = (low << 1) - 1u;
-                                const uint32_t rng = todo & upto;
-                                float part = 0.f;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i)
-                                    if (rng & (1u << i)) part += v[i];
-                                const int pos = c0 + (31 - __clz(low));
-                                M->out[pos][n] = (sum + part) * M->scale[pos];
-                                sum = 0.f;
-                                todo &= ~upto;
-                                fm &= fm - 1;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                if (todo & (1u << i)) sum += v[i];
-                        }
-                    }
+                    if (NSPLIT == 2 && vmax >= 32768.f && a.range_flag) *a.range_flag = 1;
+                    umma::fence_async_smem();
                     umma::tc_fence_before();
-                    umma::mbar_arrive(&x_empty[t]);
-                    umma::mbar_arrive(&m_empty[slot]);
+                    umma::mbar_arrive(&x_ready[t]);
                     if (warp == 0 || warp == 4) IETL(1 + hf, it, l, t, 1);
                 }
+            }
+            // ---- last layer: y = D + b4 -> LayerNorm over channels -> segmented mean over positions.
+            // Phase A (both tiles): the LayerNorm statistics go through the operand tile, which is handed back to the producers
+            // right after; phase B (both tiles): normalise from TMEM + reduce — overlaps the next pair's first layers.
+            const float bias = a.bias[(IE_L - 1) * 128 + n];
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                if (pair * 2 + t >= n_tiles) continue;
+                unsigned char* xt = x_img + (size_t)t * 2 * TILE_BYTES;
+                const uint32_t tacc = tmem + (uint32_t)(((it & 1) * 2 + t) * 128) + lane_base + (uint32_t)(hf * 64);
+                umma::mbar_wait(&t_full[t], tf[t] & 1);
+                ++tf[t];
+                umma::tc_fence_after();
+                if (warp == 0 || warp == 4) IETL(1 + hf, it, IE_L - 1, t, 0);
+                // pass 1: y[n][e] -> staging [e][n] fp32 (16-byte chunks of a row permuted by the row index: every
+                // access pattern below is bank-conflict free).  The operand tile is free: all MMAs that read it are done.
+#pragma unroll 1
+                for (int cb = 0; cb < 64; cb += 16) {
+                    const int c0 = hf * 64 + cb;
+                    float v[16];
+                    umma::tmem_ld16(tacc + (uint32_t)cb, v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int e = c0 + i;
+                        *reinterpret_cast<float*>(xt + e * 512 + ((((n >> 2) ^ (e & 31))) << 4) + (n & 3) * 4) = v[i] + bias;
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
+                // pass 2: two threads per edge (64 channels each), exact two-pass mean / variance
+                {
+                    const int j = tid & 127;
+                    const int e = hf * 64 + (j >> 1), part = j & 1;
+                    const unsigned char* row = xt + e * 512;
+                    float4 y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int chunk = part * 16 + (i ^ (part << 2));
+                        y[i] = *reinterpret_cast<const float4*>(row + ((chunk ^ (e & 31)) << 4));
+                    }
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    const float mean = s * (1.0f / 128.0f);
+                    float q = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float dx = y[i].x - mean, dy = y[i].y - mean, dz = y[i].z - mean, dw = y[i].w - mean;
+                        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                    }
+                    q += __shfl_xor_sync(0xffffffffu, q, 1);
+                    if (part == 0) stats[((it & 1) * 2 + t) * IE_TE + e] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / 128.0f) + 1e-5f));
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
+                // the tile slot goes back to the producers (hardware barrier: the waiting side costs no issue slots), which refill
+                // it while phase B runs
+                asm volatile("bar.arrive %0, 512;" ::"r"(3 + t) : "memory");
+                if (warp == 0 || warp == 4) IETL(1 + hf, it, IE_L - 1, t, 2);
+            }
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                if (pair * 2 + t >= n_tiles) continue;
+                const int slot = (it & 1) * 2 + t;
+                umma::mbar_wait(&m_full[slot], (it >> 1) & 1);
+                ie_norm_reduce(tmem + (uint32_t)(slot * 128) + lane_base + (uint32_t)(hf * 64), metas + slot, stats + slot * IE_TE, hf, n, bias,
+                               gamma, beta);
+                umma::tc_fence_before();
+                umma::mbar_arrive(&m_empty[slot]);
+                if (warp == 0 || warp == 4) IETL(1 + hf, it, IE_L - 1, t, 1);
             }
         }
     } else if (warp == IE_MMA_WARP) {
@@ -325,35 +344,41 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
             for (int t = 0; t < 2; ++t) {
                 if (pair * 2 + t >= n_tiles) continue;
                 const int slot = (it & 1) * 2 + t;
-                umma::mbar_wait_relaxed<1000>(&m_empty[slot], ((it >> 1) & 1) ^ 1);
+                umma::mbar_wait_relaxed<2000>(&m_empty[slot], ((it >> 1) & 1) ^ 1);
                 build_tile_meta(metas + slot, a.rowptr, a.dstv, a.srcv, a.n_edges, pair * 2 + t, lane, a.agg, SEG_H, true, a.part_head,
                                 a.part_tail, IE_FLUSH);
                 umma::mbar_arrive(&m_full[slot]);
             }
         }
     } else {
-        // =========================== producers: layer-0 operand + accumulator initialisation ========
+        // =========================== producers: layer-0 operand, accumulator initialisation, last-layer phase B ==========
         // (a) 16 e_features rows per warp -> fp16 hi | lo K-major image (gathered and converted BEFORE the tile slot is
         //     waited for);  (b) D^T[n][e] := P[dst_e][n] + Q[src_e][n] written straight into the accumulator with tcgen05.st
         //     (thread = channel n of the warp's TMEM lane quadrant, 64 positions per warp), so that layer 0's MMAs add
-        //     We e on top and its epilogue is the plain bias-free ReLU — the gathers never sit on the epilogue's path.
+        //     We e on top and its epilogue is the plain bias-free ReLU — the gathers never sit on the epilogue's path;
         const int pw = warp - IE_PROD_WARP0;
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
         const float* src = a.e + lane * 4;
         const float sc = a.e_scale;
         const int quad = warp & 3, chalf = pw >> 2;            // TMEM lane quadrant of this warp, its half of the positions
-        const float* pqn = a.pq + quad * 32 + lane;
-        uint32_t xe[2] = {0, 0};
+        const int n = quad * 32 + lane;
+        const float* pqn = a.pq + n;
+        const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
 #pragma unroll 1
-        for (int it = 0; it < np; ++it) {
+        for (int it = 0; it <= np; ++it) {                      // iteration np only takes the last pair's slot hand-overs
             const int64_t pair = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-            // (b) first, for both tiles of the pair: their accumulators were drained two pairs ago, so they are initialised
-            // while the previous pair is still in flight — the gathers are off every critical path
+            // (b) first, for both tiles of the pair: their accumulators were drained two pairs ago (the hand-over of the previous
+            // pair's slot came after that), so they are initialised while the previous pair is still in flight
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
                 const int64_t tile = pair * 2 + t;
-                if (tile >= n_tiles) continue;
+                if (it == np || tile >= n_tiles) continue;
+                // the accumulator was last read by phase B of pair it - 2 (normally long done: the wait falls through)
+                if (it >= 2) {
+                    umma::mbar_wait_relaxed<200>(&m_empty[(it & 1) * 2 + t], ((it - 2) >> 1) & 1);
+                    umma::tc_fence_after();
+                }
                 const int64_t c0 = tile * IE_TE + chalf * 64;
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
@@ -362,60 +387,81 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                     // no select behind the loads: all 32 stay in flight
                     const uint32_t dl = p < a.n_edges ? (uint32_t)a.dstv[p] : 0u;
                     const uint32_t sl = p < a.n_edges ? (uint32_t)a.srcv[p] : 0u;
-                    float acc[32], pv[32];
+                    float acc[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) acc[i] = pqn[(size_t)__shfl_sync(0xffffffffu, sl, i) * 256 + 128];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) pv[i] = pqn[(size_t)__shfl_sync(0xffffffffu, dl, i) * 256];      // repeat along a segment: L1 hits
+                    for (int g = 0; g < 32; g += 8) {                    // P rows repeat along a segment: mostly L1 hits
+                        float pv[8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] += pv[i];
-                    umma::tmem_st32(tmem + (uint32_t)(((it & 1) * 2 + t) * 128) + ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * 64 + h * 32), acc);
+                        for (int i = 0; i < 8; ++i) pv[i] = pqn[(size_t)__shfl_sync(0xffffffffu, dl, g + i) * 256];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[g + i] += pv[i];
+                    }
+                    umma::tmem_st32(tmem + (uint32_t)(((it & 1) * 2 + t) * 128) + lane_base + (uint32_t)(chalf * 64 + h * 32), acc);
                 }
+            }
+            // the COO ids of this warp's 16 rows of both tiles; tile 1's rows are pulled into L2 now, read after tile 0 is stored
+            int64_t mine[2] = {-1, -1};
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int64_t p0 = (pair * 2 + t) * IE_TE + pw * 16;
+                if (it < np && lane < 16 && p0 + lane < a.n_edges) mine[t] = a.perm ? (int64_t)a.perm[p0 + lane] : p0 + lane;
+            }
+            if (mine[1] >= 0) {
+                const float* row = a.e + mine[1] * 128;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 64));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 96));
             }
 #pragma unroll 1
             for (int t = 0; t < 2; ++t) {
-                const int64_t tile = pair * 2 + t;
-                if (tile >= n_tiles) continue;
-                // (a) e_features rows -> registers -> images once the tile slot is free
-                const int64_t p0 = tile * IE_TE + pw * 16;
-                int64_t mine = -1;
-                if (lane < 16 && p0 + lane < a.n_edges) mine = a.perm ? (int64_t)a.perm[p0 + lane] : p0 + lane;
-                float4 x[16];
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int64_t c = __shfl_sync(0xffffffffu, mine, r);
-                    x[r] = *reinterpret_cast<const float4*>(src + (c < 0 ? 0 : c) * 128);
-                    if (c < 0) x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                const bool cur = it < np && pair * 2 + t < n_tiles;                       // tile (it, t) exists
+                const bool prev = it > 0 && (pair - gridDim.x) * 2 + t < n_tiles;          // tile (it - 1, t) exists
                 uint4 hl[16];
+                if (cur) {
+                    // (a) e_features rows -> registers -> images once the tile slot is free
+                    const int64_t mt = t ? mine[1] : mine[0];
+                    float4 x[16];
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    float4 h = x[r];
-                    h.x *= sc; h.y *= sc; h.z *= sc; h.w *= sc;
-                    if (NSPLIT == 2) {
-                        if (fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))) >= 32768.f && a.range_flag) *a.range_flag = 1;
-                        split2_f16(h.x, h.y, hl[r].x, hl[r].z);
-                        split2_f16(h.z, h.w, hl[r].y, hl[r].w);
-                    } else {
-                        hl[r].x = umma::pack_bf16(h.x, h.y);
-                        hl[r].y = umma::pack_bf16(h.z, h.w);
+                    for (int r = 0; r < 16; ++r) {
+                        const int64_t c = __shfl_sync(0xffffffffu, mt, r);
+                        x[r] = *reinterpret_cast<const float4*>(src + (c < 0 ? 0 : c) * 128);
+                        if (c < 0) x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        float4 h = x[r];
+                        h.x *= sc; h.y *= sc; h.z *= sc; h.w *= sc;
+                        if (NSPLIT == 2) {
+                            if (fmaxf(fmaxf(fabsf(h.x), fabsf(h.y)), fmaxf(fabsf(h.z), fabsf(h.w))) >= 32768.f && a.range_flag) *a.range_flag = 1;
+                            split2_f16(h.x, h.y, hl[r].x, hl[r].z);
+                            split2_f16(h.z, h.w, hl[r].y, hl[r].w);
+                        } else {
+                            hl[r].x = umma::pack_bf16(h.x, h.y);
+                            hl[r].y = umma::pack_bf16(h.z, h.w);
+                        }
                     }
                 }
                 if (pw == 0) IETL(3, it, 0, t, 0);
-                umma::mbar_wait_relaxed<500>(&x_empty[t], (xe[t] & 1) ^ 1);
-                ++xe[t];
-                if (pw == 0) IETL(3, it, 0, t, 1);
-                umma::tc_fence_after();            // orders the NEXT tile's tcgen05.st behind the epilogue's accumulator reads
-                unsigned char* img = x_img + (size_t)t * 2 * TILE_BYTES;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
-                    *reinterpret_cast<uint2*>(img + off) = make_uint2(hl[r].x, hl[r].y);
-                    if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = make_uint2(hl[r].z, hl[r].w);
+                if (prev) {
+                    asm volatile("bar.sync %0, 512;" ::"r"(3 + t) : "memory");      // statistics of (it-1, t) written, slot t free
+                    umma::tc_fence_after();
                 }
-                umma::fence_async_smem();
-                umma::tc_fence_before();
-                umma::mbar_arrive(&x_full[t]);
+                if (pw == 0) IETL(3, it, 0, t, 1);
+                if (cur) {
+                    unsigned char* img = x_img + (size_t)t * 2 * TILE_BYTES;
+#pragma unroll
+                    for (int r = 0; r < 16; ++r) {
+                        const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
+                        *reinterpret_cast<uint2*>(img + off) = make_uint2(hl[r].x, hl[r].y);
+                        if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = make_uint2(hl[r].z, hl[r].w);
+                    }
+                    umma::fence_async_smem();
+                    umma::tc_fence_before();
+                    umma::mbar_arrive(&x_full[t]);
+                }
                 if (pw == 0) IETL(3, it, 0, t, 2);
             }
         }
