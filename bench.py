@@ -1,19 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native MAgNet hot path.
+"""bench.py — benchmarks of the B200-native MAgNet hot path, one JSON line per run.
 
+    python bench.py --gpus N --steps K --warmup W                       # headline: mp_layer (+ the other metrics inside "metrics")
+    python bench.py --metric {mp_layer,in_layer,inr_decode,rollout}     # one metric as the line itself
+    python bench.py --metric inr_sweep                                  # BASELINE configs[4]: Q x k sweep -> profiles/r02_inr_sweep.json
+    python bench.py --impl reference [--metric ...]                     # the reference's own CPU implementation (oracle/_ref)
 
-    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (oracle port)
-
-Metric (BASELINE.json): edges/s per message-passing layer, forward + backward.
-Workload (BASELINE.json configs[1]): the MP-PDE (mpnn_2d) processor — 5 GNN_Layers, hidden 128,
-time_window 10 — on synthetic 2-D irregular-uniform 64x64-point meshes, batch 32 per GPU
-(reference irregular scripts, scripts/mpnn_2d/mpnn_2d_b1_512_irregular.sh), radius chosen so that
-the reference's 32-neighbour index-order truncation is active (mean degree ~32.6).
-A step = one forward + backward pass of the 5-layer processor over one batch, the gradient all-reduce (N > 1) and the
-Adam update of its parameters;
-value = (edges per batch x 5 layers x K) / time, summed over ranks (weak scaling: the batch is
-sharded by independent samples, no data-path collective).
+BASELINE.json metric: "edges/s per MP layer fwd+bwd; query pts/s INR decode; rollout steps/s @1/2/4/8 B200".
+  mp_layer    edges/s per message-passing layer, forward + backward — BASELINE configs[1]: the MP-PDE (mpnn_2d) processor, 5 GNN_Layers,
+              hidden 128, time_window 10, synthetic 2-D irregular-uniform 64x64-point meshes, 32 samples per GPU, radius such that the
+              reference's 32-neighbour index-order truncation is active.  A step = forward + backward of the 5 layers + gradient
+              all-reduce (N > 1) + Adam update.
+  in_layer    the same metric for MAgNet[GNN]'s InteractionNetwork (models/magnet_gnn.py:44-90) on the stage-3 graph of BASELINE
+              configs[2] at test resolution 256 (65,536 nodes per sample, r = 0.08, 32-cap active); forward-only (fused kernel) next to it.
+  inr_decode  query points/s of continuous_decoder + projector (kNN search, gather, proj_head, blend, 5-layer MLP), configs[4] shape.
+  rollout     MAgNet[GNN] validation rollout steps/s (models/magnet_gnn.py:442-475), configs[2]: B = 32, L = Nq = 256 per GPU.
+Every metric line carries `roofline` (algorithmic FLOPs / CUDA-event time / MEASURED_PEAKS.json), `e2e` (host buffers in, result out,
+copies inside the timed region) and, at N = 1, `cpu_baseline` = the reference's own model files (byte-compiled into oracle/_ref by
+oracle/stage_ref.py; restated third-party surface underneath) timed on the box's host cores on a bounded sample.
+All metrics shard by independent samples with no data-path collective (weak scaling); values are summed over ranks, times are the max.
 """
 import argparse
 import ctypes
@@ -34,17 +39,44 @@ TW = 10
 NODES_PER_SAMPLE = 4096
 SAMPLES_PER_GPU = 32
 RADIUS = 0.09
-FLOP_PER_EDGE_FWD = 101_632          # 2*(269*128 + 128*128), reference formulation
+FLOP_PER_EDGE_FWD = 101_632          # 2*(269*128 + 128*128), GNN_Layer message, reference formulation
 FLOP_PER_NODE_FWD = 98_560
 EXEC_FLOP_PER_EDGE_FWD = 2 * 128 * 128        # what the fused edge kernel executes per edge (factorised first Linear)
+IN_FLOP_PER_EDGE_FWD = 229_376       # 2*(384*128 + 4*128^2), InteractionNetwork edge_fn
+IN_FLOP_PER_NODE_FWD = 196_608
+ENC_FLOP_PER_ROW = 2 * (13 * 128 + 4 * 128 * 128)      # Encoder MLPs (approx.: 12/13-wide first Linear)
+INR_FLOP_PER_QUERY_T = lambda k: k * 2 * 132 * 128 + 131_328     # per (query, time step): k proj_head rows + projector
 
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
-    return 6650.0, 1590.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained"), "measured"
+    return 6650.0, 1590.0, None, "fallback"
+
+
+def _ncu(name):
+    """dram bytes per launch of a kernel from the committed ncu --set full summaries (profiles/*.json): measured once per round
+    under ncu, NOT in this run (a number taken under a profiler is never a bench value; the traffic figure is a property of
+    the kernel + problem size and is stated with its source)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        return d.get("dram_bytes_per_launch"), d.get("source_report")
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
+class HP(dict):
+    __getattr__ = dict.__getitem__
+
+
+def magnet_hparams(**over):
+    hp = dict(time_slice=10, latent_dim=128, num_message_passing_steps=5, mlp_layers=4, mlp_hidden=128, radius=0.08, n_chan=128,
+              teacher_forcing=True, codec_neighbors=4, noise=0, interpolation="area", factor=0.3, step_size=50, loss="l1",
+              lr=1e-3, weight_decay=0)
+    hp.update(over)
+    return HP(hp)
 
 
 class ClockSampler:
@@ -110,6 +142,81 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+class Env:
+    """Rank / device / collective plumbing shared by the metrics."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dev = None
+        self.L = None
+
+    def init_gpu(self):
+        import torch.distributed as dist
+        from magnet_b200 import _lib
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.L = _lib.lib()
+        if self.world > 1 and not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(self, value: float, op: str) -> float:
+        if self.world == 1:
+            return float(value)
+        import torch.distributed as dist
+        t = torch.tensor([float(value)], device=self.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
+        return float(t)
+
+    def prof(self, kid):
+        t, c = ctypes.c_double(0), ctypes.c_int64(0)
+        self.L.mgb_profile_collect(kid, ctypes.byref(t), ctypes.byref(c))
+        return t.value, c.value
+
+    def timed(self, fn, steps, warmup, clocks=None):
+        """W untimed + K timed calls of fn between barrier + synchronize, CUDA events on the current stream; returns
+        (max-over-ranks ms for the K steps, launches per step)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(max(warmup, 3)):
+            fn()
+        self.barrier()
+        self.L.mgb_profile_enable(1)
+        l0 = self.L.mgb_launch_count()
+        if clocks is not None:
+            clocks.wait_ready()
+            self.barrier()
+            clocks.mark_start()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        self.barrier()
+        if clocks is not None:
+            clocks.mark_end()
+        self.L.mgb_profile_enable(0)
+        launches = (self.L.mgb_launch_count() - l0) // max(steps, 1)
+        return self.reduce(ev0.elapsed_time(ev1), "max"), int(launches)
+
+
+def base_line(env, metric, unit, value, ms_per_step, steps, warmup, dtype, config, **more):
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": env.world, "steps": steps, "warmup": max(warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "data": "synthetic", "config": config}
+    line.update(more)
+    return line
+
+
+# =============================================================================================================
+# mp_layer — BASELINE configs[1]
+# =============================================================================================================
 def make_workload(samples: int, seed: int, device):
     """Layer inputs of the config-2 processor for `samples` samples of one shared 4096-node mesh."""
     from magnet_b200 import synthetic as S
@@ -134,26 +241,48 @@ def layer_state_dicts():
     return [S.seeded_state_dict(shapes, 100 + l) for l in range(N_LAYERS)]
 
 
-def cpu_reference_run(samples: int, steps: int, warmup: int, threads: int):
-    """The reference CPU path (oracle port: plain torch on the host cores) on a bounded sample."""
+def mp_config(n_gpus, precision=None):
+    c = {"workload": "mpnn_2d processor (5x GNN_Layer, hidden 128, tw 10) on synthetic 2-D irregular-uniform "
+                     "64x64-point meshes, BASELINE configs[1]",
+         "samples_per_gpu": SAMPLES_PER_GPU, "nodes_per_sample": NODES_PER_SAMPLE, "radius": RADIUS,
+         "max_num_neighbors": 32, "layers": N_LAYERS, "parallelism": f"samples sharded over {n_gpus} GPU(s), no data-path collective"
+                        + ("; one NCCL all-reduce of the flat gradient buffer per step" if n_gpus > 1 else ""),
+         "l2": "working set per layer (~1 GB) exceeds the 126 MB L2; no explicit flush"}
+    if precision:
+        c["precision"] = precision
+    return c
+
+
+def ref_modules():
+    """The reference's own model files: source tree in the build container, byte-compiled copies (oracle/_ref) on the GPU box."""
+    from oracle import reference_loader as rl
+    ns = rl.load()
+    return ns, ("reference", f"unmodified reference model files ({ns.kind}: {'/root/reference' if ns.kind == 'source' else 'oracle/_ref'}) "
+                             "behind the restated torch_geometric/torch_cluster surface (oracle/thirdparty)")
+
+
+def cpu_mp_layer(samples: int, steps: int, warmup: int, threads: int):
+    """Reference CPU path: models/mpnn_2d.py GNN_Layer x5, forward + backward, on a bounded sample."""
     from oracle import graph as OG
-    from oracle import restatement as R
     torch.set_num_threads(threads)
+    ns, (kind, how) = ref_modules()
     w = make_workload(samples, 0, "cpu")
     batch = torch.arange(samples).repeat_interleave(NODES_PER_SAMPLE)
     ei = OG.radius_graph(w["coords"], RADIUS, batch, loop=False, threads=threads)
-    sds = [{k: v.clone().requires_grad_() for k, v in sd.items()} for sd in layer_state_dicts()]
+    layers = []
+    for sd in layer_state_dicts():
+        m = ns.mpnn_2d.GNN_Layer(128, 128, 128, TW, 1)
+        m.load_state_dict(sd, strict=True)
+        layers.append(m)
     E = ei.shape[1]
 
     def step():
-        h = w["x"].clone().requires_grad_()
-        out = h
-        for sd in sds:
-            out = R.gnn_layer(sd, "", out, w["u"], w["pos"], w["var"], ei, batch)
+        out = w["x"].clone().requires_grad_()
+        for m in layers:
+            out = m(out, w["u"], w["pos"], w["var"], ei, batch)
         out.backward(w["gy"])
-        for sd in sds:
-            for p in sd.values():
-                p.grad = None
+        for m in layers:
+            m.zero_grad(set_to_none=True)
 
     for _ in range(warmup):
         step()
@@ -161,149 +290,19 @@ def cpu_reference_run(samples: int, steps: int, warmup: int, threads: int):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return E * N_LAYERS * steps / dt, dt / steps * 1e3, E
+    sample = (f"{samples} of {SAMPLES_PER_GPU} samples per step ({samples * NODES_PER_SAMPLE} nodes, {E} edges), all {N_LAYERS} "
+              f"layers fwd+bwd, {steps} timed steps after {warmup} warm-up; {how}")
+    return {"value": E * N_LAYERS * steps / dt, "unit": "edges/s", "cores": threads, "kind": kind, "sample": sample,
+            "ms_per_step": dt / steps * 1e3}
 
 
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    threads = os.cpu_count() or 1
-    samples = 1
-    value, ms, E = cpu_reference_run(samples, args.steps, args.warmup, threads)
-    sample = f"{samples} of {SAMPLES_PER_GPU} samples per step ({samples * NODES_PER_SAMPLE} nodes, {E} edges), all {N_LAYERS} layers fwd+bwd"
-    line = {
-        "impl": "reference", "metric": "edges/s per MP layer fwd+bwd", "value": value, "unit": "edges/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, note="reference CPU path = oracle port (torch CPU, unmodified-reference "
-                                  "semantics); /root/reference itself cannot travel to the GPU box"),
-        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line), flush=True)
-
-
-def workload_config(n_gpus, note=None):
-    c = {"workload": "mpnn_2d processor (5x GNN_Layer, hidden 128, tw 10) on synthetic 2-D irregular-uniform "
-                     "64x64-point meshes, BASELINE configs[1]",
-         "samples_per_gpu": SAMPLES_PER_GPU, "nodes_per_sample": NODES_PER_SAMPLE, "radius": RADIUS,
-         "max_num_neighbors": 32, "layers": N_LAYERS, "parallelism": f"samples sharded over {n_gpus} GPU(s), no data-path collective"
-                        + ("; one NCCL all-reduce of the flat gradient buffer per step" if n_gpus > 1 else ""),
-         "l2": "working set per layer (~1 GB) exceeds the 126 MB L2; no explicit flush"}
-    if note:
-        c["note"] = note
-    return c
-
-
-def extra_metrics(dev, rank):
-    """The two other metrics BASELINE.json names, measured in the same run on this rank's GPU (reported per GPU;
-    both shard by independent samples with no collective, so N GPUs give N times these figures):
-      * INR decode: queries/s of continuous_decoder + projector (kNN search, gather, head, blend, 5-layer MLP) on
-        2^18 query points over a 2^18-node low-res mesh, k = 4, T = 10 (BASELINE configs[4] shape, one sample);
-      * rollout: MAgNet[GNN] validation rollout steps/s at the reference's training shape (B = 32, L = Nq = 256,
-        time_slice 10, 4 autoregressive steps; BASELINE configs[2])."""
-    from magnet_b200 import synthetic as S, functional as MF
-    from magnet_b200.magnet_gnn import MAgNetGNN
-
-    class HP(dict):
-        __getattr__ = dict.__getitem__
-    hp = HP(time_slice=10, latent_dim=128, num_message_passing_steps=5, mlp_layers=4, mlp_hidden=128, radius=0.08, n_chan=128,
-            teacher_forcing=True, codec_neighbors=4, noise=0, interpolation="area", factor=0.3, step_size=50, loss="l1",
-            lr=1e-3, weight_decay=0)
-    m = MAgNetGNN(hp).to(dev).eval()
-    sd = S.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 7)
-    m.load_state_dict(sd)
-    out = {}
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.no_grad():
-        # ---- INR decode ----
-        g = S._gen(500 + rank)
-        Lr, Q, T = 1 << 18, 1 << 18, 10
-        lr_coords = (2 * torch.rand(1, Lr, 2, generator=g) - 1).to(dev)
-        hr_coords = (2 * torch.rand(1, Q, 2, generator=g) - 1).to(dev)
-        enc = torch.randn(1, Lr, 128, generator=g).to(dev)
-        x_lr = torch.randn(1, T, 1, Lr, generator=g).to(dev)
-        t = torch.linspace(0, 1, 2 * T)[None].to(dev)
-
-        def decode():
-            z = m.continuous_decoder(x_lr, enc, lr_coords, hr_coords, t)
-            return m.projector(z)
-        for _ in range(2):
-            decode()
-        torch.cuda.synchronize()
-        reps = 3
-        ev0.record()
-        for _ in range(reps):
-            hr = decode()
-        ev1.record()
-        torch.cuda.synchronize()
-        out["inr_decode"] = {"value": Q * reps / (ev0.elapsed_time(ev1) * 1e-3), "unit": "query points/s (per GPU)",
-                             "queries": Q, "lowres_nodes": Lr, "k": 4, "time_steps": T,
-                             "includes": "kNN search + gather + proj_head + blend + projector MLP",
-                             "arithmetic": "tcgen05 fp16 hi/lo split Linears (default; 1e-5 contract on predictions)"}
-        # same call with the 128-wide Linears on the exact fp32 FFMA GEMM (functional.set_linear_tc(False))
-        old = MF.set_linear_tc(False)
-        for _ in range(2):
-            decode()
-        torch.cuda.synchronize()
-        ev0.record()
-        for _ in range(reps):
-            hr = decode()
-        ev1.record()
-        torch.cuda.synchronize()
-        MF.set_linear_tc(old)
-        out["inr_decode_ffma_linears"] = {"value": Q * reps / (ev0.elapsed_time(ev1) * 1e-3), "unit": "query points/s (per GPU)",
-                                          "arithmetic": "fp32 FFMA Linears"}
-        del hr, enc, x_lr
-        # ---- rollout ----
-        b = {k: v.to(dev) for k, v in S.implicit_batch(B=32, L=256, Nq=256, nt=50, d=2, kind="concentrated", seed=600 + rank).items()}
-        for _ in range(2):
-            m.rollout(b, teacher_forcing=False)
-        torch.cuda.synchronize()
-        reps = 3
-        ev0.record()
-        for _ in range(reps):
-            m.rollout(b, teacher_forcing=False)
-        ev1.record()
-        torch.cuda.synchronize()
-        out["rollout"] = {"value": 4 * reps / (ev0.elapsed_time(ev1) * 1e-3), "unit": "rollout steps/s (per GPU)",
-                          "config": "MAgNet[GNN] B=32, L=Nq=256, time_slice 10, 4 steps per rollout, r=0.08, fp32",
-                          "arithmetic": "tcgen05 fp16 hi/lo split Linears (default; 1e-5 contract on predictions)"}
-        old = MF.set_linear_tc(False)
-        for _ in range(2):
-            m.rollout(b, teacher_forcing=False)
-        torch.cuda.synchronize()
-        ev0.record()
-        for _ in range(reps):
-            m.rollout(b, teacher_forcing=False)
-        ev1.record()
-        torch.cuda.synchronize()
-        MF.set_linear_tc(old)
-        out["rollout_ffma_linears"] = {"value": 4 * reps / (ev0.elapsed_time(ev1) * 1e-3), "unit": "rollout steps/s (per GPU)",
-                                       "arithmetic": "fp32 FFMA Linears"}
-    return out
-
-
-def ncu_traffic():
-    """dram bytes (read + write) per launch of the dominant kernel from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "dominant_kernel_ncu.json")
-    try:
-        return json.load(open(p)).get("dram_bytes_per_launch")
-    except Exception:  # noqa: BLE001
-        return None
-
-
-def run_ours(args, rank, world, local_rank):
-    import torch.distributed as dist
-    from magnet_b200 import _lib, graph as MG, functional as MF, distributed as D
+def bench_mp_layer(env, clocks):
+    from magnet_b200 import graph as MG, functional as MF
     from magnet_b200.mpnn import GNN_Layer
+    from magnet_b200.optim import FlatAdam, allreduce_flat_gradient
+    args, dev, world, L = env.args, env.dev, env.world, env.L
     MF.set_precision(args.precision)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    L = _lib.lib()
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    w = make_workload(SAMPLES_PER_GPU, 1 + rank, dev)
+    w = make_workload(SAMPLES_PER_GPU, 1 + env.rank, dev)
     host = {k: v.pin_memory() for k, v in w.items() if torch.is_tensor(v) and k in ("x", "u", "pos", "var", "gy")}
     d = {k: v.to(dev) for k, v in w.items() if torch.is_tensor(v)}
     seg = MG.uniform_segments(SAMPLES_PER_GPU, NODES_PER_SAMPLE, dev)
@@ -320,7 +319,6 @@ def run_ours(args, rank, world, local_rank):
     # the reference's optimizer (Adam + weight decay, models/mpnn_2d.py:205-213) as one flat-buffer launch; its flat
     # gradient buffer is what the all-reduce sends.  The step is part of the timed region: so is the re-packing of the
     # kernel-side weight copies that every update triggers.
-    from magnet_b200.optim import FlatAdam, allreduce_flat_gradient
     opt = FlatAdam(params, lr=1e-5, weight_decay=1e-8)
 
     def step(x, u, pos, var, gy):
@@ -334,51 +332,20 @@ def run_ours(args, rank, world, local_rank):
         opt.zero_grad()
         return out
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        for _ in range(max(args.warmup, 3)):
-            step(d["x"], d["u"], d["pos"], d["var"], d["gy"])
-        barrier()
-        # ---- device-resident timing -------------------------------------------------------------
-        L.mgb_profile_enable(1)
-        launches0 = L.mgb_launch_count()
-        clocks.wait_ready()
-        barrier()
-        clocks.mark_start()
-        ev0.record()
-        for _ in range(args.steps):
-            step(d["x"], d["u"], d["pos"], d["var"], d["gy"])
-        ev1.record()
-        barrier()
-        clocks.mark_end()
-        if args.steps * 0.025 < 0.12:
-            time.sleep(0.12)          # a very short timed region: let the sample that covers it arrive before nvidia-smi is stopped
-    launches = (L.mgb_launch_count() - launches0) // max(args.steps, 1)
-    L.mgb_profile_enable(0)
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    prof = {}
-    for name, kid in (("edge_fwd", 0), ("edge_bwd", 1)):
-        t, c = ctypes.c_double(0), ctypes.c_int64(0)
-        L.mgb_profile_collect(kid, ctypes.byref(t), ctypes.byref(c))
-        prof[name] = (t.value, c.value)
+    total_ms, launches = env.timed(lambda: step(d["x"], d["u"], d["pos"], d["var"], d["gy"]), args.steps, args.warmup, clocks)
+    if args.steps * 0.025 < 0.12:
+        time.sleep(0.12)          # a very short timed region: let the sample that covers it arrive before nvidia-smi is stopped
+    prof = {"edge_fwd": env.prof(0), "edge_bwd": env.prof(1)}
     # ---- end to end: pinned host inputs -> H2D -> 5 layers fwd+bwd -> D2H of the result checksum ----
-    # Every step copies its own inputs from pinned host memory and reads its result back.  The copy of step k+1 is
-    # issued on a side stream before step k computes (double buffering), so the PCIe transfer overlaps the kernels; the
-    # result of every step is copied to pinned host memory inside the timed region (asynchronously: the host does not
-    # stall the pipeline on it; the closing barrier + synchronize waits for all of them).
+    # Every step copies its own inputs from pinned host memory (double-buffered on a side stream: the transfer of step k+1
+    # overlaps the kernels of step k) and reads its result back (a training step's result is its loss-like scalar: 4 bytes).
     e2e_steps = max(1, args.steps)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
-
     dbuf = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
-    results = torch.zeros(e2e_steps, dtype=torch.float32).pin_memory()       # one value per step, read back asynchronously
-    used = [None, None]          # event: the step that read buffer j has been enqueued and finished
+    results = torch.zeros(e2e_steps, dtype=torch.float32).pin_memory()
+    used = [None, None]
 
     def upload(j):
         with torch.cuda.stream(copy_stream):
@@ -391,7 +358,7 @@ def run_ours(args, rank, world, local_rank):
         return ev
 
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    env.barrier()
     ee0.record()
     copy_stream.wait_stream(main_stream)
     nxt = upload(0)
@@ -404,68 +371,412 @@ def run_ours(args, rank, world, local_rank):
         out = step(dx["x"], dx["u"], dx["pos"], dx["var"], dx["gy"])
         used[j] = torch.cuda.Event()
         used[j].record(main_stream)
-        results[i:i + 1].copy_(out.sum().reshape(1), non_blocking=True)      # device -> host read of the step's result
+        results[i:i + 1].copy_(out.sum().reshape(1), non_blocking=True)
     ee1.record()
-    barrier()                                            # every copy has landed before the clock is read
+    env.barrier()
     checksum = float(results.sum())
     assert checksum == checksum, "e2e produced NaN"
-    e2e_ms = torch.tensor([ee0.elapsed_time(ee1)], device=dev)
-    edges = torch.tensor([float(E)], device=dev)
-    extras = None
-    if not args.no_extra:
-        del d, out
-        torch.cuda.empty_cache()
-        extras = extra_metrics(dev, rank)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(edges, op=dist.ReduceOp.SUM)
-    if rank == 0:
-        total_ms = float(ms)
-        value = float(edges) * N_LAYERS * args.steps / (total_ms * 1e-3)
-        e2e_value = float(edges) * N_LAYERS * e2e_steps / (float(e2e_ms) * 1e-3)
-        hbm, tf, which = _peaks()
-        # dominant kernel: the fused edge backward (recompute + dgrad + wgrad of the message nets)
-        bt, bc = prof["edge_bwd"]
-        ft, fc = prof["edge_fwd"]
-        bwd_ms = bt / max(bc, 1)
-        fwd_ms = ft / max(fc, 1)
-        alg_flops = 2 * FLOP_PER_EDGE_FWD * E            # dgrad + wgrad of both message Linears, reference formulation
-        achieved = alg_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
-                    "traffic": ncu_traffic(), "kernel": "gnn_edge_bwd_tc_kernel" if args.precision != "fp32" else "gnn_edge_bwd_kernel",
-                    "peak_source": which,
-                    "kernel_ms": bwd_ms, "kernel_share_of_step": bt / total_ms if total_ms > 0 else None,
-                    "executed_tflops": 3 * EXEC_FLOP_PER_EDGE_FWD * E / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0,
-                    "edge_fwd_kernel_ms": fwd_ms,
-                    # other floors of the same kernel: fp32-accurate Swish costs 6 transcendental ops per
-                    # edge-channel in the backward kernel (4 in the forward one) on a 16-lane/clk/SM MUFU pipe
-                    "mufu_floor_ms": (6 if args.precision != "bf16" else 3) * E * 128 / (16 * 148 * 1.965e9) * 1e3,
-                    "edge_fwd_algorithmic_tflops": FLOP_PER_EDGE_FWD * E / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0,
-                    "note": {"fp32": "fp32 FFMA path (1e-5 contract) measured against the bf16 tensor peak",
-                             "fp32_tc": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (1e-5 contract)",
-                             "bf16": "tcgen05 bf16 operands, fp32 accumulate (1e-2 contract)"}[args.precision]}
-        line = {
-            "metric": "edges/s per MP layer fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": dict(workload_config(world), precision=args.precision), "clocks": clocks.summary(),
-            "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps},
-            "gpu_launches": int(launches), "roofline": roofline, "edges_per_gpu": E,
-        }
-        if not args.no_extra:
-            line["extra_metrics"] = extras
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            v, cms, ce = cpu_reference_run(1, 2, 1, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "edges/s", "cores": threads, "kind": "port",
-                                    "sample": f"1 of {SAMPLES_PER_GPU} samples ({NODES_PER_SAMPLE} nodes, {ce} edges), "
-                                              f"{N_LAYERS} layers fwd+bwd, 2 timed steps after 1 warm-up"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    e2e_ms = env.reduce(ee0.elapsed_time(ee1), "max")
+    edges = env.reduce(float(E), "sum")
+    del d, out, dbuf
+    torch.cuda.empty_cache()
+    if env.rank != 0:
+        return None
+    value = edges * N_LAYERS * args.steps / (total_ms * 1e-3)
+    e2e_value = edges * N_LAYERS * e2e_steps / (e2e_ms * 1e-3)
+    hbm, tf, tf_sus, which = _peaks()
+    bt, bc = prof["edge_bwd"]
+    ft, fc = prof["edge_fwd"]
+    bwd_ms, fwd_ms = bt / max(bc, 1), ft / max(fc, 1)
+    alg_flops = 2 * FLOP_PER_EDGE_FWD * E            # dgrad + wgrad of both message Linears, reference formulation
+    achieved = alg_flops / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0
+    traffic, tsrc = _ncu("dominant_kernel_ncu.json")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
+                "traffic": traffic, "traffic_source": f"profiles/dominant_kernel_ncu.json ({tsrc}): ncu --set full capture of the same kernel and problem size, not measured in this run",
+                "kernel": "gnn_edge_bwd_tc_kernel" if args.precision != "fp32" else "gnn_edge_bwd_kernel",
+                "peak_source": which, "frac_of_sustained_peak": achieved / tf_sus if tf_sus else None,
+                "kernel_ms": bwd_ms, "kernel_share_of_step": bt / total_ms if total_ms > 0 else None,
+                "executed_tflops": 3 * EXEC_FLOP_PER_EDGE_FWD * E / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0,
+                "edge_fwd_kernel_ms": fwd_ms,
+                "edge_fwd_algorithmic_tflops": FLOP_PER_EDGE_FWD * E / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0,
+                "note": {"fp32": "fp32 FFMA path (1e-5 contract) measured against the bf16 tensor peak",
+                         "fp32_tc": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (1e-5 contract)",
+                         "bf16": "tcgen05 bf16 operands, fp32 accumulate (1e-2 contract)"}[args.precision]}
+    line = base_line(env, "edges/s per MP layer fwd+bwd", "edges/s", value, total_ms / args.steps, args.steps, args.warmup,
+                     "bf16" if args.precision == "bf16" else "f32", mp_config(world, args.precision),
+                     clocks=clocks.summary() if clocks else None,
+                     e2e={"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                          "result": "a training step returns its scalar: the 4-byte read is the whole result (inference metrics below download fields)"},
+                     gpu_launches=launches, roofline=roofline, edges_per_gpu=E)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_mp_layer(1, 2, 1, os.cpu_count() or 1)
+    return line
+
+
+# =============================================================================================================
+# in_layer — InteractionNetwork on the stage-3 graph of BASELINE configs[2] at test resolution 256
+# =============================================================================================================
+IN_NODES_PER_SAMPLE, IN_SAMPLES = 65536, 2
+
+
+def in_workload(samples, nodes, seed, dev):
+    from magnet_b200 import synthetic as S
+    g = S._gen(seed)
+    pts = []
+    for _ in range(samples):
+        c = S.mesh("concentrated", nodes, 2, g)
+        pts.append(2 * (c - c.min(0).values) / (c.max(0).values - c.min(0).values) - 1)
+    pos = torch.cat(pts, 0)
+    x = torch.randn(samples * nodes, 128, generator=g)
+    return pos, x, g
+
+
+def in_state_dict():
+    from magnet_b200 import synthetic as S
+    from magnet_b200.magnet_gnn import InteractionNetwork
+    m = InteractionNetwork(128, 128, 128, 128, 4, 128)
+    return S.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 5)
+
+
+def in_config(env, samples, nodes, E=None):
+    return {"workload": "MAgNet[GNN] InteractionNetwork (edge MLP 384->128x4->128 + LayerNorm, mean at the unsorted row, node MLP) on the "
+                        "stage-3 radius graph (r = 0.08, loop, 32-cap active) of concentrated 2-D meshes, BASELINE configs[2] at test resolution 256",
+            "samples_per_gpu": samples, "nodes_per_sample": nodes, "edges_per_gpu": E, "radius": 0.08,
+            "parallelism": f"samples sharded over {env.world} GPU(s), no data-path collective",
+            "l2": "e_features alone (E x 512 B) exceed the 126 MB L2; no explicit flush"}
+
+
+def cpu_in_layer(threads, nodes=8192, steps=2):
+    from oracle import graph as OG
+    torch.set_num_threads(threads)
+    ns, (kind, how) = ref_modules()
+    pos, x, g = in_workload(1, nodes, 0, "cpu")
+    e = OG.radius_graph(pos, 0.08 * (65536 / nodes) ** 0.5, torch.zeros(nodes, dtype=torch.int64), loop=True, threads=threads)
+    ei = torch.stack([e[1], e[0]])
+    E = ei.shape[1]
+    ef = torch.randn(E, 128, generator=g)
+    m = ns.magnet_gnn.InteractionNetwork(128, 128, 128, 128, 4, 128)
+    m.load_state_dict(in_state_dict(), strict=True)
+    gy = torch.randn(nodes, 128, generator=g)
+
+    def step():
+        xi, ei_ = x.clone().requires_grad_(), ef.clone().requires_grad_()
+        y, _ = m(xi, ei, ei_)
+        y.backward(gy)
+        m.zero_grad(set_to_none=True)
+
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    with torch.no_grad():
+        m(x, ei, ef)
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            m(x, ei, ef)
+        dtf = time.perf_counter() - t1
+    return {"value": E * steps / dt, "unit": "edges/s", "cores": threads, "kind": kind, "forward_only_value": E * steps / dtf,
+            "sample": f"one {nodes}-node sample (radius scaled to the same mean degree; {E} edges), InteractionNetwork fwd+bwd, "
+                      f"{steps} timed steps after 1 warm-up; {how}"}
+
+
+def bench_in_layer(env, clocks=None):
+    from magnet_b200 import graph as MG, functional as MF, synthetic as S
+    from magnet_b200.magnet_gnn import InteractionNetwork
+    args, dev = env.args, env.dev
+    MF.set_precision("fp32_tc" if args.precision == "fp32" else args.precision)
+    pos, x, g = in_workload(IN_SAMPLES, IN_NODES_PER_SAMPLE, 900 + env.rank, dev)
+    pos, x = pos.to(dev), x.to(dev)
+    seg = MG.uniform_segments(IN_SAMPLES, IN_NODES_PER_SAMPLE, dev)
+    ei = MG.radius_graph(pos, 0.08, loop=True, ptr=seg.gptr, swap_rows=True)
+    N, E = x.shape[0], ei.shape[1]
+    plan = MG.plan_for(ei, N)
+    ef_host = torch.randn(E, 128, generator=g).pin_memory()
+    x_host = x.cpu().pin_memory()
+    ef = ef_host.to(dev)
+    layer = InteractionNetwork(128, 128, 128, 128, 4, 128).to(dev)
+    layer.load_state_dict(in_state_dict(), strict=True)
+    gy = torch.randn(N, 128, generator=g).to(dev)
+    steps = max(3, args.steps // 2)
+
+    def fwd():
+        with torch.no_grad():
+            return layer(x, ei, ef, plan=plan, return_e=False)[0]
+
+    def train():
+        xi, ei_ = x.detach().requires_grad_(), ef.detach().requires_grad_()
+        y, _ = layer(xi, ei, ei_, plan=plan, return_e=False)
+        y.backward(gy)
+        layer.zero_grad(set_to_none=True)
+
+    f_ms, f_launch = env.timed(fwd, steps, args.warmup, clocks)
+    k_t, k_c = env.prof(5)
+    t_ms, t_launch = env.timed(train, steps, args.warmup)
+    # e2e (inference): node + edge features from pinned host memory in, aggregated node update out
+    out_host = torch.empty(N, 128).pin_memory()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
+    ee0.record()
+    for _ in range(steps):
+        x.copy_(x_host, non_blocking=True)
+        ef.copy_(ef_host, non_blocking=True)
+        out_host.copy_(fwd(), non_blocking=True)
+    ee1.record()
+    env.barrier()
+    e2e_ms = env.reduce(ee0.elapsed_time(ee1), "max")
+    edges = env.reduce(float(E), "sum")
+    del ef, x, gy
+    torch.cuda.empty_cache()
+    if env.rank != 0:
+        return None
+    hbm, tf, tf_sus, which = _peaks()
+    k_ms = k_t / max(k_c, 1)
+    achieved = IN_FLOP_PER_EDGE_FWD * E / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    traffic, tsrc = _ncu("r02_in_edge_ncu.json")
+    line = base_line(env, "edges/s per MP layer fwd+bwd", "edges/s", edges * steps / (t_ms * 1e-3), t_ms / steps, steps, args.warmup,
+                     "bf16" if args.precision == "bf16" else "f32", in_config(env, IN_SAMPLES, IN_NODES_PER_SAMPLE, E),
+                     clocks=clocks.summary() if clocks else None,
+                     forward_only={"value": edges * steps / (f_ms * 1e-3), "unit": "edges/s", "ms_per_step": f_ms / steps, "gpu_launches": f_launch,
+                                   "note": "rollout / decode path: P|Q Linear + ONE fused edge launch (mgb_in_edge_fwd) + node MLP + LayerNorm"},
+                     e2e={"value": edges * steps / (e2e_ms * 1e-3), "unit": "edges/s (forward)", "h2d_bytes_per_step": (N + E) * 512,
+                          "d2h_bytes_per_step": N * 512, "steps": steps},
+                     gpu_launches=t_launch,
+                     roofline={"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
+                               "frac_of_sustained_peak": achieved / tf_sus if tf_sus else None, "peak_source": which,
+                               "kernel": "in_edge_fwd_tc_kernel", "kernel_ms": k_ms,
+                               "algorithmic_flop_per_edge": IN_FLOP_PER_EDGE_FWD, "executed_flop_per_edge": 5 * 2 * 128 * 128 * (3 if args.precision != "bf16" else 1),
+                               "compulsory_bytes_per_edge": 512 + 12, "achieved_hbm_gbs": (512 + 12) * E / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
+                               "traffic": traffic, "traffic_source": f"profiles/r02_in_edge_ncu.json ({tsrc}); not measured in this run",
+                               "note": "training backward of this layer still runs the row-wise kernels (fp32 FFMA dgrad/wgrad): `value` is "
+                                       "fwd+bwd through autograd, `forward_only` is the fused path"})
+    if env.world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_in_layer(os.cpu_count() or 1)
+    return line
+
+
+# =============================================================================================================
+# inr_decode — BASELINE configs[4] shape
+# =============================================================================================================
+def decode_inputs(Lr, Q, T, seed, dev):
+    from magnet_b200 import synthetic as S
+    g = S._gen(seed)
+    lr_coords = 2 * torch.rand(1, Lr, 2, generator=g) - 1
+    hr_coords = 2 * torch.rand(1, Q, 2, generator=g) - 1
+    enc = torch.randn(1, Lr, 128, generator=g)
+    x_lr = torch.randn(1, T, 1, Lr, generator=g)
+    t = torch.linspace(0, 1, 2 * T)[None]
+    return [v.to(dev) for v in (lr_coords, hr_coords, enc, x_lr, t)]
+
+
+def magnet_model(dev, ns=None, **over):
+    from magnet_b200 import synthetic as S
+    if ns is None:
+        from magnet_b200.magnet_gnn import MAgNetGNN
+        m = MAgNetGNN(magnet_hparams(**over))
+    else:
+        m = ns.magnet_gnn.MAgNetGNN(magnet_hparams(**over))
+    m.load_state_dict(S.seeded_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, 7), strict=True)
+    return m.to(dev).eval()
+
+
+def cpu_inr_decode(threads, Lr=1 << 14, Q=1 << 14, k=4, T=10):
+    torch.set_num_threads(threads)
+    ns, (kind, how) = ref_modules()
+    m = magnet_model("cpu", ns, codec_neighbors=k)
+    lr_coords, hr_coords, enc, x_lr, t = decode_inputs(Lr, Q, T, 500, "cpu")
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        hr = m.projector(m.continuous_decoder(x_lr, enc, lr_coords, hr_coords, t))
+        dt = time.perf_counter() - t0
+    assert hr.shape[0] == Q
+    return {"value": Q / dt, "unit": "query points/s", "cores": threads, "kind": kind,
+            "sample": f"capped: {Q} queries over a {Lr}-node low-res mesh, k = {k}, T = {T}, one call (the reference's brute-force kNN and "
+                      f"Python T x k loop make the full size infeasible); {how}"}
+
+
+def bench_inr_decode(env, clocks=None, Lr=1 << 18, Q=1 << 20, k=4, T=10, cpu=True):
+    from magnet_b200 import functional as MF
+    args, dev = env.args, env.dev
+    MF.set_precision("fp32_tc" if args.precision == "fp32" else args.precision)
+    m = magnet_model(dev, codec_neighbors=k)
+    lr_coords, hr_coords, enc, x_lr, t = decode_inputs(Lr, Q, T, 500 + env.rank, dev)
+    hr_host = hr_coords.cpu().pin_memory()
+    out_host = torch.empty(Q, T).pin_memory()
+    steps = max(3, args.steps // 2)
+
+    def decode():
+        with torch.no_grad():
+            return m.decode_queries(x_lr, enc, lr_coords, hr_coords, t)
+
+    ms, launches = env.timed(decode, steps, args.warmup, clocks)
+    k_t, k_c = env.prof(7)
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
+    ee0.record()
+    for _ in range(steps):
+        hr_coords.copy_(hr_host.reshape(hr_coords.shape), non_blocking=True)
+        out_host.copy_(decode().reshape(Q, T), non_blocking=True)
+    ee1.record()
+    env.barrier()
+    e2e_ms = env.reduce(ee0.elapsed_time(ee1), "max")
+    queries = env.reduce(float(Q), "sum")
+    if env.rank != 0:
+        return None
+    hbm, tf, tf_sus, which = _peaks()
+    flops = INR_FLOP_PER_QUERY_T(k) * T * Q
+    achieved = flops / (ms / steps * 1e-3) / 1e12
+    line = base_line(env, "query points/s, INR decode", "query points/s", queries * steps / (ms * 1e-3), ms / steps, steps, args.warmup,
+                     "bf16" if args.precision == "bf16" else "f32",
+                     {"workload": "MAgNetGNN.continuous_decoder + projector (kNN search, gather, proj_head, blend, 5-layer MLP), BASELINE configs[4] shape",
+                      "queries_per_gpu": Q, "lowres_nodes": Lr, "k": k, "time_steps": T, "interpolation": "area",
+                      "parallelism": f"queries sharded over {env.world} GPU(s), no collective",
+                      "l2": "the query stream (Q x T rows of 512 B through the projector) exceeds the 126 MB L2; no explicit flush"},
+                     clocks=clocks.summary() if clocks else None,
+                     e2e={"value": queries * steps / (e2e_ms * 1e-3), "unit": "query points/s", "h2d_bytes_per_step": Q * 8, "d2h_bytes_per_step": Q * T * 4,
+                          "steps": steps, "result": "hr_points [Q, T] fp32"},
+                     gpu_launches=launches,
+                     roofline={"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
+                               "frac_of_sustained_peak": achieved / tf_sus if tf_sus else None, "peak_source": which,
+                               "kernel": "whole decode call (reference-formulation FLOPs over its CUDA-event time)",
+                               "algorithmic_flop_per_query": INR_FLOP_PER_QUERY_T(k) * T,
+                               "decode_kernel_ms": k_t / max(k_c, 1), "traffic": None})
+    if env.world == 1 and cpu and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_inr_decode(os.cpu_count() or 1, k=k, T=T)
+    return line
+
+
+def run_inr_sweep(env):
+    """BASELINE configs[4]: Q in 1e4..1e8 x k in {4,8,16,32}; queries beyond 2^22 are decoded in chunks of 2^22 (the low-res mesh and its
+    latents stay resident); the CPU reference beside it on a capped problem."""
+    res = {"lowres_nodes": 1 << 18, "time_steps": 10, "rows": []}
+    cpu = {}
+    for k in (4, 8, 16, 32):
+        if env.rank == 0 and env.world == 1:
+            cpu[k] = cpu_inr_decode(os.cpu_count() or 1, Lr=1 << 12, Q=1 << 12, k=k)
+        for q_exp in (4, 5, 6, 7, 8):
+            Q = 10 ** q_exp
+            chunk = min(Q, 1 << 22)
+            env.args.steps, env.args.warmup = 6, 3
+            line = bench_inr_decode(env, None, Q=chunk, k=k, cpu=False)
+            if line is not None:
+                per_gpu = line["value"] / env.world
+                res["rows"].append({"queries": Q, "k": k, "chunk": chunk, "chunks": -(-Q // chunk), "n_gpus": env.world,
+                                    "query_points_per_s": line["value"], "e2e_query_points_per_s": line["e2e"]["value"],
+                                    "seconds_for_Q": Q / per_gpu / env.world, "roofline_frac": line["roofline"]["frac"],
+                                    "cpu_reference_query_points_per_s": cpu.get(k, {}).get("value")})
+                print(json.dumps(res["rows"][-1]), flush=True)
+    if env.rank == 0:
+        res["cpu_reference"] = cpu
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"r02_inr_sweep_n{env.world}.json"), "w"), indent=1)
+
+
+# =============================================================================================================
+# rollout — BASELINE configs[2]
+# =============================================================================================================
+def rollout_flops(B, L, Nq, E1, E3, T=10, k=4):
+    proc = lambda E, N: 5 * (E * IN_FLOP_PER_EDGE_FWD + N * IN_FLOP_PER_NODE_FWD) + (E + N) * ENC_FLOP_PER_ROW
+    return proc(E1, B * L) + proc(E3, B * (L + Nq)) + B * Nq * T * INR_FLOP_PER_QUERY_T(k) + B * (L + Nq) * ENC_FLOP_PER_ROW
+
+
+def cpu_rollout(threads, B=32, L=256, Nq=256):
+    from magnet_b200 import synthetic as S
+    torch.set_num_threads(threads)
+    ns, (kind, how) = ref_modules()
+    m = magnet_model("cpu", ns)
+    b = S.implicit_batch(B=B, L=L, Nq=Nq, nt=50, d=2, kind="concentrated", seed=600)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        m.validation_step(b, 0)
+        dt = time.perf_counter() - t0
+    return {"value": 4 / dt, "unit": "rollout steps/s", "cores": threads, "kind": kind,
+            "sample": f"one validation_step (4 autoregressive steps) at the full shape B = {B}, L = Nq = {L}, no warm-up; {how}"}
+
+
+def bench_rollout(env, clocks=None, B=32, L=256, Nq=256, cpu=True):
+    from magnet_b200 import synthetic as S, functional as MF
+    args, dev = env.args, env.dev
+    MF.set_precision("fp32_tc" if args.precision == "fp32" else args.precision)
+    m = magnet_model(dev)
+    bh = {k: v.pin_memory() for k, v in S.implicit_batch(B=B, L=L, Nq=Nq, nt=50, d=2, kind="concentrated", seed=600 + env.rank).items()}
+    b = {k: v.to(dev) for k, v in bh.items()}
+    steps = max(3, args.steps // 2)
+
+    def run(batch=b):
+        with torch.no_grad():
+            return m.rollout(batch, teacher_forcing=False)[0]
+
+    ms, launches = env.timed(run, steps, args.warmup, clocks)
+    pred = run()
+    out_host = torch.empty(pred.shape).pin_memory()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
+    ee0.record()
+    for _ in range(steps):
+        # host batch in (the coordinate tensors keep their identity so that the cached graphs stay valid: same meshes, new fields)
+        for k in ("lr_frames", "hr_points", "t"):
+            b[k].copy_(bh[k], non_blocking=True)
+        out_host.copy_(run(), non_blocking=True)
+    ee1.record()
+    env.barrier()
+    e2e_ms = env.reduce(ee0.elapsed_time(ee1), "max")
+    total_steps = env.reduce(4.0 * steps, "sum")
+    if env.rank != 0:
+        return None
+    hbm, tf, tf_sus, which = _peaks()
+    with torch.no_grad():
+        u = b["lr_frames"][:, :10].permute(0, 3, 1, 2).reshape(B, L, -1)
+        E1 = m._build_graph(u, b["coords_lr"], b["t"][:, :10])[1].shape[1]
+        allc = m._all_coords(b["coords_lr"], b["coords_hr"])
+        E3 = m._build_graph(torch.cat([u, u[:, :Nq]], 1), allc, b["t"][:, :10])[1].shape[1]
+    fl = rollout_flops(B, L, Nq, E1, E3)
+    achieved = fl * 4 * steps / (ms * 1e-3) / 1e12
+    line = base_line(env, "rollout steps/s", "rollout steps/s", total_steps / (ms * 1e-3), ms / (4 * steps), steps, args.warmup,
+                     "bf16" if args.precision == "bf16" else "f32",
+                     {"workload": "MAgNet[GNN] validation rollout (encode LR graph, INR decode, LR u HR graph, 10 InteractionNetwork layers; "
+                                  "4 autoregressive steps per rollout), BASELINE configs[2]",
+                      "batch_per_gpu": B, "lowres_nodes": L, "query_points": Nq, "time_slice": 10, "radius": 0.08, "edges_stage1": E1, "edges_stage3": E3,
+                      "parallelism": f"one batch per GPU on {env.world} GPU(s), no collective", "step": "one MAgNetGNN.forward over the batch",
+                      "l2": "the per-step working set fits the 126 MB L2 at this shape (the reference's training shape): launch-bound regime"},
+                     clocks=clocks.summary() if clocks else None,
+                     e2e={"value": total_steps / (e2e_ms * 1e-3), "unit": "rollout steps/s",
+                          "h2d_bytes_per_step": sum(bh[k].numel() * 4 for k in ("lr_frames", "hr_points", "t")) // 4,
+                          "d2h_bytes_per_step": pred.numel() * 4 // 4, "steps": steps, "result": "predicted fields [B, T_future, Nq+L, 1]"},
+                     gpu_launches=launches // 4,
+                     roofline={"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
+                               "peak_source": which, "kernel": "whole rollout step (reference-formulation FLOPs over its CUDA-event time)",
+                               "algorithmic_flop_per_step": fl, "traffic": None,
+                               "note": "16k-node problem: bounded by launch latency / occupancy, not by the tensor pipe"})
+    if env.world == 1 and cpu and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_rollout(os.cpu_count() or 1, B, L, Nq)
+    return line
+
+
+# =============================================================================================================
+def run_reference(args, env):
+    """--impl reference: the reference's own CPU implementation of the metric, all host threads, rank 0 only."""
+    if env.rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    if args.metric == "in_layer":
+        cb = cpu_in_layer(threads)
+        metric, unit, cfg = "edges/s per MP layer fwd+bwd", "edges/s", in_config(env, IN_SAMPLES, IN_NODES_PER_SAMPLE)
+    elif args.metric == "inr_decode":
+        cb = cpu_inr_decode(threads)
+        metric, unit, cfg = "query points/s, INR decode", "query points/s", {"workload": "continuous_decoder + projector, BASELINE configs[4] shape (capped)"}
+    elif args.metric == "rollout":
+        cb = cpu_rollout(threads)
+        metric, unit, cfg = "rollout steps/s", "rollout steps/s", {"workload": "MAgNet[GNN] validation rollout, BASELINE configs[2]"}
+    else:
+        cb = cpu_mp_layer(1, max(args.steps, 1), min(args.warmup, 1), threads)
+        metric, unit, cfg = "edges/s per MP layer fwd+bwd", "edges/s", mp_config(args.gpus, args.precision)
+    value = cb["value"]
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -474,19 +785,44 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--metric", default="mp_layer", choices=["mp_layer", "in_layer", "inr_decode", "rollout", "inr_sweep", "rollout_res256"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the INR-decode and rollout side metrics")
+    ap.add_argument("--no-extra", action="store_true", help="headline run without the other metrics")
     ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc", "bf16"],
-                    help="edge-kernel arithmetic: fp32 FFMA | tcgen05 bf16 hi/lo split (1e-5 contract) | tcgen05 bf16 (1e-2)")
+                    help="arithmetic of the 128-wide contractions: fp32 FFMA | tcgen05 hi/lo split (1e-5 contract) | tcgen05 bf16 (1e-2)")
     args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    env = Env(args)
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, env)
         return
-    run_ours(args, rank, world, local_rank)
+    env.init_gpu()
+    import torch.distributed as dist
+    if args.metric == "inr_sweep":
+        run_inr_sweep(env)
+    else:
+        with ClockSampler(env.local_rank) as clocks:
+            if args.metric == "mp_layer":
+                line = bench_mp_layer(env, clocks)
+                if not args.no_extra:
+                    others = {}
+                    for name, fn in (("in_layer", bench_in_layer), ("inr_decode", bench_inr_decode), ("rollout", bench_rollout)):
+                        with ClockSampler(env.local_rank) as c2:
+                            others[name] = fn(env, c2)
+                    if line is not None:
+                        line["metrics"] = others
+            elif args.metric == "in_layer":
+                line = bench_in_layer(env, clocks)
+            elif args.metric == "inr_decode":
+                line = bench_inr_decode(env, clocks)
+            elif args.metric == "rollout_res256":
+                line = bench_rollout(env, clocks, B=1, L=32768, Nq=32768, cpu=False)
+            else:
+                line = bench_rollout(env, clocks)
+        if env.rank == 0:
+            print(json.dumps(line), flush=True)
+    if env.world > 1 and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -146,6 +146,13 @@ int mgb_mlp_chain_pack_layer(const float* W, int ldw, int out_features, const fl
                              float* packed, void* stream);
 int mgb_mlp_chain_fwd(const float* x, int ldx, int64_t rows, int n_layers, const float* packed, int act, int in_act,
                       int n_out, float* y, int ldy, void* stream);
+/* The same backward on the tensor cores, for out_features == 128 and in_features 128 or 256 (the workspace query returns 0
+ * for anything else): dx through the weight images of mgb_linear_tc_pack read MN-major, dW and db in one split-K launch with
+ * TMEM-resident accumulators.  precision 1 (bf16 hi/lo split; gradients span too many binades for the fp16 split) or 2 (bf16). */
+size_t mgb_linear_tc_bwd_workspace(int64_t rows, int in_features, int out_features);
+int mgb_linear_tc_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features, int out_features,
+                      const float* packed, float* dx, float* dw, float* db, int accumulate_params, int precision, void* workspace,
+                      size_t workspace_bytes, void* stream);
 size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features);
 /* dx = (dy * act'(y_pre)) W;  dW (+)= (dy * act'(y_pre))^T x;  db (+)= colsum.  dx may be NULL. */
 int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features,

@@ -254,6 +254,45 @@ int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
     return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, STREAM(stream));
 }
 
+// ---- backward of nn.Linear (+ activation) on the tensor cores: data gradient through the forward's weight images read
+// MN-major (linear_tc.cu), weight + bias gradients in one split-K launch (wgrad_tc)
+size_t mgb_linear_tc_bwd_workspace(int64_t rows, int in_features, int out_features) {
+    if (out_features != 128 || (in_features != 128 && in_features != 256)) return 0;
+    return wgrad_tc_workspace(rows) + 1024;
+}
+
+int mgb_linear_tc_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int in_features, int out_features,
+                      const float* packed, float* dx, float* dw, float* db, int accumulate_params, int precision, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+    MGB_REQUIRE(out_features == 128 && (in_features == 128 || in_features == 256), "linear_tc_bwd: unsupported shape %d -> %d", in_features, out_features);
+    MGB_REQUIRE(precision == 1 || precision == 2, "linear_tc_bwd: precision must be 1 (bf16 hi/lo split) or 2 (bf16)");
+    MGB_REQUIRE(act >= 0 && act <= 2 && (act == 0 || y_pre != nullptr), "linear_tc_bwd: an activation needs the saved pre-activation");
+    MGB_REQUIRE(rows >= 0 && rows < ((int64_t)1 << 31), "linear_tc_bwd: row count out of range");
+    if (rows == 0) return MGB_OK;
+    const int nk = in_features / 128;
+    if (dw) {
+        WgradTcArgs w{};
+        w.dy = dy; w.lddy = 128; w.ny = 1; w.y_pre = act ? y_pre : nullptr; w.ldyp = 128; w.y_act = act;
+        w.nx = nk; w.rows = rows;
+        WgradTcOut o[2] = {};
+        for (int i = 0; i < nk; ++i) {
+            w.x[i] = x + 128 * i; w.ldx[i] = in_features; w.x_act[i] = ACT_NONE;
+            o[i].dw = dw + 128 * i; o[i].lddw = in_features; o[i].n_valid = 128; o[i].k_valid = 128; o[i].accumulate = accumulate_params;
+        }
+        w.db[0] = db; w.db_accumulate = accumulate_params;
+        MGB_TRY(launch_wgrad_tc(precision, w, o, workspace, workspace_bytes, STREAM(stream)));
+    }
+    if (dx) {
+        LinTcArgs a{};
+        a.src[0] = dy; a.ld[0] = 128; a.nk = 1; a.pre = act ? y_pre : nullptr; a.ldpre = 128; a.pre_act = act;
+        a.wimg = packed; a.nm = nk; a.a_trans = 1;
+        for (int m = 0; m < nk; ++m) a.tile_of[m][0] = m;
+        a.act = ACT_NONE; a.y = dx; a.ldy = in_features; a.rows = rows; a.n_out = in_features;
+        MGB_TRY(launch_linear_tc(precision, a, STREAM(stream)));
+    }
+    return MGB_OK;
+}
+
 size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features) {
     return wgrad_workspace_bytes((int)rows, out_features, in_features) + 1024;
 }

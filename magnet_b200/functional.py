@@ -155,10 +155,11 @@ class LinearActFn(torch.autograd.Function):
     """y = act(x W^T + b) (+ residual) — nn.Linear followed by Swish/ReLU (models/backbones/mlp.py:24-27)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, act: int, residual: Optional[torch.Tensor], packed=None):
+    def forward(ctx, x, W, b, act: int, residual: Optional[torch.Tensor], packed=None, owner=None):
         y, x2, y_pre = _linear_forward(x, W, b, act, residual, packed, any(ctx.needs_input_grad))
         ctx.save_for_backward(x2, _lib.f32c(W.detach()), y_pre)
         ctx.act, ctx.shape, ctx.has_res = act, x.shape, residual is not None
+        ctx.w_ref, ctx.owner = W, owner          # for the backward's tensor-core weight images (cached on the parameter)
         return y
 
     @staticmethod
@@ -171,12 +172,22 @@ class LinearActFn(torch.autograd.Function):
         dx = _empty((rows, fin), x2) if ctx.needs_input_grad[0] else None
         dW, db = _empty(Wc.shape, x2), _empty((fout,), x2)
         with torch.cuda.device(x2.device):
-            ws = _lib.workspace(L.mgb_linear_bwd_workspace(rows, fin, fout), x2.device)
-            _lib.check(L.mgb_linear_bwd(_lib.ptr(dy2), _lib.ptr(y_pre), ctx.act, _lib.ptr(x2), rows, fin, fout,
-                                        _lib.ptr(Wc), _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db), 0, _lib.ptr(ws),
-                                        ws.numel(), _lib.stream()), "linear_bwd")
+            tc_ws = L.mgb_linear_tc_bwd_workspace(rows, fin, fout) if (_linear_tc and _precision != "fp32" and rows >= 512) else 0
+            if tc_ws:
+                # tensor cores: bf16 hi/lo split of both operands (gradients span too many binades for the fp16 split)
+                prec = 2 if _precision == "bf16" else 1
+                packed = _tc_weight_images(ctx.w_ref, ctx.owner, prec)
+                ws = _lib.workspace(tc_ws, x2.device)
+                _lib.check(L.mgb_linear_tc_bwd(_lib.ptr(dy2), _lib.ptr(y_pre), ctx.act, _lib.ptr(x2), rows, fin, fout, _lib.ptr(packed),
+                                               _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db), 0, prec, _lib.ptr(ws), ws.numel(), _lib.stream()),
+                           "linear_tc_bwd")
+            else:
+                ws = _lib.workspace(L.mgb_linear_bwd_workspace(rows, fin, fout), x2.device)
+                _lib.check(L.mgb_linear_bwd(_lib.ptr(dy2), _lib.ptr(y_pre), ctx.act, _lib.ptr(x2), rows, fin, fout,
+                                            _lib.ptr(Wc), _lib.ptr(dx), _lib.ptr(dW), _lib.ptr(db), 0, _lib.ptr(ws),
+                                            ws.numel(), _lib.stream()), "linear_bwd")
         dres = dy if ctx.has_res else None
-        return (dx.reshape(ctx.shape) if dx is not None else None), dW, db, None, dres, None
+        return (dx.reshape(ctx.shape) if dx is not None else None), dW, db, None, dres, None, None
 
 
 # The 128-wide Linears of MLP / Encoder / Decoder / projector (models/backbones/mlp.py) run on the tensor cores
@@ -196,7 +207,7 @@ def set_linear_tc(on: bool) -> bool:
     return old
 
 
-def _tc_weight_images(W: torch.Tensor, owner: Optional[torch.Tensor] = None):
+def _tc_weight_images(W: torch.Tensor, owner: Optional[torch.Tensor] = None, prec: Optional[int] = None):
     """Swizzled 16-bit (hi | lo) images of W for the tensor-core Linear, or None when the shape is not covered.  Cached on
     the owning parameter object (``owner``; W may be a column slice of it — a slice taken under torch.inference_mode()
     has neither ``_base`` nor a version counter, so callers that slice pass the parameter explicitly), keyed on the slice
@@ -211,7 +222,8 @@ def _tc_weight_images(W: torch.Tensor, owner: Optional[torch.Tensor] = None):
     if owner is None:
         owner = W._base if W._base is not None else W
     cache = owner.__dict__.setdefault("_mgb_tc_images", {})
-    prec = 2 if _precision == "bf16" else _LINEAR_TC_PRECISION
+    if prec is None:
+        prec = 2 if _precision == "bf16" else _LINEAR_TC_PRECISION
     key = (W.storage_offset(), fout, fin, W.stride(0), owner.data_ptr(), prec, torch.cuda.current_stream().cuda_stream)
     hit = cache.get(key)
     version = _lib.ver(owner)
@@ -270,7 +282,7 @@ def linear_act(x, W, b, act: str = "none", residual=None, owner=None):
     if not torch.is_grad_enabled() or not (x.requires_grad or W.requires_grad or b.requires_grad or
                                            (residual is not None and residual.requires_grad)):
         return _linear_forward(x, W, b, ACT[act], residual, packed, False)[0]      # rollout / decode: no autograd node
-    return LinearActFn.apply(x, W, b, ACT[act], residual, packed)
+    return LinearActFn.apply(x, W, b, ACT[act], residual, packed, owner)
 
 
 @_lib.guard

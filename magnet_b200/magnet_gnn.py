@@ -249,12 +249,18 @@ class MAgNetGNN(LightningModule):
 
     # ---- INR decoder ---------------------------------------------------------------------
     def continuous_decoder(self, x_lr, lr_encoded, lr_coords, hr_coords, t):
-        """models/magnet_gnn.py:224-283: z [B*Nq, T, n_chan].  Fused kNN search + gather + proj_head +
-        interpolation of neighbours 0 and 1 (F9) in one kernel (csrc/inr_decode.cu)."""
+        """models/magnet_gnn.py:224-283: z [B*Nq, T, n_chan].  Grid-hashed kNN (csrc/graph.cu), the latent part of proj_head
+        factorised per low-res node (one Linear over the nodes), then gather + relative coordinates + interpolation of
+        neighbours 0 and 1 (F9) per query (csrc/interaction.cu, mgb_inr_decode_fwd)."""
         B, T, _, L = x_lr.shape
         return MF.inr_decode(x_lr.reshape(B, T, L), lr_encoded.reshape(B * L, -1), lr_coords.reshape(B * L, -1),
                              hr_coords.reshape(B * hr_coords.shape[1], -1), t[:, :T], self.proj_head.weight,
                              self.proj_head.bias, B, L, hr_coords.shape[1], self.codec_neighbors, self.interpolation)
+
+    def decode_queries(self, x_lr, lr_encoded, lr_coords, hr_coords, t):
+        """``projector(continuous_decoder(...))`` (models/magnet_gnn.py:338-339) as one call: hr_points [B*Nq, T, 1]."""
+        z = self.continuous_decoder(x_lr, lr_encoded, lr_coords, hr_coords, t)
+        return self.projector(z)
 
     # ---- model ---------------------------------------------------------------------------
     def forward(self, x_lr, lr_coords, hr_coords, t, hr_last):
@@ -266,8 +272,7 @@ class MAgNetGNN(LightningModule):
         nf, ef = self.encoder(nf, ei, ef)
         lr_encoded, _ = self.processor(nf, ei, ef, plan=plan, need_e=False)
 
-        z = self.continuous_decoder(x_lr, lr_encoded, lr_coords, hr_coords, t)
-        hr_points = self.projector(z).reshape(B, N, -1)
+        hr_points = self.decode_queries(x_lr, lr_encoded, lr_coords, hr_coords, t).reshape(B, N, -1)
 
         all_coords = self._all_coords(lr_coords, hr_coords)
         all_feats = torch.cat([u, hr_points], dim=1)

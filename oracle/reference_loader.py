@@ -20,9 +20,30 @@ def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "mpnn_2d.py"))
 
 
+_EXT = ".pyc.bin"
+
+
 def staged() -> bool:
     """oracle/_ref/ holds the byte-compiled reference files (travels to the GPU box, where /root/reference does not exist)."""
-    return os.path.isfile(os.path.join(STAGED_ROOT, "models", "mpnn_2d.pyc"))
+    return os.path.isfile(os.path.join(STAGED_ROOT, "models", "mpnn_2d" + _EXT))
+
+
+class _StagedFinder:
+    """meta-path finder for the staged bytecode: `models.mpnn_2d` -> oracle/_ref/models/mpnn_2d.pyc.bin (sourceless)."""
+
+    @staticmethod
+    def find_spec(fullname, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        rel = os.path.join(STAGED_ROOT, *fullname.split("."))
+        if os.path.isfile(rel + _EXT):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, rel + _EXT)
+            return importlib.util.spec_from_file_location(fullname, rel + _EXT, loader=loader)
+        if os.path.isdir(rel) and fullname.split(".")[0] == "models":
+            spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        return None
 
 
 def load(prefer_staged: bool = False):
@@ -35,9 +56,11 @@ def load(prefer_staged: bool = False):
     else:
         raise RuntimeError(f"reference not found: neither {REFERENCE_ROOT} nor staged bytecode under {STAGED_ROOT} "
                            "(python -m oracle.stage_ref)")
-    for p in (_REPO, _STUBS, root):
+    for p in (_REPO, _STUBS) + ((root,) if root == REFERENCE_ROOT else ()):
         if p not in sys.path:
             sys.path.insert(0, p) if p != root else sys.path.append(p)
+    if root == STAGED_ROOT and not any(f is _StagedFinder for f in sys.meta_path):
+        sys.meta_path.append(_StagedFinder)
     ns = types.SimpleNamespace(root=root, kind="source" if root == REFERENCE_ROOT else "bytecode")
     ns.mlp = importlib.import_module("models.backbones.mlp")
     ns.mpnn = importlib.import_module("models.mpnn")

@@ -2,7 +2,7 @@
 
 The reference is pure Python: "building" it means byte-compiling its model files, from the sources where they
 lie under /root/reference, into oracle/_ref/ (git-ignored, travels with gpurun like the built .so files).  No reference
-SOURCE enters this repository or the snapshot: only CPython bytecode (.pyc, sourceless imports), the analogue of a compiled
+SOURCE enters this repository or the snapshot: only CPython bytecode (.pyc format, sourceless imports through oracle/reference_loader.py), the analogue of a compiled
 reference binary.  The GPU box runs the same image (same CPython), so the bytecode loads there.
 
     python -m oracle.stage_ref            # also run by __graft_entry__.build() when /root/reference is present
@@ -19,6 +19,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = os.environ.get("MAGNET_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(_HERE, "_ref")
+EXT = ".pyc.bin"      # not "*.pyc": snapshot tools drop those; reference_loader imports these files by explicit path
 FILES = ["utils.py", "models/mpnn.py", "models/mpnn_2d.py", "models/magnet_gnn.py", "models/magnet_cnn_2d.py",
          "models/backbones/mlp.py", "models/backbones/edsr.py"]
 
@@ -32,7 +33,7 @@ def stage(force: bool = False) -> str:
         return OUT
     shutil.rmtree(OUT, ignore_errors=True)
     for f in FILES:
-        dst = os.path.join(OUT, f[:-3] + ".pyc")
+        dst = os.path.join(OUT, f[:-3] + EXT)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         # dfile: the path recorded in tracebacks points at the reference tree, not at this repository
         py_compile.compile(os.path.join(REF_ROOT, f), cfile=dst, dfile=os.path.join("reference", f), doraise=True,
