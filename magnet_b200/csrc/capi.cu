@@ -1,5 +1,6 @@
 // magnet_b200 — extern "C" entry points (see include/magnet_b200.h for the contract).
 #include "internal.cuh"
+#include "grid.cuh"
 #include "../../include/magnet_b200.h"
 
 using namespace mgb;
@@ -188,7 +189,7 @@ int mgb_mlp_chain_pack_layer(const float* W, int ldw, int out_features, const fl
                              void* stream) {
     MGB_REQUIRE(n_layers >= 1 && n_layers <= 8 && layer >= 0 && layer < n_layers, "mlp_chain_pack_layer: layer %d of %d", layer, n_layers);
     MGB_REQUIRE(out_features >= 1 && out_features <= 128, "mlp_chain_pack_layer: 1 <= out_features <= 128 (got %d)", out_features);
-    MGB_TRY(pack_weight_tile(W, ldw, out_features, 128, 0, 0, packed + (size_t)layer * 128 * 128, STREAM(stream), 1));
+    MGB_TRY(pack_weight_tmem(W, ldw, out_features, 128, packed + (size_t)layer * 128 * 128, STREAM(stream)));
     float* b = packed + (size_t)n_layers * 128 * 128 + (size_t)layer * 128;
     MGB_CUDA(cudaMemsetAsync(b, 0, 128 * sizeof(float), STREAM(stream)));
     if (bias) MGB_CUDA(cudaMemcpyAsync(b, bias, (size_t)out_features * sizeof(float), cudaMemcpyDeviceToDevice, STREAM(stream)));
@@ -247,6 +248,38 @@ int mgb_in_edge_fwd(const float* e_features, float e_scale, const int32_t* perm,
     }
     return launch_in_edge_fwd(precision, e_features, e_scale, perm, pq, rowptr, dst, src, n_nodes, n_edges, packed, agg, dev_flag,
                               workspace, workspace_bytes, STREAM(stream));
+}
+
+// ---- fused INR decoder (mlp_chain_tc.cu, MODE 1): search + gather + proj_head + blend + projector in one launch
+size_t mgb_inr_decode_fused_workspace(int64_t n_lowres, int n_samples) { return grid_workspace_bytes(n_lowres, n_samples) + 1024; }
+
+int mgb_inr_decode_fused(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
+                         const float* wsmall, int ldw, const int64_t* idx, int k, const int64_t* ptr_x, int n_samples, int64_t n_query,
+                         int nq_per_sample, int L, int T, int d, int mode, int n_layers, const float* packed, int n_out, float* y,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    MGB_REQUIRE(n_layers >= 1 && n_layers <= 8, "inr_decode_fused: 1..8 projector layers (got %d)", n_layers);
+    MGB_REQUIRE(d == 1 || d == 2, "inr_decode_fused: coordinate dimension must be 1 or 2");
+    MlpChainArgs c{};
+    int* dev_flag = nullptr;
+    volatile int* host_flag = f16_range_flag(&dev_flag);
+    if (host_flag && *host_flag) {
+        *host_flag = 0;
+        MGB_REQUIRE(false, "inr_decode_fused: an earlier fp16-split kernel met |x| >= 32768 (fp16 range); use the fp32 path (set_linear_tc(False)) for this data");
+    }
+    c.range_flag = dev_flag;
+    InrFuseArgs& f = c.inr;
+    if (idx == nullptr) {
+        MGB_REQUIRE(ptr_x != nullptr, "inr_decode_fused: the in-kernel search needs the sample offsets of the low-res nodes");
+        GridParams* gp; CellPoint* pts; int32_t* cell_start;
+        MGB_TRY(build_grid_ws(lr_coords, (int64_t)n_samples * L, d, ptr_x, n_samples, 0.f, 2.0f, workspace, workspace_bytes, &gp, &pts,
+                              &cell_start, STREAM(stream)));
+        f.gp = gp; f.pts = pts; f.cell_start = cell_start;
+    }
+    f.idx = idx; f.k = k; f.A = a; f.xlr = xlr; f.lr_coords = lr_coords; f.hr_coords = hr_coords; f.t = t; f.ldt = ldt;
+    f.wsmall = wsmall; f.ldw = ldw; f.n_query = n_query; f.nq_per_sample = nq_per_sample; f.L = L; f.T = T; f.d = d; f.mode = mode;
+    c.rows = n_query * T; c.n_layers = n_layers; c.wimg = packed; c.bias = packed + (size_t)n_layers * 128 * 128;
+    c.act = ACT_RELU; c.in_act = ACT_NONE; c.n_out = n_out; c.y = y; c.ldy = n_out;
+    return launch_inr_decode_fused(c, STREAM(stream));
 }
 
 int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,

@@ -16,19 +16,10 @@
 // cell order, so a warp shares its candidate cells (L1-resident broadcast loads).  All integer /
 // compare work, HBM- and latency-bound: no tensor cores here.
 #include "common.cuh"
+#include "grid.cuh"
 #include <math.h>
 
 namespace mgb {
-
-struct GridParams {      // written by one device thread, read by every later kernel (no host sync)
-    float min_x, min_y;
-    float inv_hx, inv_hy;
-    float hx, hy;
-    int ncx, ncy;
-    int cells_per_sample;
-};
-
-struct __align__(16) CellPoint { float x, y; int idx; int cell; };
 
 __device__ __forceinline__ int float_order_key(float f) {
     int i = __float_as_int(f);
@@ -92,22 +83,6 @@ __global__ void grid_params_kernel(const int* __restrict__ bbox, int d, float h_
     gp->inv_hx = 1.0f / hx; gp->inv_hy = 1.0f / hy;
     gp->ncx = ncx; gp->ncy = ncy;
     gp->cells_per_sample = ncx * ncy;
-}
-
-__device__ __forceinline__ int sample_of(const int64_t* __restrict__ ptr, int n_samples, int64_t i) {
-    int lo = 0, hi = n_samples;                 // largest b with ptr[b] <= i
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (ptr[mid] <= i) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ void cell_coords(const GridParams& gp, float x, float y, int& cx, int& cy) {
-    cx = (int)floorf((x - gp.min_x) * gp.inv_hx);
-    cy = (int)floorf((y - gp.min_y) * gp.inv_hy);
-    cx = max(0, min(cx, gp.ncx - 1));
-    cy = max(0, min(cy, gp.ncy - 1));
 }
 
 __global__ void __launch_bounds__(256)
@@ -299,29 +274,6 @@ int radius_emit(const int32_t* nbr, const int32_t* rowptr, int64_t n, int cap, i
 // ------------------------------------------------------------------------------------------
 // kNN: expanding-ring search over the grid of the x points, per-thread sorted (dist, idx) list
 // ------------------------------------------------------------------------------------------
-template <int K>
-struct BestList {
-    float d[K];
-    int i[K];
-    __device__ __forceinline__ void init() {
-#pragma unroll
-        for (int e = 0; e < K; ++e) { d[e] = 1e10f; i[e] = -1; }
-    }
-    // keeps the K smallest (dist, idx) pairs in ascending order; equal to the reference's stable
-    // insertion over an ascending-index scan (ties: lower index first).
-    __device__ __forceinline__ void push(float dist, int idx, int k) {
-        float cd = dist; int ci = idx;
-#pragma unroll
-        for (int e = 0; e < K; ++e) {
-            if (e < k) {
-                // lexicographic (dist, idx); empty slots are (1e10, -1) and lose to any dist < 1e10
-                bool better = (cd < d[e]) || (cd == d[e] && ci < i[e]);
-                if (better) { float td = d[e]; int ti = i[e]; d[e] = cd; i[e] = ci; cd = td; ci = ti; }
-            }
-        }
-    }
-};
-
 template <int K, int D>
 __global__ void __launch_bounds__(128)
 knn_kernel(const CellPoint* __restrict__ pts, const int32_t* __restrict__ cell_start, const GridParams* __restrict__ gpp,
@@ -332,52 +284,8 @@ knn_kernel(const CellPoint* __restrict__ pts, const int32_t* __restrict__ cell_s
     const GridParams gp = *gpp;
     const float qx = y[q * D], qy = D > 1 ? y[q * D + 1] : 0.f;
     const int b = sample_of(ptr_y, n_samples, q);
-    const int64_t n_in_sample = ptr_x[b + 1] - ptr_x[b];
-    const int sample_base = b * gp.cells_per_sample;
-    int cx, cy;
-    cell_coords(gp, qx, qy, cx, cy);
     BestList<K> best;
-    best.init();
-    const int want = (int)(n_in_sample < (int64_t)k ? n_in_sample : (int64_t)k);
-    int found = 0;
-    const int max_ring = max(gp.ncx, gp.ncy);
-    for (int ring = 0; ring <= max_ring && want > 0; ++ring) {
-        const int x0 = cx - ring, x1 = cx + ring, y0 = D > 1 ? cy - ring : 0, y1 = D > 1 ? cy + ring : 0;
-        for (int yy = max(y0, 0); yy <= min(y1, gp.ncy - 1); ++yy) {
-            const bool edge_row = (D > 1) && (yy == y0 || yy == y1);
-            const int step = edge_row ? 1 : max(x1 - x0, 1);      // interior rows: only the two end columns
-            for (int xx = x0; xx <= x1; xx += step) {
-                if (xx < 0 || xx >= gp.ncx) continue;
-                const int c = sample_base + yy * gp.ncx + xx;
-                const int s = cell_start[c], e = cell_start[c + 1];
-                for (int p = s; p < e; ++p) {
-                    const CellPoint c4 = pts[p];
-                    float ddx = c4.x - qx;
-                    float dist = __fmaf_rn(ddx, ddx, 0.0f);
-                    if (D > 1) { float ddy = c4.y - qy; dist = __fmaf_rn(ddy, ddy, dist); }
-                    ++found;
-                    best.push(dist, c4.idx, k);
-                }
-                if (ring == 0) break;
-            }
-        }
-        if (found >= want) {
-            // distance from the query to the nearest face of the visited block that still has grid beyond it
-            float bd = 3.0e38f;
-            const float m = 2e-3f;    // cell-index rounding margin, in cell units
-            if (x0 > 0)          bd = fminf(bd, qx - (gp.min_x + ((float)x0 + m) * gp.hx));
-            if (x1 < gp.ncx - 1) bd = fminf(bd, (gp.min_x + ((float)(x1 + 1) - m) * gp.hx) - qx);
-            if (D > 1) {
-                if (y0 > 0)          bd = fminf(bd, qy - (gp.min_y + ((float)y0 + m) * gp.hy));
-                if (y1 < gp.ncy - 1) bd = fminf(bd, (gp.min_y + ((float)(y1 + 1) - m) * gp.hy) - qy);
-            }
-            if (bd >= 3.0e38f) break;                              // the block covers the sample's whole grid
-            float kth = 0.f;
-#pragma unroll
-            for (int e = 0; e < K; ++e) if (e == want - 1) kth = best.d[e];
-            if (bd > 0.f && kth < bd * bd * 0.9999f) break;      // strict: an outside point can neither beat nor tie
-        }
-    }
+    knn_query<K, D>(pts, cell_start, gp, qx, qy, b, ptr_x[b + 1] - ptr_x[b], k, best);
 #pragma unroll
     for (int e = 0; e < K; ++e)
         if (e < k) {
@@ -387,6 +295,14 @@ knn_kernel(const CellPoint* __restrict__ pts, const int32_t* __restrict__ cell_s
 }
 
 size_t knn_workspace_bytes(int64_t nx, int n_samples) { return radius_workspace_bytes(nx, n_samples); }
+
+size_t grid_workspace_bytes(int64_t n, int n_samples) { return radius_workspace_bytes(n, n_samples); }
+
+int build_grid_ws(const float* pos, int64_t n, int d, const int64_t* ptr, int n_samples, float h_min, float target_ppc, void* ws_ptr,
+                  size_t ws_bytes, GridParams** gp, CellPoint** pts, int32_t** cell_start, cudaStream_t s) {
+    Workspace ws(ws_ptr, ws_bytes);
+    return build_grid(pos, n, d, ptr, n_samples, h_min, target_ppc, default_max_cells(n, n_samples), ws, gp, pts, cell_start, s);
+}
 
 int knn_search(const float* x, int64_t nx, const float* y, int64_t ny, int d, const int64_t* ptr_x, const int64_t* ptr_y,
                int n_samples, int k, int64_t* out_idx, float* out_dist, void* ws_ptr, size_t ws_bytes, cudaStream_t s) {

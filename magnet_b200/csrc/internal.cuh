@@ -132,6 +132,7 @@ struct WgradTcOut {          // destination of accumulator (y, x): dw[n*lddw + k
     float* dw; int lddw; int n_valid, k_valid; int accumulate;
 };
 int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s, int f16 = 0);
+int pack_weight_tmem(const float* W, int ld, int n_rows, int n_cols, void* out, cudaStream_t s);
 int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s);
 size_t wgrad_tc_workspace(int64_t rows);
 int launch_wgrad_tc(int precision, WgradTcArgs a, const WgradTcOut* outs /*[ny][nx + tail]*/, void* ws, size_t ws_bytes,
@@ -143,10 +144,24 @@ int set_timeline_buffer(long long* p);
 int set_ie_timeline_buffer(long long* p);
 #endif
 // mlp_chain_tc.cu (a whole 128-wide MLP in one launch, forward only)
+struct CellPoint;
+struct GridParams;
+struct InrFuseArgs {                 // fused INR decoder: the rows of the chain are (query, time step) pairs computed in place
+    const CellPoint* pts; const int32_t* cell_start; const GridParams* gp;     // grid of the low-res nodes (grid.cuh), or
+    const int64_t* idx; int k;       // a precomputed neighbour table [Q][k] (then no search)
+    const float* A;                  // [B*L][128] latent part of proj_head per low-res node (+ bias)
+    const float* xlr;                // [B][T][L]
+    const float* lr_coords;          // [B*L][d]
+    const float* hr_coords;          // [Q][d]
+    const float* t; int ldt;         // [B][ldt], first T entries used
+    const float* wsmall; int ldw;    // proj_head.weight + 128: columns input value, relative coordinates, time
+    int64_t n_query; int nq_per_sample, L, T, d, mode;
+};
 struct MlpChainArgs {
+    InrFuseArgs inr;                 // used by the fused decoder only
     const float* x; int ldx; int64_t rows;
     int n_layers;                    // Linear layers, all with 128 inputs; 128 outputs except the last (n_out <= 128)
-    const void* wimg;                // [n_layers][hi | lo] swizzled fp16 images of W_l [out, 128] (zero-padded rows), 64 KB each
+    const void* wimg;                // [n_layers] fp16 hi | lo pairs of W_l [out, 128] in tensor-memory order (pack_weight_tmem), 64 KB each
     const float* bias;               // [n_layers][128], zero-padded
     int act;                         // activation after every layer but the last
     int in_act;                      // activation applied to x on load (0 none, 1 ReLU)
@@ -154,6 +169,7 @@ struct MlpChainArgs {
     int* range_flag;                 // raised when an operand leaves the fp16 range
 };
 int launch_mlp_chain_tc(const MlpChainArgs& a, cudaStream_t s);
+int launch_inr_decode_fused(const MlpChainArgs& a, cudaStream_t s);      // a.inr filled; a.rows = n_query * T
 // in_edge_tc.cu (fused InteractionNetwork edge function: gather + 5-layer MLP + LayerNorm + segmented mean)
 size_t in_edge_fwd_workspace(int64_t n_edges);
 int launch_in_edge_fwd(int precision, const float* e, float e_scale, const int32_t* perm, const float* pq, const int32_t* rowptr,

@@ -52,6 +52,28 @@ __global__ void pack_weight_tile_kernel(const float* __restrict__ W, int ld, int
     }
 }
 
+// The same 128 x 128 block as fp16 hi | lo pairs in the order the weight-loader warps of mlp_chain_tc.cu read it (A operand in
+// tensor memory): 32-bit word j of row m = elements (2j, 2j+1); part (hi, lo) x chunk (j / 32) x w4 ((j % 32) / 4) x m x 4 words,
+// so that thread m's eight 16-byte loads of a chunk are coalesced across the warp.  16384 words = 64 KB per block.
+__global__ void pack_weight_tmem_kernel(const float* __restrict__ W, int ld, int n_rows, int n_cols, uint32_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 128 * 64) return;
+    const int m = idx >> 6, j = idx & 63;
+    const float v0 = (m < n_rows && 2 * j < n_cols) ? W[(int64_t)m * ld + 2 * j] : 0.f;
+    const float v1 = (m < n_rows && 2 * j + 1 < n_cols) ? W[(int64_t)m * ld + 2 * j + 1] : 0.f;
+    uint32_t hi, lo;
+    split2_f16(v0, v1, hi, lo);
+    const int word = (((j >> 5) * 8 + ((j & 31) >> 2)) * 128 + m) * 4 + (j & 3);
+    out[word] = hi;
+    out[8192 + word] = lo;
+}
+
+int pack_weight_tmem(const float* W, int ld, int n_rows, int n_cols, void* out, cudaStream_t s) {
+    pack_weight_tmem_kernel<<<32, 256, 0, s>>>(W, ld, n_rows, n_cols, (uint32_t*)out);
+    MGB_LAUNCH_CHECK();
+    return MGB_OK;
+}
+
 int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s, int f16) {
     pack_weight_tile_kernel<<<64, 256, 0, s>>>(W, ld, n_rows, n_cols, r0, c0, (unsigned char*)img, f16);
     MGB_LAUNCH_CHECK();

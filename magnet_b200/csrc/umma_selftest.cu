@@ -33,12 +33,36 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const UmmaTestArgs t
         umma::mbar_init(&bar, 1);
         umma::fence_barrier_init();
     }
-    if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
     umma::tc_fence_before();
     __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = tmem_base;
-    if (tid == 0) {
+    if (t.a_mn == 2) {
+        // A in tensor memory (TS form): thread m writes row m of A as 64 packed bf16 pairs into columns [128, 192)
+#pragma unroll 1
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                w[j] = __uint_as_float(umma::pack_bf16(t.a[tid * 128 + 2 * (c0 + j)], t.a[tid * 128 + 2 * (c0 + j) + 1]));
+            umma::tmem_st32(tmem + ((uint32_t)(warp * 32) << 16) + 128u + (uint32_t)c0, w);
+        }
+        umma::tc_fence_before();
+        __syncthreads();
+        umma::tc_fence_after();
+    }
+    if (tid == 0 && t.a_mn == 2) {
+        const uint32_t idesc = umma::idesc_bf16(128, 128, 0, t.b_mn);
+        const uint32_t sb = umma::smem_u32(tile_b);
+        const uint32_t lbo = t.lbo_mn ? (uint32_t)t.lbo_mn : 128u * 128u, sbo = t.sbo_mn ? (uint32_t)t.sbo_mn : 1024u;
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            const uint64_t db = t.b_mn ? umma::desc_sw128(sb + k * 2048, lbo, sbo) : umma::desc_kmajor(sb, k);
+            umma::mma_bf16_ts(tmem, tmem + 128u + (uint32_t)(k * 8), db, idesc, k > 0);
+        }
+        umma::mma_commit(&bar);
+    } else if (tid == 0) {
         const uint32_t idesc = umma::idesc_bf16(128, 128, t.a_mn, t.b_mn);
         const uint32_t sa = umma::smem_u32(tile_a), sb = umma::smem_u32(tile_b);
         const uint32_t lbo = t.lbo_mn ? (uint32_t)t.lbo_mn : 128u * 128u, sbo = t.sbo_mn ? (uint32_t)t.sbo_mn : 1024u;
@@ -61,7 +85,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const UmmaTestArgs t
     }
     umma::tc_fence_before();
     __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem, 128);
+    if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 int umma_selftest(const float* a, const float* b, int a_mn, int b_mn, int lbo_mn, int sbo_mn, float* d, cudaStream_t s) {

@@ -238,6 +238,65 @@ def _tc_weight_images(W: torch.Tensor, owner: Optional[torch.Tensor] = None, pre
 
 
 @_lib.guard
+def _chain_packed(linears, cache_owner, device):
+    """fp16 hi | lo weight images + biases of a 128-wide Linear chain (mgb_mlp_chain_pack_layer), cached on ``cache_owner``
+    keyed on the version counters of the parameters."""
+    L = _lib.lib()
+    nl = len(linears)
+    key = tuple((l.weight.data_ptr(), _lib.ver(l.weight), l.bias.data_ptr(), _lib.ver(l.bias)) for l in linears) + \
+        (torch.cuda.current_stream().cuda_stream,)
+    store = cache_owner.__dict__ if cache_owner is not None else None
+    hit = store.get("_mgb_chain") if store is not None else None
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    packed = torch.empty(L.mgb_mlp_chain_packed_floats(nl), dtype=torch.float32, device=device)
+    for i, l in enumerate(linears):
+        W, b = l.weight.detach(), l.bias.detach()
+        if W.stride(1) != 1:
+            W = W.contiguous()
+        _lib.check(L.mgb_mlp_chain_pack_layer(_lib.ptr(W), W.stride(0), l.out_features, _lib.ptr(b.contiguous()), i, nl,
+                                              _lib.ptr(packed), _lib.stream()), "mlp_chain_pack_layer")
+    if store is not None:
+        store["_mgb_chain"] = (key, packed)
+    return packed
+
+
+def _chain_ok(linears) -> bool:
+    return (1 <= len(linears) <= 8 and all(l.in_features == 128 for l in linears) and all(l.out_features == 128 for l in linears[:-1])
+            and linears[-1].out_features <= 128)
+
+
+def inr_decode_fusable(x_lr, lr_encoded, wp, linears) -> bool:
+    """The fused decoder covers the reference configuration (latent_dim = n_chan = mlp_hidden = 128, ReLU projector) on the
+    fp16-split tensor-core arithmetic, forward only."""
+    return (_linear_tc and _precision == "fp32_tc" and x_lr.is_cuda and lr_encoded.shape[-1] == 128 and wp.shape[0] == 128
+            and _chain_ok(linears) and _no_grad_needed(x_lr, lr_encoded, wp, *[p for l in linears for p in (l.weight, l.bias)]))
+
+
+@_lib.guard
+def inr_decode_fused(xlr, lr_encoded, lr_coords, hr_coords, t, wp, bp, linears, B, L_, nq, k, interpolation, cache_owner=None, idx=None):
+    """projector(continuous_decoder(...)) (models/magnet_gnn.py:338-339) in one launch plus the per-node Linear for the latent
+    part of proj_head: xlr [B,T,L], lr_encoded [B*L,128], lr_coords [B*L,d], hr_coords [B*nq,d], t [B,>=T] -> [B*nq, T, n_out].
+    ``idx`` None: the nearest low-res nodes are searched inside the kernel."""
+    from . import graph as MG
+    Lb = _lib.lib()
+    T, d = xlr.shape[1], lr_coords.shape[1]
+    xlr, lr_coords, hr_coords, t = (_lib.f32c(v) for v in (xlr, lr_coords, hr_coords, t))
+    a = linear_act(lr_encoded, wp[:, :128], bp, "none", owner=wp)
+    wpc = _lib.f32c(wp.detach())
+    packed = _chain_packed(linears, cache_owner, xlr.device)
+    Q = hr_coords.shape[0]
+    n_out = linears[-1].out_features
+    y = _empty((Q * T, n_out), a)
+    ptr_x = MG.uniform_ptr(B, L_, xlr.device) if idx is None else None
+    ws = _lib.workspace(Lb.mgb_inr_decode_fused_workspace(B * L_, B) if idx is None else 0, xlr.device)
+    _lib.check(Lb.mgb_inr_decode_fused(_lib.ptr(a), _lib.ptr(xlr), _lib.ptr(lr_coords), _lib.ptr(hr_coords), _lib.ptr(t), t.shape[1],
+                                       ctypes_offset(wpc, 128), wpc.shape[1], _lib.ptr(idx), k, _lib.ptr(ptr_x), B, Q, nq, L_, T, d,
+                                       INTERP[interpolation], len(linears), _lib.ptr(packed), n_out, _lib.ptr(y), _lib.ptr(ws), ws.numel(),
+                                       _lib.stream()), "inr_decode_fused")
+    return y.reshape(Q, T, n_out)
+
+
 def mlp_chain(x, linears, act: str = "relu", in_act: str = "none", cache_owner=None):
     """Inference forward of ``linears`` (nn.Linear modules: Linear(128,128) + act ... Linear(128, out <= 128)) in one launch
     (mgb_mlp_chain_fwd): the activations never leave the SM between the layers.  Returns None when the shapes or the
@@ -251,22 +310,7 @@ def mlp_chain(x, linears, act: str = "relu", in_act: str = "none", cache_owner=N
         return None
     L = _lib.lib()
     nl = len(linears)
-    key = tuple((l.weight.data_ptr(), _lib.ver(l.weight), l.bias.data_ptr(), _lib.ver(l.bias)) for l in linears) + \
-        (torch.cuda.current_stream().cuda_stream,)
-    store = cache_owner.__dict__ if cache_owner is not None else None
-    hit = store.get("_mgb_chain") if store is not None else None
-    if hit is not None and hit[0] == key:
-        packed = hit[1]
-    else:
-        packed = torch.empty(L.mgb_mlp_chain_packed_floats(nl), dtype=torch.float32, device=x.device)
-        for i, l in enumerate(linears):
-            W, b = l.weight.detach(), l.bias.detach()
-            if W.stride(1) != 1:
-                W = W.contiguous()
-            _lib.check(L.mgb_mlp_chain_pack_layer(_lib.ptr(W), W.stride(0), l.out_features, _lib.ptr(b.contiguous()), i, nl,
-                                                  _lib.ptr(packed), _lib.stream()), "mlp_chain_pack_layer")
-        if store is not None:
-            store["_mgb_chain"] = (key, packed)
+    packed = _chain_packed(linears, cache_owner, x.device)
     shape = x.shape
     x2 = _lib.f32c(x).reshape(-1, 128)
     n_out = linears[-1].out_features

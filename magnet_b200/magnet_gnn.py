@@ -259,6 +259,14 @@ class MAgNetGNN(LightningModule):
 
     def decode_queries(self, x_lr, lr_encoded, lr_coords, hr_coords, t):
         """``projector(continuous_decoder(...))`` (models/magnet_gnn.py:338-339) as one call: hr_points [B*Nq, T, 1]."""
+        lin = self.projector.linears()
+        if self.projector.activation == "relu" and MF.inr_decode_fusable(x_lr, lr_encoded, self.proj_head.weight, lin):
+            # rollout / decode: search + gather + proj_head + blend + projector in ONE launch; z is never materialised
+            B, T, _, L = x_lr.shape
+            return MF.inr_decode_fused(x_lr.reshape(B, T, L), lr_encoded.reshape(B * L, -1), lr_coords.reshape(B * L, -1),
+                                       hr_coords.reshape(B * hr_coords.shape[1], -1), t[:, :T], self.proj_head.weight,
+                                       self.proj_head.bias, lin, B, L, hr_coords.shape[1], self.codec_neighbors,
+                                       self.interpolation, cache_owner=self.projector)
         z = self.continuous_decoder(x_lr, lr_encoded, lr_coords, hr_coords, t)
         return self.projector(z)
 
