@@ -32,6 +32,11 @@ def get_precision() -> str:
     return _precision
 
 
+def precision_key() -> tuple:
+    """Everything that selects kernels globally (part of the key of captured CUDA graphs)."""
+    return (_precision, _linear_tc)
+
+
 def _empty(shape, ref):
     return torch.empty(shape, dtype=torch.float32, device=ref.device)
 

@@ -7,6 +7,7 @@ Deviation (flagged): the reference hard-codes d = 2 (`time_slice+3`, 
 ``hparams.dim`` (default 2), which is what BASELINE config 1 (1-D E1) needs.  For d = 2 the
 parameter shapes are identical to the reference's.
 """
+import os
 import weakref
 from typing import Optional
 
@@ -165,6 +166,30 @@ class Decoder(nn.Module):
         return self.node_fn(x)
 
 
+class _GraphedForward:
+    """One captured ``MAgNetGNN._forward_impl`` (fixed shapes and meshes): static input buffers, the CUDA graph, static outputs."""
+
+    def __init__(self, model, x_lr, lr_coords, hr_coords, t, hr_last):
+        self.lr_ref, self.hr_ref = weakref.ref(lr_coords), weakref.ref(hr_coords)
+        self.inputs = [x_lr.clone(), t.clone(), hr_last.clone()]
+        self.stream = torch.cuda.Stream(device=x_lr.device)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        # the kernel-side caches (packed weights, graphs, plans) are keyed on the stream: warm them up on the capture stream so
+        # that the captured step holds the data path only
+        with torch.cuda.stream(self.stream):
+            model._forward_impl(self.inputs[0], lr_coords, hr_coords, self.inputs[1], self.inputs[2])
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.outputs = model._forward_impl(self.inputs[0], lr_coords, hr_coords, self.inputs[1], self.inputs[2])
+
+    def __call__(self, x_lr, t, hr_last):
+        for dst, src in zip(self.inputs, (x_lr, t, hr_last)):
+            dst.copy_(src)
+        self.graph.replay()
+        return tuple(o.clone() for o in self.outputs)
+
+
 class MAgNetGNN(LightningModule):
     """models/magnet_gnn.py:139-475 (FACTORY key 'magnet_gnn')."""
 
@@ -191,6 +216,12 @@ class MAgNetGNN(LightningModule):
         self.teacher_forcing = hparams.teacher_forcing
         self.noise = hparams.noise
         self.interpolation = hparams.interpolation
+        try:                                     # not a reference hyper-parameter: CUDA-graph replay of inference forwards
+            self.cuda_graph = bool(hparams.cuda_graph)
+        except (AttributeError, KeyError):
+            self.cuda_graph = os.environ.get("MGB_CUDA_GRAPH", "1") != "0"
+        self._graphed = {}
+        self._graph_seen = None
         try:
             self.dim = int(hparams.dim)          # extension: 1-D meshes; absent in the reference config
         except (AttributeError, KeyError):
@@ -272,6 +303,35 @@ class MAgNetGNN(LightningModule):
 
     # ---- model ---------------------------------------------------------------------------
     def forward(self, x_lr, lr_coords, hr_coords, t, hr_last):
+        """models/magnet_gnn.py:312-376.  Inference calls (no autograd) that repeat with the same meshes — every step of a
+        rollout (:442-475) — are captured once into a CUDA graph and replayed: one launch per step instead of ~90."""
+        if self.cuda_graph and not torch.is_grad_enabled() and x_lr.is_cuda and not torch.cuda.is_current_stream_capturing():
+            out = self._forward_graphed(x_lr, lr_coords, hr_coords, t, hr_last)
+            if out is not None:
+                return out
+        return self._forward_impl(x_lr, lr_coords, hr_coords, t, hr_last)
+
+    def _forward_graphed(self, x_lr, lr_coords, hr_coords, t, hr_last):
+        """Replay of the captured forward for this (shapes, mesh tensors, parameter versions, arithmetic mode).  The first
+        sighting of a key runs eagerly (a mesh seen once is not worth a capture); the second captures; later ones replay.
+        Captured against the identity of the coordinate tensors: their cached graphs / plans are baked into the launch."""
+        key = (tuple(x_lr.shape), tuple(t.shape), tuple(hr_last.shape), x_lr.dtype, t.dtype, hr_last.dtype, x_lr.device.index,
+               lr_coords.data_ptr(), _lib.ver(lr_coords), tuple(lr_coords.shape), hr_coords.data_ptr(), _lib.ver(hr_coords),
+               tuple(hr_coords.shape), sum(_lib.ver(p) for p in self.parameters()), MF.precision_key(), self.training)
+        g = self._graphed.get(key)
+        if g is None:
+            if self._graph_seen != key:
+                self._graph_seen = key
+                return None
+            if len(self._graphed) >= 2:
+                self._graphed.clear()
+            g = self._graphed[key] = _GraphedForward(self, x_lr, lr_coords, hr_coords, t, hr_last)
+        if g.lr_ref() is not lr_coords or g.hr_ref() is not hr_coords:
+            del self._graphed[key]
+            return None
+        return g(x_lr, t, hr_last)
+
+    def _forward_impl(self, x_lr, lr_coords, hr_coords, t, hr_last):
         B, T, C, L = x_lr.shape
         N = hr_coords.shape[1]
         T_out = t.shape[1] - T
