@@ -209,6 +209,20 @@ int mgb_in_edge_fwd(const float* e_features, float e_scale, const int32_t* perm,
                     const int32_t* dst, const int32_t* src, int64_t n_nodes, int64_t n_edges, const float* packed, int precision,
                     float* agg, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of the same edge function (autograd through models/magnet_gnn.py:70-90), recompute-based: the forward pass saves
+ * nothing of size [E,128].  Two persistent tcgen05 passes over the edges (upper layers / lower layers; the weight gradients
+ * accumulate in tensor memory, two per pass), see csrc/in_edge_bwd_tc.cu.  Inputs as mgb_in_edge_fwd plus dagg [N,128].
+ *   dpq [N,256]: columns 0..127 = dP (summed by destination, fixed order); columns 128..255 zeroed (dQ = sum of dz0 rows by
+ *                source: mgb_segment_sum_rows over the transposed plan, divided by e_scale);
+ *   dz0 [E,128]: e_scale * d loss / d z0 in COO order (rows of the first Linear's pre-activation): d e_features = dz0 We,
+ *                dWe = dz0^T e_features through mgb_linear_tc_bwd;
+ *   dW [4][128][128], db [4][128]: gradients of edge_fn's Linears 1..4; dgamma, dbeta [128]: LayerNorm affine. */
+size_t mgb_in_edge_bwd_workspace(int64_t n_edges);
+int mgb_in_edge_bwd(const float* dagg, const float* e_features, float e_scale, const int32_t* perm, const float* pq,
+                    const int32_t* rowptr, const int32_t* dst, const int32_t* src, int64_t n_nodes, int64_t n_edges,
+                    const float* packed, int precision, float* dpq, float* dz0, float* dW, float* db, float* dgamma, float* dbeta,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * INR decoder.  Replaces the body of MAgNetGNN.continuous_decoder (models/magnet_gnn.py:254-280) given the
  * neighbour table of mgb_knn (:247).  a [B*L,128] = lr_encoded proj_head.weight[:, :128]^T + proj_head.bias

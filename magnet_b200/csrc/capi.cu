@@ -250,6 +250,24 @@ int mgb_in_edge_fwd(const float* e_features, float e_scale, const int32_t* perm,
                               workspace, workspace_bytes, STREAM(stream));
 }
 
+size_t mgb_in_edge_bwd_workspace(int64_t n_edges) { return in_edge_bwd_workspace(n_edges); }
+
+int mgb_in_edge_bwd(const float* dagg, const float* e_features, float e_scale, const int32_t* perm, const float* pq,
+                    const int32_t* rowptr, const int32_t* dst, const int32_t* src, int64_t n_nodes, int64_t n_edges,
+                    const float* packed, int precision, float* dpq, float* dz0, float* dW, float* db, float* dgamma, float* dbeta,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    int* dev_flag = nullptr;
+    if (precision != 2) {
+        volatile int* host_flag = f16_range_flag(&dev_flag);
+        if (host_flag && *host_flag) {
+            *host_flag = 0;
+            MGB_REQUIRE(false, "in_edge_bwd: an earlier fp16-split kernel met |x| >= 32768 (fp16 range); use the fp32 path (set_linear_tc(False)) for this data");
+        }
+    }
+    return launch_in_edge_bwd(precision, dagg, e_features, e_scale, perm, pq, rowptr, dst, src, n_nodes, n_edges, packed, dpq, dz0, dW,
+                              db, dgamma, dbeta, dev_flag, workspace, workspace_bytes, STREAM(stream));
+}
+
 // ---- fused INR decoder (mlp_chain_tc.cu, MODE 1): search + gather + proj_head + blend + projector in one launch
 size_t mgb_inr_decode_fused_workspace(int64_t n_lowres, int n_samples) { return grid_workspace_bytes(n_lowres, n_samples) + 1024; }
 

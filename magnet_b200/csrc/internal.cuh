@@ -175,6 +175,12 @@ size_t in_edge_fwd_workspace(int64_t n_edges);
 int launch_in_edge_fwd(int precision, const float* e, float e_scale, const int32_t* perm, const float* pq, const int32_t* rowptr,
                        const int32_t* dstv, const int32_t* srcv, int64_t n_nodes, int64_t n_edges, const float* packed, float* agg,
                        int* range_flag, void* ws, size_t ws_bytes, cudaStream_t s);
+// in_edge_bwd_tc.cu (its backward: two recompute passes, weight gradients resident in tensor memory)
+size_t in_edge_bwd_workspace(int64_t n_edges);
+int launch_in_edge_bwd(int precision, const float* dagg, const float* e, float e_scale, const int32_t* perm, const float* pq,
+                       const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv, int64_t n_nodes, int64_t n_edges,
+                       const float* packed, float* dpq, float* dz0, float* dW, float* db, float* dgamma, float* dbeta, int* range_flag,
+                       void* ws, size_t ws_bytes, cudaStream_t s);
 // optim.cu
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
               double weight_decay, int64_t step, double grad_scale, cudaStream_t s);

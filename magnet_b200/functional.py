@@ -566,6 +566,93 @@ def in_edge_fused(x, e_features, e_scale: float, plan: AggregationPlan, packs):
     return agg
 
 
+_fused_training = True
+
+
+def set_fused_training(on: bool) -> bool:
+    """Route MAgNet's InteractionNetwork training step through the fused edge kernels (forward + recompute backward); off: the
+    row-wise kernels with saved [E,128] activations.  Returns the previous setting."""
+    global _fused_training
+    old, _fused_training = _fused_training, bool(on)
+    return old
+
+
+def fused_training() -> bool:
+    return _fused_training
+
+
+def in_edge_trainable(x, e_features, linears) -> bool:
+    """Training: the same fused forward launch plus the recompute-based fused backward (csrc/in_edge_bwd_tc.cu)."""
+    return (_linear_tc and _precision != "fp32" and x.is_cuda and x.dtype == torch.float32 and e_features.dtype == torch.float32
+            and x.dim() == 2 and x.shape[1] == 128 and e_features.dim() == 2 and e_features.shape[1] == 128 and len(linears) == 5
+            and linears[0].in_features == 384 and all(l.out_features == 128 for l in linears)
+            and all(l.in_features == 128 for l in linears[1:]))
+
+
+class InEdgeFn(torch.autograd.Function):
+    """agg = mean_{e -> i} LayerNorm(edge_fn(cat[x_i, x_j, e_scale * e])) given pq = [P | Q] (the node part of the first Linear,
+    computed by the caller through autograd).  Forward: mgb_in_edge_fwd (one launch, nothing of size [E,128] saved);
+    backward: mgb_in_edge_bwd (two recompute passes on the tensor cores) + the by-source sum for dQ + one tensor-core Linear
+    backward for d e_features and dWe."""
+
+    @staticmethod
+    def forward(ctx, pq, e, W0, W1, b1, W2, b2, W3, b3, W4, b4, gamma, beta, e_scale, plan, packed):
+        L = _lib.lib()
+        pq, e = _lib.f32c(pq), _lib.f32c(e)
+        N, E = pq.shape[0], plan.n_edges
+        if plan.n_nodes != N or e.shape[0] != E:
+            raise RuntimeError(f"InEdgeFn: plan is for {plan.n_nodes} nodes / {plan.n_edges} edges, got pq {tuple(pq.shape)}, "
+                               f"e_features {tuple(e.shape)}")
+        prec = 2 if _precision == "bf16" else 3
+        agg = _empty((N, 128), pq)
+        with torch.cuda.device(pq.device):
+            ws = _lib.workspace(L.mgb_in_edge_fwd_workspace(E), pq.device)
+            _lib.check(L.mgb_in_edge_fwd(_lib.ptr(e), float(e_scale), _lib.ptr(plan.perm), _lib.ptr(pq), _lib.ptr(plan.rowptr),
+                                         _lib.ptr(plan.dst), _lib.ptr(plan.src), N, E, _lib.ptr(packed), prec, _lib.ptr(agg),
+                                         _lib.ptr(ws), ws.numel(), _lib.stream()), "in_edge_fwd")
+        ctx.save_for_backward(pq, e, packed, W0)
+        ctx.plan, ctx.e_scale, ctx.prec = plan, float(e_scale), prec
+        return agg
+
+    @staticmethod
+    def backward(ctx, dagg):
+        L = _lib.lib()
+        pq, e, packed, W0 = ctx.saved_tensors
+        plan, e_scale = ctx.plan, ctx.e_scale
+        N, E = pq.shape[0], plan.n_edges
+        dagg = _lib.f32c(dagg)
+        with torch.cuda.device(pq.device):
+            dpq = _empty((N, 256), pq)
+            dz0 = _empty((max(E, 1), 128), pq)
+            dW, db = _empty((4, 128, 128), pq), _empty((4, 128), pq)
+            dgamma, dbeta = _empty((128,), pq), _empty((128,), pq)
+            ws = _lib.workspace(L.mgb_in_edge_bwd_workspace(E), pq.device)
+            _lib.check(L.mgb_in_edge_bwd(_lib.ptr(dagg), _lib.ptr(e), e_scale, _lib.ptr(plan.perm), _lib.ptr(pq), _lib.ptr(plan.rowptr),
+                                         _lib.ptr(plan.dst), _lib.ptr(plan.src), N, E, _lib.ptr(packed), ctx.prec, _lib.ptr(dpq),
+                                         _lib.ptr(dz0), _lib.ptr(dW), _lib.ptr(db), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(ws),
+                                         ws.numel(), _lib.stream()), "in_edge_bwd")
+            del ws
+            de = dW0 = None
+            if E > 0:
+                # dQ[j] = sum of the dz0 rows of the edges leaving j (COO rows grouped by source: the transposed plan)
+                dq = _segment_sum(dz0, 128, plan.rowptr_t, plan.perm_src(), N, False)
+                dpq[:, 128:] = dq * (1.0 / e_scale) if e_scale != 1.0 else dq
+                # d e_features = dz0 We and dWe = dz0^T e_features: one tensor-core Linear backward (x = e, W = We, dy = dz0)
+                prec = 2 if ctx.prec == 2 else 1
+                We = W0.detach()[:, 256:]
+                img = _tc_weight_images(We, W0, prec)
+                need_de = ctx.needs_input_grad[1]
+                de = _empty((E, 128), pq) if need_de else None
+                dWe, dbe = _empty((128, 128), pq), _empty((128,), pq)
+                lws = _lib.workspace(L.mgb_linear_tc_bwd_workspace(E, 128, 128), pq.device)
+                _lib.check(L.mgb_linear_tc_bwd(_lib.ptr(dz0), None, 0, _lib.ptr(e), E, 128, 128, _lib.ptr(img), _lib.ptr(de),
+                                               _lib.ptr(dWe), _lib.ptr(dbe), 0, prec, _lib.ptr(lws), lws.numel(), _lib.stream()),
+                           "linear_tc_bwd")
+                dW0 = torch.zeros_like(W0)
+                dW0[:, 256:] = dWe
+        return (dpq, de, dW0, dW[0], db[0], dW[1], db[1], dW[2], db[2], dW[3], db[3], dgamma, dbeta, None, None, None)
+
+
 INTERP = {"area": 0, "knn": 1, "sph": 2}
 
 

@@ -118,6 +118,19 @@ class InteractionNetwork(nn.Module):
                 self._fused_packs = MF.in_edge_pack(x, lin, self.edge_fn[1])
                 self._fused_key = key
             agg = MF.in_edge_fused(x, e_features, e_scale, plan, self._fused_packs)
+        elif MF.in_edge_trainable(x, e_features, lin) and self.edge_fn[0].activation == "relu" and MF.fused_training():
+            # training: P | Q through autograd, then the fused edge launch with its recompute-based fused backward
+            params = [p for l in lin for p in (l.weight, l.bias)] + [self.edge_fn[1].weight, self.edge_fn[1].bias]
+            key = MF.params_key(params)
+            if getattr(self, "_fused_key", None) != key:
+                self._fused_packs = MF.in_edge_pack(x, lin, self.edge_fn[1])
+                self._fused_key = key
+            W, b = lin[0].weight, lin[0].bias
+            p = MF.linear_act(x, W[:, :h], b, "none", owner=W)
+            q = MF.linear_act(x, W[:, h:2 * h], torch.zeros_like(b), "none", owner=W)
+            agg = MF.InEdgeFn.apply(torch.cat([p, q], dim=1), e_features, W, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias,
+                                    lin[3].weight, lin[3].bias, lin[4].weight, lin[4].bias, self.edge_fn[1].weight,
+                                    self.edge_fn[1].bias, e_scale, plan, self._fused_packs[2])
         else:
             first = lin[0]
             W, b = first.weight, first.bias
