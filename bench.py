@@ -513,6 +513,8 @@ def bench_in_layer(env, clocks=None):
     f_ms, f_launch = env.timed(fwd, steps, args.warmup, clocks)
     k_t, k_c = env.prof(5)
     t_ms, t_launch = env.timed(train, steps, args.warmup)
+    kf_t, kf_c = env.prof(5)            # the forward launches of the training steps
+    kb_t, kb_c = env.prof(6)            # mgb_in_edge_bwd: both recompute passes, per call
     # e2e (inference): node + edge features from pinned host memory in, aggregated node update out
     out_host = torch.empty(N, 128).pin_memory()
     ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -532,8 +534,15 @@ def bench_in_layer(env, clocks=None):
         return None
     hbm, tf, tf_sus, which = _peaks()
     k_ms = k_t / max(k_c, 1)
-    achieved = IN_FLOP_PER_EDGE_FWD * E / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    traffic, tsrc = _ncu("r02_in_edge_ncu.json")
+    kb_ms = kb_t / max(kb_c, 1)
+    # dominant kernels of the training step: the two backward passes.  Algorithmic work = data + weight gradients of the four
+    # 128x128 Linears they cover (2 x 4 x 2*128*128 FLOP per edge); the recompute (7 MMA groups of 15) is overhead by definition.
+    bwd_flop = 2 * 4 * 2 * 128 * 128
+    nterm = 3 if args.precision != "bf16" else 1
+    achieved = bwd_flop * E / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else 0.0
+    step_achieved = 3 * IN_FLOP_PER_EDGE_FWD * E / (t_ms / steps * 1e-3) / 1e12
+    fwd_achieved = IN_FLOP_PER_EDGE_FWD * E / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    traffic, tsrc = _ncu("r02_in_edge_bwd_v1.json")
     line = base_line(env, "edges/s per MP layer fwd+bwd", "edges/s", edges * steps / (t_ms * 1e-3), t_ms / steps, steps, args.warmup,
                      "bf16" if args.precision == "bf16" else "f32", in_config(env, IN_SAMPLES, IN_NODES_PER_SAMPLE, E),
                      clocks=clocks.summary() if clocks else None,
@@ -544,12 +553,20 @@ def bench_in_layer(env, clocks=None):
                      gpu_launches=t_launch,
                      roofline={"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf,
                                "frac_of_sustained_peak": achieved / tf_sus if tf_sus else None, "peak_source": which,
-                               "kernel": "in_edge_fwd_tc_kernel", "kernel_ms": k_ms,
-                               "algorithmic_flop_per_edge": IN_FLOP_PER_EDGE_FWD, "executed_flop_per_edge": 5 * 2 * 128 * 128 * (3 if args.precision != "bf16" else 1),
-                               "compulsory_bytes_per_edge": 512 + 12, "achieved_hbm_gbs": (512 + 12) * E / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
-                               "traffic": traffic, "traffic_source": f"profiles/r02_in_edge_ncu.json ({tsrc}); not measured in this run",
-                               "note": "training backward of this layer still runs the row-wise kernels (fp32 FFMA dgrad/wgrad): `value` is "
-                                       "fwd+bwd through autograd, `forward_only` is the fused path"})
+                               "kernel": "in_edge_bwd_tc_kernel<0> + <1> (the two recompute passes of mgb_in_edge_bwd, one call)", "kernel_ms": kb_ms,
+                               "kernel_share_of_step": kb_ms / (t_ms / steps) if t_ms > 0 else None,
+                               "algorithmic_flop_per_edge": bwd_flop, "executed_flop_per_edge": 15 * 2 * 128 * 128 * nterm,
+                               "executed_tflops": 15 * 2 * 128 * 128 * nterm * E / (kb_ms * 1e-3) / 1e12 if kb_ms > 0 else 0.0,
+                               "compulsory_bytes_per_edge": 2 * 512 + 512 + 12,
+                               "traffic": traffic, "traffic_source": f"profiles/r02_in_edge_bwd_v1.json ({tsrc}): sum of both passes' first captured launches is in the file; not measured in this run",
+                               "forward_kernel": {"kernel": "in_edge_fwd_tc_kernel", "kernel_ms": k_ms, "achieved": fwd_achieved, "frac": fwd_achieved / tf,
+                                                  "algorithmic_flop_per_edge": IN_FLOP_PER_EDGE_FWD, "executed_flop_per_edge": 5 * 2 * 128 * 128 * nterm,
+                                                  "training_launch_ms": kf_t / max(kf_c, 1)},
+                               "whole_step": {"achieved": step_achieved, "frac": step_achieved / tf,
+                                              "algorithmic_flop_per_edge": 3 * IN_FLOP_PER_EDGE_FWD,
+                                              "note": "reference formulation (384-wide first Linear per edge), forward + data + weight gradients, over the whole fwd+bwd step incl. the node MLP"},
+                               "note": "training = fused forward launch + two fused recompute backward passes (weight gradients resident in tensor memory) "
+                                       "+ by-source sum for dQ + one tensor-core Linear backward for d e_features / dWe; nothing of size [E,128] is saved by the forward"})
     if env.world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_in_layer(os.cpu_count() or 1)
     return line
