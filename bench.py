@@ -785,6 +785,117 @@ def bench_rollout(env, clocks=None, B=32, L=256, Nq=256, cpu=True):
 
 
 # =============================================================================================================
+# magnet_train — BASELINE configs[3] (C4): MAgNet[GNN] training, bf16, batch 64 = 8 samples per GPU, batch-sharded, flat
+# gradient all-reduce overlapped with backward.  The mesh size per sample is capped by what 180 GB hold (see config.cap).
+# =============================================================================================================
+C4_SAMPLES_PER_GPU, C4_L, C4_NQ = 8, 16384, 16384
+
+
+def cpu_magnet_train(threads, B=1, L=2048, Nq=2048):
+    from magnet_b200 import synthetic as S
+    torch.set_num_threads(threads)
+    ns, (kind, how) = ref_modules()
+    m = magnet_model("cpu", ns, teacher_forcing=False).train()
+    b = S.implicit_batch(B=B, L=L, Nq=Nq, nt=20, d=2, kind="uniform", seed=700)
+    t0 = time.perf_counter()
+    loss = m.training_step(b, 0)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    with torch.no_grad():
+        u = b["lr_frames"][:, :10].permute(0, 3, 1, 2).reshape(B, L, -1)
+        E1 = m._build_graph(u, b["coords_lr"], b["t"][:, :10])[1].shape[1]
+        E3 = m._build_graph(torch.cat([u, u[:, :Nq]], 1), torch.cat([b["coords_lr"], b["coords_hr"]], 1), b["t"][:, :10])[1].shape[1]
+    return {"value": 5 * (E1 + E3) / dt, "unit": "edges/s", "cores": threads, "kind": kind, "ms_per_step": dt * 1e3,
+            "sample": f"capped: one training step (forward + backward, no optimizer) of the full model on ONE sample with L = Nq = {L} "
+                      f"(radius 0.08: {E1} + {E3} edges), fp32; {how}"}
+
+
+def bench_magnet_train(env, clocks=None):
+    from magnet_b200 import synthetic as S, functional as MF
+    from magnet_b200.optim import FlatAdam, OverlappedFlatAllReduce
+    args, dev = env.args, env.dev
+    MF.set_precision("fp32_tc" if args.precision == "fp32" else args.precision)
+    B, L, Nq = C4_SAMPLES_PER_GPU, C4_L, C4_NQ
+    m = magnet_model(dev, teacher_forcing=False).train()
+    opt = FlatAdam(m.parameters(), lr=1e-5, weight_decay=1e-8)
+    ar = OverlappedFlatAllReduce(opt, env.world, n_buckets=4)
+    bh = {k: v.pin_memory() for k, v in S.implicit_batch(B=B, L=L, Nq=Nq, nt=20, d=2, kind="uniform", seed=700 + env.rank).items()}
+    b = {k: v.to(dev) for k, v in bh.items()}
+    steps = max(3, args.steps // 3)
+    ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    exposed = []
+
+    def step(batch=b):
+        loss = m.training_step(batch, 0)           # one autoregressive step (nt = 20): rollout, both L1 losses
+        loss.backward()                            # bucketed all-reduces leave from the gradient hooks
+        ev_a.record()
+        scale = ar.finish()                        # what is left of the collective: the compute stream waits here
+        ev_b.record()
+        opt.step(grad_scale=scale)
+        opt.zero_grad()
+        exposed.append((ev_a, ev_b))
+        return loss.detach()
+
+    ms, launches = env.timed(step, steps, 2, clocks)
+    torch.cuda.synchronize()
+    exposed_ms = ev_a.elapsed_time(ev_b)          # last step's (events are re-recorded every step)
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+    kb_t, kb_c = env.prof(6)
+    kf_t, kf_c = env.prof(5)
+    loss_host = torch.zeros(1).pin_memory()
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    env.barrier()
+    ee0.record()
+    for _ in range(steps):
+        for k in ("lr_frames", "hr_points", "t"):                      # same meshes (cached graphs), new fields from the host
+            b[k].copy_(bh[k], non_blocking=True)
+        loss_host.copy_(step().reshape(1), non_blocking=True)
+    ee1.record()
+    env.barrier()
+    e2e_ms = env.reduce(ee0.elapsed_time(ee1), "max")
+    with torch.no_grad():
+        u = b["lr_frames"][:, :10].permute(0, 3, 1, 2).reshape(B, L, -1)
+        E1 = m._build_graph(u, b["coords_lr"], b["t"][:, :10])[1].shape[1]
+        E3 = m._build_graph(torch.cat([u, u[:, :Nq]], 1), m._all_coords(b["coords_lr"], b["coords_hr"]), b["t"][:, :10])[1].shape[1]
+    edge_layers = env.reduce(5.0 * (E1 + E3), "sum")
+    exposed_ms = env.reduce(exposed_ms, "max")
+    peak_gb = env.reduce(peak_gb, "max")
+    if env.rank != 0:
+        return None
+    hbm, tf, tf_sus, which = _peaks()
+    fl = 3 * (rollout_flops(B, L, Nq, E1, E3))           # forward + data + weight gradients, reference formulation
+    achieved = fl * steps / (ms * 1e-3) / 1e12
+    n_param = sum(p.numel() for p in m.parameters())
+    line = base_line(env, "edges/s per MP layer fwd+bwd", "edges/s", edge_layers * steps / (ms * 1e-3), ms / steps, steps, 3,
+                     "bf16" if args.precision == "bf16" else "f32",
+                     {"workload": "MAgNet[GNN] full-model training step (encoders, 2 x 5 InteractionNetwork layers, INR decoder, decoder; L1 losses; "
+                                  "flat Adam), synthetic 2-D irregular-uniform meshes, BASELINE configs[3]",
+                      "samples_per_gpu": B, "global_batch": B * env.world, "lowres_nodes": L, "query_points": Nq, "nodes_per_sample": L + Nq,
+                      "edges_stage1": E1, "edges_stage3": E3, "radius": 0.08, "time_slice": 10, "rollout_steps_per_training_step": 1,
+                      "cap": "configs[3] names 1 M-node meshes: at 32 in-edges per node e_features alone are 16 GB per sample and the edge encoder's "
+                             "saved activations ~4x that; the largest power-of-two mesh that trains with 8 samples per GPU in 180 GB is used "
+                             "(the InteractionNetwork layers themselves save 1 KB per node: the limit is the edge encoder, DESIGN.md §7.6)",
+                      "parallelism": f"batch sharded over {env.world} GPU(s); one flat-buffer gradient all-reduce in 4 buckets launched from gradient hooks, overlapped with backward",
+                      "l2": "per-layer working sets (GBs) exceed the 126 MB L2; no explicit flush"},
+                     clocks=clocks.summary() if clocks else None,
+                     train_steps_per_s=steps / (ms * 1e-3) , samples_per_s=env.world * B * steps / (ms * 1e-3),
+                     e2e={"value": edge_layers * steps / (e2e_ms * 1e-3), "unit": "edges/s",
+                          "h2d_bytes_per_step": sum(bh[k].numel() * 4 for k in ("lr_frames", "hr_points", "t")), "d2h_bytes_per_step": 4, "steps": steps,
+                          "result": "the training loss (4 bytes) is the step's result"},
+                     gpu_launches=launches,
+                     allreduce={"bytes": n_param * 4, "buckets": len(ar.buckets), "exposed_ms_last_step": exposed_ms,
+                                "note": "exposed = time the compute stream waits in finish() after backward (CUDA events); the rest of the collective ran under backward"},
+                     peak_memory_gb=peak_gb,
+                     roofline={"bound": "tensor", "achieved": achieved, "peak": tf, "unit": "TFLOP/s", "frac": achieved / tf, "peak_source": which,
+                               "kernel": "whole training step (reference-formulation FLOPs, forward + data + weight gradients, over its CUDA-event time)",
+                               "algorithmic_flop_per_step": fl, "in_edge_bwd_ms_per_call": kb_t / max(kb_c, 1), "in_edge_bwd_calls_per_step": kb_c / max(steps, 1),
+                               "in_edge_fwd_ms_per_call": kf_t / max(kf_c, 1), "traffic": None})
+    if env.world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_magnet_train(os.cpu_count() or 1)
+    return line
+
+
+# =============================================================================================================
 def run_reference(args, env):
     """--impl reference: the reference's own CPU implementation of the metric, all host threads, rank 0 only."""
     if env.rank != 0:
@@ -796,6 +907,9 @@ def run_reference(args, env):
     elif args.metric == "inr_decode":
         cb = cpu_inr_decode(threads)
         metric, unit, cfg = "query points/s, INR decode", "query points/s", {"workload": "continuous_decoder + projector, BASELINE configs[4] shape (capped)"}
+    elif args.metric == "magnet_train":
+        cb = cpu_magnet_train(threads)
+        metric, unit, cfg = "edges/s per MP layer fwd+bwd", "edges/s", {"workload": "MAgNet[GNN] full-model training step, BASELINE configs[3] (capped)"}
     elif args.metric == "rollout":
         cb = cpu_rollout(threads)
         metric, unit, cfg = "rollout steps/s", "rollout steps/s", {"workload": "MAgNet[GNN] validation rollout, BASELINE configs[2]"}
@@ -816,7 +930,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--metric", default="mp_layer", choices=["mp_layer", "in_layer", "inr_decode", "rollout", "inr_sweep", "rollout_res256"])
+    ap.add_argument("--metric", default="mp_layer", choices=["mp_layer", "in_layer", "inr_decode", "rollout", "inr_sweep", "rollout_res256", "magnet_train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline run without the other metrics")
     ap.add_argument("--precision", default="fp32_tc", choices=["fp32", "fp32_tc", "bf16"],
@@ -846,6 +960,8 @@ def main():
                 line = bench_in_layer(env, clocks)
             elif args.metric == "inr_decode":
                 line = bench_inr_decode(env, clocks)
+            elif args.metric == "magnet_train":
+                line = bench_magnet_train(env, clocks)
             elif args.metric == "rollout_res256":
                 line = bench_rollout(env, clocks, B=1, L=32768, Nq=32768, cpu=False)
             else:

@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
     __shared__ __align__(16) float Bs[2][GK][GN];
     const int tid = threadIdx.x;
     const int tm = tid >> 4, tn = tid & 15;
-    const int64_t row0 = (int64_t)blockIdx.y * GM;
-    const int col0 = blockIdx.x * GN;
+    const int64_t row0 = (int64_t)blockIdx.x * GM;      // rows on grid.x: millions of edge rows exceed grid.y's 65,535
+    const int col0 = blockIdx.y * GN;
     const int ar = tid >> 1, ak0 = (tid & 1) * 8;      // A loader: row ar, k offsets ak0..ak0+7
     const int bk = tid >> 4, bc0 = (tid & 15) * 8;     // B loader: k row bk, cols bc0..bc0+7
     float ra[8], rb[8];
@@ -121,7 +121,7 @@ int launch_gemm(const GemmArgs& g, cudaStream_t s) {
     MGB_REQUIRE(!(g.accumulate && g.act != ACT_NONE), "gemm: accumulate with an activation is not supported");
     GemmArgs a = g;
     for (int i = g.a.nseg; i < 4; ++i) { a.a.p[i] = nullptr; a.a.ld[i] = 0; a.a.k[i] = 0; }
-    dim3 grid(ceil_div(g.N, GN), ceil_div(g.M, GM));
+    dim3 grid((unsigned)ceil_div<int64_t>(g.M, GM), ceil_div(g.N, GN));
     gemm_kernel<<<grid, 256, 0, s>>>(a);
     MGB_LAUNCH_CHECK();
     return MGB_OK;

@@ -124,3 +124,103 @@ def allreduce_flat_gradient(opt: FlatAdam, world: int = None) -> float:
     if world > 1:
         dist.all_reduce(opt.flat_grad, op=dist.ReduceOp.SUM)
     return 1.0 / world
+
+
+class OverlappedFlatAllReduce:
+    """The training all-reduce of SURVEY §8e / K12, overlapped with the tail of backward: FlatAdam's flat gradient buffer is cut
+    into ``n_buckets`` contiguous parameter ranges; a post-accumulate hook per parameter counts a bucket down and, when the
+    last gradient of the bucket has been written, launches its sum all-reduce on a side stream behind an event — so every
+    bucket but the one autograd finishes last travels over NVLink while the remaining backward kernels run (what Lightning's
+    DDP does with 25 MB buckets, models/magnet_gnn.py:378-386 + scripts/magnet_gnn/*.sh `--gpus`).  ``finish()`` launches what
+    is left (parameters that received no gradient), makes the compute stream wait for the side stream and returns the
+    ``grad_scale`` for ``FlatAdam.step``.  One collective per bucket on views of the buffer itself: no copies."""
+
+    def __init__(self, opt: FlatAdam, world: int = None, n_buckets: int = 4, group=None):
+        import torch.distributed as dist
+        self.opt, self.group = opt, group
+        self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        params, offs = opt._params, opt._offs
+        total = opt.flat_grad.numel()
+        n_buckets = max(1, min(n_buckets, len(params)))
+        # contiguous parameter ranges of about equal size, in buffer order
+        bounds, target, acc, start = [], total / n_buckets, 0, 0
+        for i, p in enumerate(params):
+            acc += (p.numel() + 3) // 4 * 4
+            if acc >= target * (len(bounds) + 1) and len(bounds) < n_buckets - 1:
+                bounds.append((start, i + 1))
+                start = i + 1
+        bounds.append((start, len(params)))
+        self.buckets = []            # (first param, last param + 1, flat lo, flat hi)
+        for a, b in bounds:
+            if a >= b:
+                continue
+            hi = offs[b] if b < len(params) else total
+            self.buckets.append((a, b, offs[a], hi))
+        self._bucket_of = {}
+        for bi, (a, b, _, _) in enumerate(self.buckets):
+            for i in range(a, b):
+                self._bucket_of[id(params[i])] = bi
+        self._cuda = opt.flat_grad.is_cuda
+        self._side = torch.cuda.Stream(device=opt.flat_grad.device) if self._cuda else None
+        self._left, self._launched, self._works = [], [], []
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in params]
+        self.reset()
+
+    def reset(self):
+        self._left = [b - a for a, b, _, _ in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+
+    def _launch(self, bi):
+        import torch.distributed as dist
+        self._launched[bi] = True
+        if self.world <= 1:
+            return
+        _, _, lo, hi = self.buckets[bi]
+        view = self.opt.flat_grad[lo:hi]
+        if self._cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(ev)
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self._works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _hook(self, p):
+        bi = self._bucket_of.get(id(p))
+        if bi is None or self._launched[bi]:
+            return
+        self._left[bi] -= 1
+        if self._left[bi] == 0:
+            # autograd may have re-created p.grad outside the flat buffer (first step after a set_to_none): FlatAdam.step
+            # copies such gradients in, and a bucket holding one must be reduced after that copy -> leave it to finish()
+            a, b, _, _ = self.buckets[bi]
+            fg = self.opt.flat_grad
+            ok = all(q.grad is not None and q.grad.data_ptr() == fg.data_ptr() + 4 * o
+                     for q, o in zip(self.opt._params[a:b], self.opt._offs[a:b]))
+            if ok:
+                self._launch(bi)
+
+    def finish(self) -> float:
+        """Call after ``loss.backward()``: returns the grad_scale (1 / world) for ``FlatAdam.step``."""
+        opt = self.opt
+        with torch.no_grad():
+            for p, o in zip(opt._params, opt._offs):          # stray gradients into the buffer before the late buckets go out
+                if p.grad is not None and p.grad.data_ptr() != opt.flat_grad.data_ptr() + 4 * o:
+                    opt.flat_grad[o:o + p.numel()].view_as(p).copy_(p.grad)
+                    p.grad = opt.flat_grad[o:o + p.numel()].view_as(p)
+        for bi in range(len(self.buckets)):
+            if not self._launched[bi]:
+                self._launch(bi)
+        if self._cuda and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self._side)
+        for w in self._works:
+            w.wait()
+        self.reset()
+        return 1.0 / self.world
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

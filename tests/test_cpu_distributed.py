@@ -74,3 +74,57 @@ def test_two_rank_gradient_allreduce_matches_single_process(tmp_path):
     want = batch["u"].reshape(6, -1).sum(1, keepdim=True)
     assert torch.equal(r0["gathered"], want) and torch.equal(r1["gathered"], want)
     assert torch.equal(r0["flat"], torch.full((5,), 3.0)) and torch.equal(r1["flat"], r0["flat"]) and r0["scale"] == 0.5
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from magnet_b200.optim import OverlappedFlatAllReduce
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+        params = list(model.parameters())
+
+        class _Flat:          # the part of FlatAdam the all-reduce touches (FlatAdam itself needs CUDA parameters)
+            pass
+        opt, offs, n = _Flat(), [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        opt._params, opt._offs, opt.flat_grad = params, offs, torch.zeros(n)
+        for p, o in zip(params, offs):
+            p.grad = opt.flat_grad[o:o + p.numel()].view_as(p)
+        ar = OverlappedFlatAllReduce(opt, world, n_buckets=3)
+        batch = S.graph_batch(B=6, N=5, nt=6, d=2, seed=3)
+        local = D.shard_batch(batch, rank, world)
+        launched_during_backward = []
+        for step in range(2):                      # twice: the bucket counters reset
+            opt.flat_grad.zero_()
+            model(local["u"].reshape(-1, 6)).pow(2).mean().backward()
+            launched_during_backward.append(list(ar._launched))
+            scale = ar.finish()
+        torch.save({"flat": opt.flat_grad.clone() * scale, "buckets": ar.buckets, "launched": launched_during_backward},
+                   os.path.join(out_dir, f"o{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_overlapped_bucketed_allreduce(tmp_path):
+    """OverlappedFlatAllReduce: every bucket is launched from the gradient hooks during backward, the buckets tile the flat
+    buffer, and the result is the full-batch gradient on both ranks."""
+    world = 2
+    mp.spawn(_overlap_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = torch.load(tmp_path / "o0.pt"), torch.load(tmp_path / "o1.pt")
+    assert torch.equal(r0["flat"], r1["flat"])
+    assert all(all(l) for l in r0["launched"]) and len(r0["launched"]) == 2          # all three buckets left during backward
+    b = r0["buckets"]
+    assert b[0][2] == 0 and all(x[3] == y[2] for x, y in zip(b, b[1:])) and b[-1][3] == r0["flat"].numel()
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    batch = S.graph_batch(B=6, N=5, nt=6, d=2, seed=3)
+    model(batch["u"].reshape(-1, 6)).pow(2).mean().backward()
+    off = 0
+    for p in model.parameters():
+        assert torch.allclose(r0["flat"][off:off + p.numel()].view_as(p), p.grad, rtol=1e-6, atol=1e-8)
+        off += (p.numel() + 3) // 4 * 4
