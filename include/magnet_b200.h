@@ -173,6 +173,21 @@ int mgb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const
                       float* dx, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Temporal-bundling decoder + Euler update of MP-PDE (models/mpnn_2d.py:138-162 `output_mlp`, :196-200; models/mpnn.py:139-162,
+ * :196-200) in one launch per direction:
+ *   out[n, j] = u[n, u_col] + (j + 1) dt * Conv1d(8 -> 1, k2)(act(Conv1d(1 -> 8, k1, stride1)(h[n, None, :])))[j],  j < time_window
+ * h [N, hidden = 128]; w1 = output_mlp[0].weight [8,1,k1], w2 = output_mlp[-1].weight [1,8,k2]; act: 0 none (the 1-D tw = 10
+ * decoder has no Swish, models/mpnn.py:139-142), 2 Swish; dt: DEVICE scalar (the reference derives it from the batch, :317 — no
+ * host sync).  bwd: dh [N,128], du[:, u_col] (row stride lddu; NULL to skip), dw1, db1, dw2, db2 overwritten; fixed-order sums. */
+int mgb_bundling_decoder_fwd(const float* h, int64_t n, int hidden, const float* u, int ldu, int u_col, const float* w1, const float* b1,
+                             int k1, int stride1, const float* w2, const float* b2, int k2, int time_window, int act, const float* dt,
+                             float* out, void* stream);
+size_t mgb_bundling_decoder_bwd_workspace(int64_t n);
+int mgb_bundling_decoder_bwd(const float* h, int64_t n, int hidden, const float* u, int ldu, int u_col, const float* w1, const float* b1,
+                             int k1, int stride1, const float* w2, const float* b2, int k2, int time_window, int act, const float* dt,
+                             const float* dout, float* dh, float* du, int lddu, float* dw1, float* db1, float* dw2, float* db2,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * MAgNet[GNN] InteractionNetwork glue (models/magnet_gnn.py:70-90).  The first Linear of edge_fn is
  * factorised, W [x_i, x_j, e] = P[i] + Q[j] + R[e] with i = edge_index[1] (the aggregation endpoint),

@@ -300,6 +300,31 @@ int mgb_inr_decode_fused(const float* a, const float* xlr, const float* lr_coord
     return launch_inr_decode_fused(c, STREAM(stream));
 }
 
+// ---- temporal-bundling decoder + Euler update (decoder.cu)
+static DecArgs dec_args(const float* h, int64_t n, const float* u, int ldu, int u_col, const float* w1, const float* b1, int k1, int stride1,
+                        const float* w2, const float* b2, int k2, int time_window, int act, const float* dt) {
+    DecArgs a{};
+    a.h = h; a.u = u; a.ldu = ldu; a.u_col = u_col; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.dt = dt;
+    a.k1 = k1; a.s1 = stride1; a.k2 = k2; a.tw = time_window; a.act = act; a.n = n;
+    return a;
+}
+
+int mgb_bundling_decoder_fwd(const float* h, int64_t n, int hidden, const float* u, int ldu, int u_col, const float* w1, const float* b1,
+                             int k1, int stride1, const float* w2, const float* b2, int k2, int time_window, int act, const float* dt,
+                             float* out, void* stream) {
+    return decoder_fwd(dec_args(h, n, u, ldu, u_col, w1, b1, k1, stride1, w2, b2, k2, time_window, act, dt), hidden, out, STREAM(stream));
+}
+
+size_t mgb_bundling_decoder_bwd_workspace(int64_t n) { return decoder_bwd_workspace(n); }
+
+int mgb_bundling_decoder_bwd(const float* h, int64_t n, int hidden, const float* u, int ldu, int u_col, const float* w1, const float* b1,
+                             int k1, int stride1, const float* w2, const float* b2, int k2, int time_window, int act, const float* dt,
+                             const float* dout, float* dh, float* du, int lddu, float* dw1, float* db1, float* dw2, float* db2,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+    return decoder_bwd(dec_args(h, n, u, ldu, u_col, w1, b1, k1, stride1, w2, b2, k2, time_window, act, dt), hidden, dout, dh, du, lddu,
+                       dw1, db1, dw2, db2, workspace, workspace_bytes, STREAM(stream));
+}
+
 int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
                   double eps, double weight_decay, int64_t step, double grad_scale, void* stream) {
     return adam_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, STREAM(stream));

@@ -33,14 +33,10 @@
 namespace mgb {
 
 constexpr int IB_TE = 128;                       // edge positions per tile
-// warps: 0-15 epilogue (thread = channel; warp / 4 = quarter of the tile's positions: one tile is in flight per CTA, so the
-// epilogue between two MMA groups is pure latency — sixteen warps of 32 positions halve it against eight of 64), 16 MMA
-// issue, 17 segment metadata, 18-19 idle (producers start on a warpgroup boundary), 20-27 producers
-constexpr int IB_EPI_WARPS = 16, IB_PROD_WARPS = 8;
-constexpr int IB_MMA_WARP = IB_EPI_WARPS, IB_META_WARP = IB_EPI_WARPS + 1, IB_PROD_WARP0 = IB_EPI_WARPS + 4;
-constexpr int IB_THREADS = (IB_PROD_WARP0 + IB_PROD_WARPS) * 32;      // 896
-constexpr int IB_FLUSH = 32;                     // positions per epilogue warp = granularity of the stored partial sums
-constexpr int IB_Q = 4;                          // quarters of a tile
+constexpr int IB_EPI_WARPS = 8, IB_PROD_WARPS = 8;
+constexpr int IB_MMA_WARP = IB_EPI_WARPS, IB_META_WARP = IB_EPI_WARPS + 1, IB_PROD_WARP0 = IB_EPI_WARPS + 2;
+constexpr int IB_THREADS = (IB_PROD_WARP0 + IB_PROD_WARPS) * 32;      // 576
+constexpr int IB_FLUSH = 64;                     // positions per epilogue warp = granularity of the stored partial sums
 constexpr int IB_DRAIN = 8;                      // tiles between drains of the weight-gradient accumulators
 constexpr int IB_NVEC_A = 5, IB_NVEC_B = 1;      // per-channel vector gradients of pass A (db4, db3, db2, dgamma, dbeta) / B (db1)
 using IbMeta = TileMetaT<IB_TE>;
@@ -68,7 +64,7 @@ struct InEdgeBwdArgs {
     float* part_head;
     float* part_tail;
     float* wpart;              // [grid][2][128][128] partial weight gradients of this pass (zeroed by the launcher)
-    float* vpart;              // [grid][4 quarters][NVEC][128] partial per-channel gradients of this pass
+    float* vpart;              // [grid][2 halves][NVEC][128] partial per-channel gradients of this pass
     int* range_flag;
     int dbg;                   // developer switch (MGB_IB_DEBUG): 1 / 2 / 3 = pass A stores y / dy / dz3 instead of dz2
 };
@@ -125,60 +121,69 @@ __device__ __forceinline__ void ib_store32(unsigned char* xrow, int c0, int n, c
     }
 }
 
-// hidden-layer epilogue of the recompute: h = relu(D + bias) for the 32 positions [c0, c0+32) of this thread -> image (slot)
-// [+ TS copy], returns the ReLU mask of the 32 positions
+// hidden-layer epilogue of the recompute: h = relu(D + bias) for the 64 positions of this thread -> image (slot) [+ TS copy],
+// returns the ReLU mask of the 64 positions
 template <int NSPLIT>
-__device__ __forceinline__ uint32_t ib_relu_epilogue(uint32_t tacc, float bias, unsigned char* slot, int c0, int n, uint32_t ts_base,
-                                                     int* range_flag, bool image) {
+__device__ __forceinline__ uint2 ib_relu_epilogue(uint32_t tacc, float bias, unsigned char* slot, int hf, int n, uint32_t ts_base,
+                                                  int* range_flag, bool image) {
     unsigned char* xrow = slot + n * 128;
+    uint32_t mask[2];
     float vmax = 0.f;
-    float v[32];
-    umma::tmem_ld32(tacc, v);
-    uint32_t m = 0;
+#pragma unroll 1
+    for (int cb = 0; cb < 64; cb += 32) {
+        float v[32];
+        umma::tmem_ld32(tacc + (uint32_t)cb, v);
+        uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const float z = v[i] + bias;
-        m |= (z > 0.f ? 1u : 0u) << i;
-        v[i] = fmaxf(z, 0.f);
-    }
-    if (NSPLIT == 2) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) vmax = fmaxf(vmax, fmaxf(v[i], v[i + 1]));
-    }
-    if (image) {
-        ib_store32<NSPLIT>(xrow, c0, n, v, ts_base);
-    } else {                      // tensor-memory copy only
-        uint32_t th[16], tl[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (NSPLIT == 2) split2_f16(v[2 * j], v[2 * j + 1], th[j], tl[j]);
-            else th[j] = umma::pack_bf16(v[2 * j], v[2 * j + 1]);
+        for (int i = 0; i < 32; ++i) {
+            const float z = v[i] + bias;
+            m |= (z > 0.f ? 1u : 0u) << i;
+            v[i] = fmaxf(z, 0.f);
         }
-        tmem_st16u(ts_base + (uint32_t)(c0 >> 1), th);
-        if (NSPLIT == 2) tmem_st16u(ts_base + 64u + (uint32_t)(c0 >> 1), tl);
+        mask[cb >> 5] = m;
+        if (NSPLIT == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) vmax = fmaxf(vmax, fmaxf(v[i], v[i + 1]));
+        }
+        if (image) {
+            ib_store32<NSPLIT>(xrow, hf * 64 + cb, n, v, ts_base);
+        } else {                      // tensor-memory copy only
+            uint32_t th[16], tl[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (NSPLIT == 2) split2_f16(v[2 * j], v[2 * j + 1], th[j], tl[j]);
+                else th[j] = umma::pack_bf16(v[2 * j], v[2 * j + 1]);
+            }
+            tmem_st16u(ts_base + (uint32_t)((hf * 64 + cb) >> 1), th);
+            if (NSPLIT == 2) tmem_st16u(ts_base + 64u + (uint32_t)((hf * 64 + cb) >> 1), tl);
+        }
     }
     if (ts_base) tmem_wait_st();
     if (NSPLIT == 2 && vmax >= 32768.f && range_flag) *range_flag = 1;
-    return m;
+    return make_uint2(mask[0], mask[1]);
 }
 
-// data-gradient epilogue: dz = D . mask for the 32 positions of this thread -> image (slot), returns the sum over the positions
+// data-gradient epilogue: dz = D . mask for the 64 positions of this thread -> image (slot), returns the sum over the positions
 template <int NSPLIT>
-__device__ __forceinline__ float ib_mask_epilogue(uint32_t tacc, uint32_t mask, unsigned char* slot, int c0, int n, int* range_flag) {
+__device__ __forceinline__ float ib_mask_epilogue(uint32_t tacc, uint2 mask, unsigned char* slot, int hf, int n, int* range_flag) {
     unsigned char* xrow = slot + n * 128;
     float sum = 0.f, vmax = 0.f;
-    float v[32];
-    umma::tmem_ld32(tacc, v);
+#pragma unroll 1
+    for (int cb = 0; cb < 64; cb += 32) {
+        float v[32];
+        umma::tmem_ld32(tacc + (uint32_t)cb, v);
+        const uint32_t m = cb ? mask.y : mask.x;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        v[i] = (mask >> i) & 1u ? v[i] : 0.f;
-        sum += v[i];
-    }
-    if (NSPLIT == 2) {
+        for (int i = 0; i < 32; ++i) {
+            v[i] = (m >> i) & 1u ? v[i] : 0.f;
+            sum += v[i];
+        }
+        if (NSPLIT == 2) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) vmax = fmaxf(vmax, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
+            for (int i = 0; i < 32; i += 2) vmax = fmaxf(vmax, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
+        }
+        ib_store32<NSPLIT>(xrow, hf * 64 + cb, n, v, 0u);
     }
-    ib_store32<NSPLIT>(xrow, c0, n, v, 0u);
     if (NSPLIT == 2 && vmax >= 32768.f && range_flag) *range_flag = 1;
     return sum;
 }
@@ -262,14 +267,11 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
     // [256,384) and [384,512) the two weight-gradient accumulators of the pass (transposed: lane = input k, column = output n)
     const float gs = ib_scale(a.gmax_bits), inv_gs = 1.0f / gs;
 
-    // registers follow the work (setmaxnreg, whole warpgroups; 896 x 72 at launch): epilogue 64, MMA / metadata / padding 40,
-    // producers 104
     if (warp < IB_EPI_WARPS) {
-        umma::reg_dec<64>();
-        // =========================== epilogue: thread = channel n; warp / 4 = quarter q of the tile: positions 32 q .. 32 q + 31 ====
-        const int n = tid & 127, q = warp >> 2, c0 = q * 32;
+        // =========================== epilogue: thread = channel n; warps 0-3 positions 0-63, warps 4-7 positions 64-127 ====
+        const int n = tid & 127, hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t R1 = tmem + lane_base + (uint32_t)c0, R2 = tmem + 128u + lane_base + (uint32_t)c0;
+        const uint32_t R1 = tmem + lane_base + (uint32_t)(hf * 64), R2 = tmem + 128u + lane_base + (uint32_t)(hf * 64);
         const uint32_t TS = tmem + 128u + lane_base;                    // packed operand: columns [0,64) hi, [64,128) lo
         const float b1 = a.bias[128 + n], b2 = a.bias[256 + n], b3 = a.bias[384 + n], b4 = a.bias[512 + n];
         const float gamma = a.gamma[n];
@@ -296,9 +298,9 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             auto dump = [&](uint32_t tacc, float bias) {          // developer switch: h_l of pass A instead of dz2
                 float v[32];
-                for (int cb = 0; cb < 32; cb += 32) {
+                for (int cb = 0; cb < 64; cb += 32) {
                     umma::tmem_ld32(tacc + (uint32_t)cb, v);
-                    for (int i = 0; i < 32; ++i) a.dz2[(tile * IB_TE + c0 + cb + i) * 128 + n] = fmaxf(v[i] + bias, 0.f);
+                    for (int i = 0; i < 32; ++i) a.dz2[(tile * IB_TE + hf * 64 + cb + i) * 128 + n] = fmaxf(v[i] + bias, 0.f);
                 }
             };
             if constexpr (PASS == 0) {
@@ -306,19 +308,19 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                 // h3 -> working tile + tensor memory (A operand of dW4)
                 wait_t0(it);
                 if (a.dbg == 4) dump(R2, 0.f);
-                ib_relu_epilogue<NSPLIT>(R2, 0.f, x_img, c0, n, 0u, a.range_flag, true);
+                ib_relu_epilogue<NSPLIT>(R2, 0.f, x_img, hf, n, 0u, a.range_flag, true);
                 signal();
                 wait_t();
                 if (a.dbg == 5) dump(R1, b1);
-                ib_relu_epilogue<NSPLIT>(R1, b1, x_img, c0, n, 0u, a.range_flag, true);
+                ib_relu_epilogue<NSPLIT>(R1, b1, x_img, hf, n, 0u, a.range_flag, true);
                 signal();
                 wait_t();
                 if (a.dbg == 6) dump(R1, b2);
-                const uint32_t mask2 = ib_relu_epilogue<NSPLIT>(R1, b2, h_img, c0, n, 0u, a.range_flag, true);
+                const uint2 mask2 = ib_relu_epilogue<NSPLIT>(R1, b2, h_img, hf, n, 0u, a.range_flag, true);
                 signal();
                 wait_t();
                 if (a.dbg == 7) dump(R1, b3);
-                const uint32_t mask3 = ib_relu_epilogue<NSPLIT>(R1, b3, x_img, c0, n, TS, a.range_flag, true);
+                const uint2 mask3 = ib_relu_epilogue<NSPLIT>(R1, b3, x_img, hf, n, TS, a.range_flag, true);
                 signal();
                 // ---- y = D + b4: LayerNorm forward statistics and backward, dy -> working tile
                 wait_t();
@@ -333,38 +335,38 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                     dinv[tid] = make_int2(d, __float_as_int(inv));
                 }
 #pragma unroll 1
-                for (int cb = 0; cb < 32; cb += 16) {          // pass 1: y[n][e] -> fp32 staging [e][n] in the working tile
+                for (int cb = 0; cb < 64; cb += 16) {          // pass 1: y[n][e] -> fp32 staging [e][n] in the working tile
+                    const int c0 = hf * 64 + cb;
                     float v[16];
                     umma::tmem_ld16(R1 + (uint32_t)cb, v);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int e = c0 + cb + i;
+                        const int e = c0 + i;
                         *reinterpret_cast<float*>(x_img + e * 512 + ((((n >> 2) ^ (e & 31))) << 4) + (n & 3) * 4) = v[i] + b4;
                         if (a.dbg == 1) a.dz2[(tile * IB_TE + e) * 128 + n] = v[i] + b4;
                     }
                 }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                {                                               // pass 2: four threads per edge (32 channels each)
-                    const int e = tid >> 2, part = tid & 3;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {                                               // pass 2: two threads per edge (64 channels each)
+                    const int e = tid >> 1, part = tid & 1;
                     const unsigned char* row = x_img + e * 512;
                     const int2 di = dinv[e];
                     const float* drow = a.dagg + (int64_t)di.x * 128;
-                    float4 y[8];
+                    float4 y[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {           // (the four parts of an edge and the two edges of a quarter-warp hit 8 distinct 16-byte slots)
-                        const int chunk = part * 8 + ((i ^ (part * 2)) & 7);
+                    for (int i = 0; i < 16; ++i) {
+                        const int chunk = part * 16 + (i ^ (part << 2));
                         y[i] = *reinterpret_cast<const float4*>(row + ((chunk ^ (e & 31)) << 4));
                     }
                     float s = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
+                    for (int i = 0; i < 16; ++i) s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
                     s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
                     const float mean = s * (1.0f / 128.0f);
                     float q = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int chunk = part * 8 + ((i ^ (part * 2)) & 7);
+                    for (int i = 0; i < 16; ++i) {
+                        const int chunk = part * 16 + (i ^ (part << 2));
                         const float4 dg = __ldg(reinterpret_cast<const float4*>(drow) + chunk);
                         const float4 gm = *reinterpret_cast<const float4*>(gam_s + chunk * 4);
                         const float dx = y[i].x - mean, dy = y[i].y - mean, dz = y[i].z - mean, dw = y[i].w - mean;
@@ -376,24 +378,21 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                     q += __shfl_xor_sync(0xffffffffu, q, 1);
                     s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
                     s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-                    q += __shfl_xor_sync(0xffffffffu, q, 2);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
                     const float rstd = 1.0f / sqrtf(q * (1.0f / 128.0f) + 1e-5f);
                     const float inv = __int_as_float(di.y);
                     if (part == 0) stats[e] = make_float4(mean, rstd, s1 * inv * (1.0f / 128.0f), s2 * inv * rstd * (1.0f / 128.0f));
                 }
-                asm volatile("bar.sync 2, 512;" ::: "memory");
+                asm volatile("bar.sync 2, 256;" ::: "memory");
                 {                                               // pass 3: dy from the accumulator, written as the next operand
                     unsigned char* xrow = x_img + n * 128;
                     float vmax = 0.f;
-                    {
-                        constexpr int cb = 0;
+#pragma unroll 1
+                    for (int cb = 0; cb < 64; cb += 32) {
                         float v[32];
                         umma::tmem_ld32(R1 + (uint32_t)cb, v);
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            const int e = c0 + cb + i;
+                            const int e = hf * 64 + cb + i;
                             const float4 st = stats[e];
                             const int2 di = dinv[e];
                             const float dm = __ldg(a.dagg + (int64_t)di.x * 128 + n) * __int_as_float(di.y);
@@ -410,46 +409,52 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
 #pragma unroll
                             for (int i = 0; i < 32; i += 2) vmax = fmaxf(vmax, fmaxf(fabsf(v[i]), fabsf(v[i + 1])));
                         }
-                        ib_store32<NSPLIT>(xrow, c0 + cb, n, v, 0u);
+                        ib_store32<NSPLIT>(xrow, hf * 64 + cb, n, v, 0u);
                     }
                     if (NSPLIT == 2 && vmax >= 32768.f && a.range_flag) *a.range_flag = 1;
                 }
                 signal();
                 // ---- dz3 = (W4^T dy) . [z3 > 0] -> working tile
                 wait_t();
-                acc_v[1] += ib_mask_epilogue<NSPLIT>(R1, mask3, x_img, c0, n, a.range_flag);
+                acc_v[1] += ib_mask_epilogue<NSPLIT>(R1, mask3, x_img, hf, n, a.range_flag);
                 if (a.dbg == 3) {
                     float v[32];
-                    umma::tmem_ld32(R1, v);
-                    for (int i = 0; i < 32; ++i) a.dz2[(tile * IB_TE + c0 + i) * 128 + n] = ((mask3 >> i) & 1u) ? v[i] : 0.f;
+                    for (int cb = 0; cb < 64; cb += 32) {
+                        umma::tmem_ld32(R1 + (uint32_t)cb, v);
+                        for (int i = 0; i < 32; ++i) a.dz2[(tile * IB_TE + hf * 64 + cb + i) * 128 + n] = (((cb ? mask3.y : mask3.x) >> i) & 1u) ? v[i] : 0.f;
+                    }
                 }
                 signal();
                 // ---- dz2 = (W3^T dz3) . [z2 > 0] -> HBM (scaled; aggregation order, whole tiles)
                 wait_t();
                 {
-                    float* out = a.dz2 + (tile * IB_TE + c0) * 128 + n;
+                    float* out = a.dz2 + (tile * IB_TE + hf * 64) * 128 + n;
                     float sum = 0.f;
-                    float v[32];
-                    umma::tmem_ld32(R1, v);
+#pragma unroll 1
+                    for (int cb = 0; cb < 64; cb += 32) {
+                        float v[32];
+                        umma::tmem_ld32(R1 + (uint32_t)cb, v);
+                        const uint32_t m = cb ? mask2.y : mask2.x;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float z = (mask2 >> i) & 1u ? v[i] : 0.f;
-                        sum += z;
-                        if (a.dbg == 0) out[i * 128] = z;
+                        for (int i = 0; i < 32; ++i) {
+                            const float z = (m >> i) & 1u ? v[i] : 0.f;
+                            sum += z;
+                            if (a.dbg == 0) out[(cb + i) * 128] = z;
+                        }
                     }
                     acc_v[2] += sum;
                 }
             } else {
                 // ---- recompute: h0 -> retained tile, h1 -> tensor memory (A operand of dW2)
                 wait_t0(it);
-                const uint32_t mask0 = ib_relu_epilogue<NSPLIT>(R2, 0.f, h_img, c0, n, 0u, a.range_flag, true);
+                const uint2 mask0 = ib_relu_epilogue<NSPLIT>(R2, 0.f, h_img, hf, n, 0u, a.range_flag, true);
                 signal();
                 wait_t();
-                const uint32_t mask1 = ib_relu_epilogue<NSPLIT>(R1, b1, x_img, c0, n, TS, a.range_flag, false);
+                const uint2 mask1 = ib_relu_epilogue<NSPLIT>(R1, b1, x_img, hf, n, TS, a.range_flag, false);
                 signal();
                 // ---- dz1 = (W2^T dz2) . [z1 > 0] -> working tile
                 wait_t();
-                acc_v[0] += ib_mask_epilogue<NSPLIT>(R1, mask1, x_img, c0, n, a.range_flag);
+                acc_v[0] += ib_mask_epilogue<NSPLIT>(R1, mask1, x_img, hf, n, a.range_flag);
                 signal();
                 // ---- dz0 = (W1^T dz1) . [z0 > 0]: unscaled, times e_scale -> HBM in COO order; segmented sum by destination -> dP
                 wait_t();
@@ -460,18 +465,18 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                     const int* rid = rowid + slot * IB_TE;
                     float sum = 0.f;
 #pragma unroll 1
-                    for (int cb = 0; cb < 32; cb += 8) {
-                        const int c1 = c0 + cb;
+                    for (int cb = 0; cb < 64; cb += 8) {
+                        const int c0 = hf * 64 + cb;
                         float v[8];
                         umma::tmem_ld8(R1 + (uint32_t)cb, v);
-                        const uint32_t mb = mask0 >> cb;
+                        const uint32_t mb = ((cb & 32) ? mask0.y : mask0.x) >> (cb & 31);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             v[i] = (mb >> i) & 1u ? v[i] * inv_gs : 0.f;
-                            const int r = rid[c1 + i];
+                            const int r = rid[c0 + i];
                             if (r >= 0) a.dz0[(int64_t)r * 128 + n] = v[i] * a.e_scale;
                         }
-                        uint32_t fm = (M->flushmask[c1 >> 5] >> (c1 & 31)) & 0xffu, todo = 0xffu;
+                        uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 31)) & 0xffu, todo = 0xffu;
                         if (fm == 0) {
                             sum += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
                             continue;
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 if (rng & (1u << i)) part += v[i];
-                            const int pos = c1 + (31 - __clz(low));
+                            const int pos = c0 + (31 - __clz(low));
                             M->out[pos][n] = (sum + part) * M->scale[pos];
                             sum = 0.f;
                             todo &= ~upto;
@@ -502,24 +507,24 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
             if (((it + 1) % IB_DRAIN) == 0 || it + 1 == nt) {
 #pragma unroll 1
                 for (int g = 0; g < 2; ++g) {
-                    const uint32_t acc = tmem + 256u + (uint32_t)(g * 128) + lane_base + (uint32_t)c0;
-                    float* wp = a.wpart + ((size_t)blockIdx.x * 2 + g) * 128 * 128 + (size_t)c0 * 128 + n;
-                    float v[32];
-                    umma::tmem_ld32(acc, v);
+                    const uint32_t acc = tmem + 256u + (uint32_t)(g * 128) + lane_base + (uint32_t)(hf * 64);
+                    float* wp = a.wpart + ((size_t)blockIdx.x * 2 + g) * 128 * 128 + (size_t)(hf * 64) * 128 + n;
+#pragma unroll 1
+                    for (int cb = 0; cb < 64; cb += 32) {
+                        float v[32];
+                        umma::tmem_ld32(acc + (uint32_t)cb, v);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) wp[i * 128] += v[i] * inv_gs;
+                        for (int i = 0; i < 32; ++i) wp[(cb + i) * 128] += v[i] * inv_gs;
+                    }
                 }
                 umma::tc_fence_before();
             }
         }
-        // per-channel gradients of this CTA (four quarters of the positions: four rows)
+        // per-channel gradients of this CTA (two halves of the positions: two rows)
         constexpr int NV = PASS == 0 ? IB_NVEC_A : IB_NVEC_B;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) a.vpart[(((size_t)blockIdx.x * IB_Q + q) * NV + i) * 128 + n] = acc_v[i] * inv_gs;
-    } else if (warp < IB_PROD_WARP0 && warp != IB_MMA_WARP && warp != IB_META_WARP) {
-        umma::reg_dec<40>();          // padding warps of the MMA / metadata warpgroup
+        for (int i = 0; i < NV; ++i) a.vpart[(((size_t)blockIdx.x * 2 + hf) * NV + i) * 128 + n] = acc_v[i] * inv_gs;
     } else if (warp == IB_MMA_WARP) {
-        umma::reg_dec<40>();
         // =========================== MMA issue + weight loads =======================================
         const uint32_t id_kk = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 0) : umma::idesc_bf16(128, 128, 0, 0);   // A K-major,  B K-major
         const uint32_t id_km = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 1) : umma::idesc_bf16(128, 128, 0, 1);   // A K-major,  B MN-major
@@ -624,7 +629,6 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
             }
         }
     } else if (warp == IB_META_WARP) {
-        umma::reg_dec<40>();
         // =========================== pass B: segment metadata + COO rows, one tile ahead ===============================
         if (PASS == 1) {
 #pragma unroll 1
@@ -643,7 +647,6 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
             }
         }
     } else {
-        umma::reg_inc<104>();
         // =========================== producers: layer-0 operand + accumulator initialisation (+ the dz2 tile in pass B) =====
         const int pw = warp - IB_PROD_WARP0;
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
@@ -783,7 +786,7 @@ size_t in_edge_bwd_workspace(int64_t n_edges) {
     const int64_t sub = ceil_div<int64_t>(n_edges > 0 ? n_edges : 1, IB_FLUSH);
     const size_t grid = (size_t)sm_count();
     return align_up((size_t)tiles * IB_TE * 128 * sizeof(float)) + 2 * align_up((size_t)sub * SEG_H * sizeof(float)) +
-           align_up(grid * 4 * 128 * 128 * sizeof(float)) + align_up(grid * IB_Q * (IB_NVEC_A + IB_NVEC_B) * 128 * sizeof(float)) + 1024;
+           align_up(grid * 4 * 128 * 128 * sizeof(float)) + align_up(grid * 2 * (IB_NVEC_A + IB_NVEC_B) * 128 * sizeof(float)) + 1024;
 }
 
 // precision: 2 = plain bf16 (1e-2 contract), anything else = fp16 hi/lo split (1e-5 contract)
@@ -808,7 +811,7 @@ int launch_in_edge_bwd(int precision, const float* dagg, const float* e, float e
     float* part_head = ws.take<float>((size_t)sub * SEG_H);
     float* part_tail = ws.take<float>((size_t)sub * SEG_H);
     float* wpart = ws.take<float>((size_t)grid * 4 * 128 * 128);
-    float* vpart = ws.take<float>((size_t)grid * IB_Q * (IB_NVEC_A + IB_NVEC_B) * 128);
+    float* vpart = ws.take<float>((size_t)grid * 2 * (IB_NVEC_A + IB_NVEC_B) * 128);
     uint32_t* gmax = ws.take<uint32_t>(64);
     MGB_WS_CHECK(ws);
     MGB_CUDA(cudaMemsetAsync(wpart, 0, (size_t)grid * 4 * 128 * 128 * sizeof(float), s));
@@ -828,7 +831,7 @@ int launch_in_edge_bwd(int precision, const float* dagg, const float* e, float e
     a.dagg = dagg; a.gmax_bits = gmax; a.dz2 = dz2; a.dz0 = dz0; a.dpq = dpq; a.part_head = part_head; a.part_tail = part_tail;
     a.range_flag = range_flag;
     { const char* dbg = getenv("MGB_IB_DEBUG"); a.dbg = dbg ? atoi(dbg) : 0; }
-    float* vpart_b = vpart + (size_t)grid * IB_Q * IB_NVEC_A * 128;
+    float* vpart_b = vpart + (size_t)grid * 2 * IB_NVEC_A * 128;
     {
         ProfScope prof(PROF_IN_EDGE_BWD, s);
         a.wpart = wpart; a.vpart = vpart;
@@ -863,13 +866,13 @@ int launch_in_edge_bwd(int precision, const float* dagg, const float* e, float e
     MGB_LAUNCH_CHECK();
     in_edge_partial_reduce_kernel<<<wb, 256, 0, s>>>(wpb + 128 * 128, grid, wstride, 128 * 128, dW);                                    // pass B, acc 1: dW1
     MGB_LAUNCH_CHECK();
-    // per-channel gradients: [grid * 4 quarters][NV][128]
+    // per-channel gradients: [grid * 2 halves][NV][128]
     float* vdst_a[IB_NVEC_A] = {db + 3 * 128, db + 2 * 128, db + 1 * 128, dgamma, dbeta};
     for (int i = 0; i < IB_NVEC_A; ++i) {
-        in_edge_partial_reduce_kernel<<<1, 128, 0, s>>>(vpart + (size_t)i * 128, grid * IB_Q, (size_t)IB_NVEC_A * 128, 128, vdst_a[i]);
+        in_edge_partial_reduce_kernel<<<1, 128, 0, s>>>(vpart + (size_t)i * 128, grid * 2, (size_t)IB_NVEC_A * 128, 128, vdst_a[i]);
         MGB_LAUNCH_CHECK();
     }
-    in_edge_partial_reduce_kernel<<<1, 128, 0, s>>>(vpart_b, grid * IB_Q, (size_t)IB_NVEC_B * 128, 128, db);
+    in_edge_partial_reduce_kernel<<<1, 128, 0, s>>>(vpart_b, grid * 2, (size_t)IB_NVEC_B * 128, 128, db);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }

@@ -27,12 +27,9 @@ namespace mgb {
 
 constexpr int IE_TE = 128;                       // edge positions per tile (MMA N)
 constexpr int IE_L = 5;                          // Linear layers of edge_fn
-// warps: 0-7 epilogue of tile 0 of a pair, 8-15 epilogue of tile 1 (each tile has its own eight warps: the epilogues are the
-// longest stage of the layer chain, and the two tiles' epilogues now run side by side), 16 MMA issue, 17 segment metadata,
-// 18-19 idle (the producers start on a warpgroup boundary: TMEM lane quadrant = warp % 4), 20-27 producers
-constexpr int IE_EPI_WARPS = 16, IE_TILE_EPI_WARPS = 8, IE_PROD_WARPS = 8;
-constexpr int IE_MMA_WARP = IE_EPI_WARPS, IE_META_WARP = IE_EPI_WARPS + 1, IE_PROD_WARP0 = IE_EPI_WARPS + 4;
-constexpr int IE_THREADS = (IE_PROD_WARP0 + IE_PROD_WARPS) * 32;      // 896
+constexpr int IE_EPI_WARPS = 8, IE_PROD_WARPS = 8;
+constexpr int IE_MMA_WARP = IE_EPI_WARPS, IE_META_WARP = IE_EPI_WARPS + 1, IE_PROD_WARP0 = IE_EPI_WARPS + 2;
+constexpr int IE_THREADS = (IE_PROD_WARP0 + IE_PROD_WARPS) * 32;      // 576
 constexpr int IE_FLUSH = 64;                     // positions per epilogue warp = granularity of the stored partial sums
 constexpr int IE_MSLOTS = 4;                     // metadata slots: (pair parity, tile of the pair)
 using IeMeta = TileMetaT<IE_TE>;
@@ -121,7 +118,7 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
     float2* stats = reinterpret_cast<float2*>(metas + IE_MSLOTS);       // [pair parity][tile][128] mean, rstd of every edge
     uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 4 * IE_TE);
     uint64_t* x_full = bars;          // [2] producers -> MMA (layer 0 operand written)
-    // (the tile slots go back to the producers through hardware barriers 5 and 6: a waiting producer issues nothing)
+    // (the tile slots go back to the producers through hardware barriers 3 and 4: a waiting producer issues nothing)
     uint64_t* t_full = bars + 4;      // [2] MMA -> epilogue
     uint64_t* x_ready = bars + 6;     // [2] hidden-layer epilogue -> MMA
     uint64_t* w_bar = bars + 8;
@@ -139,11 +136,11 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
         for (int t = 0; t < 2; ++t) {
             umma::mbar_init(&x_full[t], IE_PROD_WARPS * 32);
             umma::mbar_init(&t_full[t], 1);
-            umma::mbar_init(&x_ready[t], IE_TILE_EPI_WARPS * 32);
+            umma::mbar_init(&x_ready[t], IE_EPI_WARPS * 32);
         }
         for (int s = 0; s < IE_MSLOTS; ++s) {
             umma::mbar_init(&m_full[s], 32);
-            umma::mbar_init(&m_empty[s], IE_TILE_EPI_WARPS * 32);
+            umma::mbar_init(&m_empty[s], IE_EPI_WARPS * 32);
         }
         umma::mbar_init(w_bar, 1);
         umma::mbar_init(w_free, 1);
@@ -155,13 +152,9 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    // registers follow the work (setmaxnreg moves them between whole warpgroups; 896 x 72 at launch): epilogue 64, MMA /
-    // metadata / padding 40, producers 104 (a tile's converted rows wait in registers for the slot)
     if (warp < IE_EPI_WARPS) {
-        umma::reg_dec<64>();
-        // =========================== epilogue: thread = output channel n; tile t of the pair = warp / 8; within a tile warps
-        // 0-3 take positions 0-63, warps 4-7 positions 64-127 ====
-        const int n = tid & 127, hf = (warp >> 2) & 1, t = warp >> 3;
+        // =========================== epilogue: thread = output channel n; warps 0-3 positions 0-63, warps 4-7 64-127 ====
+        const int n = tid & 127, hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float gamma = a.gamma[n], beta = a.beta[n];
         uint32_t tf[2] = {0, 0};        // completed phases of t_full[t]
@@ -173,7 +166,8 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                 // ---- layers 0-3: bias, ReLU, next operand in place (MN-major image [n][e]); layer 0's accumulator was
                 // initialised with P[dst] + Q[src] by the producers (b0 is folded into P)
                 const float bias = l ? a.bias[l * 128 + n] : 0.f;
-                {
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {
                     if (pair * 2 + t >= n_tiles) continue;
                     unsigned char* xrow = x_img + (size_t)t * 2 * TILE_BYTES + n * 128;
                     const uint32_t tacc = tmem + (uint32_t)(((it & 1) * 2 + t) * 128) + lane_base + (uint32_t)(hf * 64);
@@ -225,8 +219,9 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
             // Phase A (both tiles): the LayerNorm statistics go through the operand tile, which is handed back to the producers
             // right after; phase B (both tiles): normalise from TMEM + reduce — overlaps the next pair's first layers.
             const float bias = a.bias[(IE_L - 1) * 128 + n];
-            if (pair * 2 + t >= n_tiles) continue;
-            {
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                if (pair * 2 + t >= n_tiles) continue;
                 unsigned char* xt = x_img + (size_t)t * 2 * TILE_BYTES;
                 const uint32_t tacc = tmem + (uint32_t)(((it & 1) * 2 + t) * 128) + lane_base + (uint32_t)(hf * 64);
                 umma::mbar_wait(&t_full[t], tf[t] & 1);
@@ -246,40 +241,41 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                         *reinterpret_cast<float*>(xt + e * 512 + ((((n >> 2) ^ (e & 31))) << 4) + (n & 3) * 4) = v[i] + bias;
                     }
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + t * 2 + hf) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
                 // pass 2: two threads per edge (64 channels each), exact two-pass mean / variance
                 {
                     const int j = tid & 127;
                     const int e = hf * 64 + (j >> 1), part = j & 1;
                     const unsigned char* row = xt + e * 512;
-                    // (the row is read twice from shared memory instead of being held in 64 registers: 896 threads leave 72 each)
-                    float s = 0.f;
+                    float4 y[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int chunk = part * 16 + (i ^ (part << 2));
-                        const float4 y = *reinterpret_cast<const float4*>(row + ((chunk ^ (e & 31)) << 4));
-                        s += (y.x + y.y) + (y.z + y.w);
+                        y[i] = *reinterpret_cast<const float4*>(row + ((chunk ^ (e & 31)) << 4));
                     }
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) s += (y[i].x + y[i].y) + (y[i].z + y[i].w);
                     s += __shfl_xor_sync(0xffffffffu, s, 1);
                     const float mean = s * (1.0f / 128.0f);
                     float q = 0.f;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const int chunk = part * 16 + (i ^ (part << 2));
-                        const float4 y = *reinterpret_cast<const float4*>(row + ((chunk ^ (e & 31)) << 4));
-                        const float dx = y.x - mean, dy = y.y - mean, dz = y.z - mean, dw = y.w - mean;
+                        const float dx = y[i].x - mean, dy = y[i].y - mean, dz = y[i].z - mean, dw = y[i].w - mean;
                         q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
                     }
                     q += __shfl_xor_sync(0xffffffffu, q, 1);
                     if (part == 0) stats[((it & 1) * 2 + t) * IE_TE + e] = make_float2(mean, 1.0f / sqrtf(q * (1.0f / 128.0f) + 1e-5f));
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + t * 2 + hf) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + hf) : "memory");
                 // the tile slot goes back to the producers (hardware barrier: the waiting side costs no issue slots), which refill
                 // it while phase B runs
-                asm volatile("bar.arrive %0, 512;" ::"r"(5 + t) : "memory");
+                asm volatile("bar.arrive %0, 512;" ::"r"(3 + t) : "memory");
                 if (warp == 0 || warp == 4) IETL(1 + hf, it, IE_L - 1, t, 2);
             }
-            {
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                if (pair * 2 + t >= n_tiles) continue;
                 const int slot = (it & 1) * 2 + t;
                 umma::mbar_wait(&m_full[slot], (it >> 1) & 1);
                 ie_norm_reduce(tmem + (uint32_t)(slot * 128) + lane_base + (uint32_t)(hf * 64), metas + slot, stats + slot * IE_TE, hf, n, bias,
@@ -289,10 +285,7 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                 if (warp == 0 || warp == 4) IETL(1 + hf, it, IE_L - 1, t, 1);
             }
         }
-    } else if (warp < IE_PROD_WARP0 && warp != IE_MMA_WARP && warp != IE_META_WARP) {
-        umma::reg_dec<40>();          // padding warps of the MMA / metadata warpgroup
     } else if (warp == IE_MMA_WARP) {
-        umma::reg_dec<40>();
         // =========================== MMA issue + weight loads =======================================
         const uint32_t id_k = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 0) : umma::idesc_bf16(128, 128, 0, 0);   // layer 0: B K-major
         const uint32_t id_m = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 1) : umma::idesc_bf16(128, 128, 0, 1);   // layers >= 1: B MN-major
@@ -343,7 +336,6 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
             }
         }
     } else if (warp == IE_META_WARP) {
-        umma::reg_dec<40>();
         // =========================== segment metadata, one pair ahead ===============================
 #pragma unroll 1
         for (int it = 0; it < np; ++it) {
@@ -359,7 +351,6 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
             }
         }
     } else {
-        umma::reg_inc<104>();
         // =========================== producers: layer-0 operand, accumulator initialisation, last-layer phase B ==========
         // (a) 16 e_features rows per warp -> fp16 hi | lo K-major image (gathered and converted BEFORE the tile slot is
         //     waited for);  (b) D^T[n][e] := P[dst_e][n] + Q[src_e][n] written straight into the accumulator with tcgen05.st
@@ -455,7 +446,7 @@ __global__ void __launch_bounds__(IE_THREADS, 1) in_edge_fwd_tc_kernel(const InE
                 }
                 if (pw == 0) IETL(3, it, 0, t, 0);
                 if (prev) {
-                    asm volatile("bar.sync %0, 512;" ::"r"(5 + t) : "memory");      // statistics of (it-1, t) written, slot t free
+                    asm volatile("bar.sync %0, 512;" ::"r"(3 + t) : "memory");      // statistics of (it-1, t) written, slot t free
                     umma::tc_fence_after();
                 }
                 if (pw == 0) IETL(3, it, 0, t, 1);

@@ -181,6 +181,22 @@ int launch_in_edge_bwd(int precision, const float* dagg, const float* e, float e
                        const int32_t* rowptr, const int32_t* dstv, const int32_t* srcv, int64_t n_nodes, int64_t n_edges,
                        const float* packed, float* dpq, float* dz0, float* dW, float* db, float* dgamma, float* dbeta, int* range_flag,
                        void* ws, size_t ws_bytes, cudaStream_t s);
+// decoder.cu (temporal-bundling Conv1d decoder + Euler update of MP-PDE, one launch per direction)
+struct DecArgs {
+    const float* h;        // [N][128]
+    const float* u; int ldu, u_col;     // u[:, u_col] = last input value
+    const float* w1;       // [8][k1]
+    const float* b1;       // [8]
+    const float* w2;       // [8][k2]   (Conv1d(8,1,k2).weight [1,8,k2])
+    const float* b2;       // [1]
+    const float* dt;       // device scalar
+    int k1, s1, k2, L1, tw, act;
+    int64_t n;
+};
+int decoder_fwd(DecArgs a, int hidden, float* out, cudaStream_t s);
+size_t decoder_bwd_workspace(int64_t n);
+int decoder_bwd(DecArgs a, int hidden, const float* dout, float* dh, float* du, int lddu, float* dw1, float* db1, float* dw2, float* db2,
+                void* ws, size_t ws_bytes, cudaStream_t s);
 // optim.cu
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
               double weight_decay, int64_t step, double grad_scale, cudaStream_t s);

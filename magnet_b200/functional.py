@@ -128,6 +128,66 @@ class GNNLayerFn(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
+# temporal-bundling decoder + Euler update (models/mpnn_2d.py:138-162,196-200) — csrc/decoder.cu
+# --------------------------------------------------------------------------------------------
+class BundlingDecoderFn(torch.autograd.Function):
+    """out[n, j] = u[n, -1] + (j + 1) dt * Conv1d(8->1, k2)(act(Conv1d(1->8, k1, stride)(h[n, None, :])))[j] in one launch per
+    direction; dt is a 0-dim device tensor (no host sync)."""
+
+    @staticmethod
+    def _args(h, u, w1, b1, w2, b2, dt, stride, act):
+        k1, k2 = w1.shape[-1], w2.shape[-1]
+        tw = (128 - k1) // stride + 1 - k2 + 1
+        return (_lib.ptr(h), h.shape[0], h.shape[1], _lib.ptr(u), u.stride(0), u.shape[1] - 1, _lib.ptr(w1), _lib.ptr(b1), k1, stride,
+                _lib.ptr(w2), _lib.ptr(b2), k2, tw, act, _lib.ptr(dt)), tw
+
+    @staticmethod
+    def forward(ctx, h, u, w1, b1, w2, b2, dt, stride: int, act: int):
+        _lib.require_cuda(h, u, w1, w2, dt)
+        L = _lib.lib()
+        h, u = _lib.f32c(h), _lib.f32c(u)
+        w1c, b1c, w2c, b2c = (_lib.f32c(v.detach()) for v in (w1, b1, w2, b2))
+        dtc = _lib.f32c(dt.detach()).reshape(1)
+        with torch.cuda.device(h.device):
+            args, tw = BundlingDecoderFn._args(h, u, w1c, b1c, w2c, b2c, dtc, stride, act)
+            out = _empty((h.shape[0], tw), h)
+            _lib.check(L.mgb_bundling_decoder_fwd(*args, _lib.ptr(out), _lib.stream()), "bundling_decoder_fwd")
+        ctx.save_for_backward(h, u, w1c, b1c, w2c, b2c, dtc)
+        ctx.stride, ctx.act, ctx.shapes = stride, act, (w1.shape, w2.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        h, u, w1c, b1c, w2c, b2c, dtc = ctx.saved_tensors
+        dout = _lib.f32c(dout)
+        with torch.cuda.device(h.device):
+            args, tw = BundlingDecoderFn._args(h, u, w1c, b1c, w2c, b2c, dtc, ctx.stride, ctx.act)
+            dh = _empty(h.shape, h)
+            du = torch.zeros_like(u) if ctx.needs_input_grad[1] else None
+            dw1, db1, dw2, db2 = _empty(w1c.shape, h), _empty(b1c.shape, h), _empty(w2c.shape, h), _empty(b2c.shape, h)
+            ws = _lib.workspace(L.mgb_bundling_decoder_bwd_workspace(h.shape[0]), h.device)
+            _lib.check(L.mgb_bundling_decoder_bwd(*args, _lib.ptr(dout), _lib.ptr(dh), _lib.ptr(du), u.shape[1] if du is not None else 0,
+                                                  _lib.ptr(dw1), _lib.ptr(db1), _lib.ptr(dw2), _lib.ptr(db2), _lib.ptr(ws), ws.numel(),
+                                                  _lib.stream()), "bundling_decoder_bwd")
+        return dh, du, dw1.reshape(ctx.shapes[0]), db1, dw2.reshape(ctx.shapes[1]), db2, None, None, None
+
+
+def bundling_decoder(h, u, conv1, conv2, dt, swish: bool):
+    """``u[:, -1:] + cumsum(dt) * output_mlp(h[:, None]).squeeze(1)`` (models/mpnn_2d.py:196-200) for the reference's decoder shapes
+    (Conv1d(1, 8, k1 <= 16, stride) [Swish] Conv1d(8, 1, k2 <= 16) on 128 hidden features)."""
+    ok = (h.is_cuda and h.shape[1] == 128 and conv1.in_channels == 1 and conv1.out_channels == 8 and conv2.in_channels == 8
+          and conv2.out_channels == 1 and conv1.kernel_size[0] <= 16 and conv2.kernel_size[0] <= 16 and conv2.stride[0] == 1
+          and conv1.padding[0] == 0 and conv2.padding[0] == 0 and conv1.dilation[0] == 1 and conv2.dilation[0] == 1
+          and conv1.bias is not None and conv2.bias is not None)
+    if not ok:
+        raise RuntimeError("bundling_decoder kernels cover the reference's decoders: Conv1d(1,8,k1<=16,stride) [Swish] Conv1d(8,1,k2<=16) "
+                           "on 128 hidden features")
+    dt = torch.as_tensor(dt, dtype=torch.float32, device=h.device)
+    return BundlingDecoderFn.apply(h, u, conv1.weight, conv1.bias, conv2.weight, conv2.bias, dt, conv1.stride[0], ACT["swish"] if swish else 0)
+
+
+# --------------------------------------------------------------------------------------------
 # row-wise Linear (+activation, +residual) and LayerNorm
 # --------------------------------------------------------------------------------------------
 @_lib.guard

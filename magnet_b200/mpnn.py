@@ -173,9 +173,8 @@ class _MPNNBase(LightningModule):
         h = MF.linear_act(h, e2.weight, e2.bias, "swish")
         for layer in self.gnn_layers:
             h = layer(h, u, pos_x, variables, edge_index, batch, plan=plan, segments=seg)
-        dts = torch.cumsum(torch.ones(1, self.time_window, device=u.device, dtype=u.dtype) * dt, dim=1)
-        diff = self.output_mlp(h[:, None]).squeeze(1)
-        return u[:, -1:].expand(-1, self.time_window) + dts * diff
+        # temporal-bundling decoder + Euler update in one launch (csrc/decoder.cu); dt stays on the device
+        return MF.bundling_decoder(h, u, self.output_mlp[0], self.output_mlp[-1], dt, swish=len(self.output_mlp) == 3)
 
     def configure_optimizers(self):
         if getattr(self, "flat_adam", False):     # opt-in (hparams.flat_adam): same update, one launch, flat gradient buffer

@@ -382,3 +382,38 @@ def test_flat_adam_checkpoint_interchanges_with_torch_adam():
     oe = FlatAdam(pe, lr=1e-3, weight_decay=1e-2)
     oe.load_state_dict(od.state_dict())
     assert oe.steps == 6
+
+
+# ---- temporal-bundling decoder + Euler update in one launch per direction (csrc/decoder.cu) -----------------------------------
+@pytest.mark.parametrize("tw,swish", [(10, True), (10, False), (16, True), (20, True), (25, True), (50, True)])
+def test_bundling_decoder_vs_torch_fp64(tw, swish):
+    """out = u[:, -1:] + cumsum(dt) * Conv1d(8,1,k2)(Swish(Conv1d(1,8,k1,stride)(h[:, None]))) (models/mpnn_2d.py:138-162,196-200;
+    no Swish for the 1-D tw = 10 decoder, models/mpnn.py:139-142): values and every gradient against an fp64 torch evaluation,
+    all five decoder shapes of the reference, a node count that is no multiple of the warps per block."""
+    from magnet_b200.mpnn import _CONV
+    k1, s1, k2 = _CONV[tw]
+    g = torch.Generator().manual_seed(300 + tw)
+    N = 1003
+    conv1, conv2 = torch.nn.Conv1d(1, 8, k1, stride=s1), torch.nn.Conv1d(8, 1, k2)
+    h = torch.randn(N, 128, generator=g)
+    u = torch.randn(N, tw, generator=g)
+    gy = torch.randn(N, tw, generator=g)
+    dt = torch.tensor(0.0375)
+    c1, c2 = conv1.double(), conv2.double()
+    h64, u64 = h.double().requires_grad_(), u.double().requires_grad_()
+    z = c1(h64[:, None])
+    z = z * torch.sigmoid(z) if swish else z
+    diff = c2(z).squeeze(1)
+    dts = torch.cumsum(torch.ones(1, tw, dtype=torch.float64) * dt.double(), 1)
+    want = u64[:, -1:].expand(-1, tw) + dts * diff
+    want.backward(gy.double())
+    d1, d2 = torch.nn.Conv1d(1, 8, k1, stride=s1).to(DEV), torch.nn.Conv1d(8, 1, k2).to(DEV)
+    d1.load_state_dict({k: v.float() for k, v in c1.state_dict().items()})
+    d2.load_state_dict({k: v.float() for k, v in c2.state_dict().items()})
+    hg, ug = h.to(DEV).requires_grad_(), u.to(DEV).requires_grad_()
+    got = MF.bundling_decoder(hg, ug, d1, d2, dt.to(DEV), swish)
+    assert got.shape == (N, tw) and rel_err(got, want) < 1e-6
+    got.backward(gy.to(DEV))
+    assert rel_err(hg.grad, h64.grad) < 1e-5 and rel_err(ug.grad, u64.grad) < 1e-6
+    for a, b in ((d1.weight, c1.weight), (d1.bias, c1.bias), (d2.weight, c2.weight), (d2.bias, c2.bias)):
+        assert rel_err(a.grad, b.grad) < 1e-5, (tuple(a.shape), rel_err(a.grad, b.grad))
