@@ -272,10 +272,59 @@ def gen_magnet_shapes(ref):
     torch.save(out, os.path.join(OUT, "magnet_shapes.pt"))
 
 
+def cnn_batch(B, W, N_side, nt, seed):
+    """MAgNet[CNN]_2d batch dict (datamodule/dataset_2d.py: 'lr_frames' [B,nt,1,W,W] on the regular grid, queries on a regular
+    N_side x N_side grid — validation feeds the query predictions back through a bilinear resize — 'coords', 'cells', 't')."""
+    g = S._gen(seed)
+    t = torch.linspace(0, 1, nt)
+    ax_lr = (-1 + 1 / W) + (2 / W) * torch.arange(W).float()
+    ax_hr = (-1 + 1 / N_side) + (2 / N_side) * torch.arange(N_side).float()
+    lr = torch.stack(torch.meshgrid(ax_lr, ax_lr, indexing="ij"), -1).reshape(-1, 2)
+    hr = torch.stack(torch.meshgrid(ax_hr, ax_hr, indexing="ij"), -1).reshape(-1, 2)
+    frames, points = [], []
+    for b in range(B):
+        u = S.field(torch.cat([lr, hr]) * 0.5 + 0.5, t, g)                  # [W*W + N, nt]
+        frames.append(u[:W * W].T.reshape(nt, 1, W, W))
+        points.append(u[W * W:].T[:, :, None])
+    cells = torch.full((B, N_side * N_side, 2), 2.0 / N_side)
+    return {"t": t[None].repeat(B, 1), "lr_frames": torch.stack(frames), "hr_points": torch.stack(points),
+            "coords": hr[None].repeat(B, 1, 1).contiguous(), "cells": cells}
+
+
+def gen_magnet_cnn(ref):
+    """MAgNet[CNN]_2d: the unmodified models/magnet_cnn_2d.py at latent_dim = mlp_hidden = n_chan = 128."""
+    import importlib
+    mod = importlib.import_module("models.magnet_cnn_2d")
+    hp = rl.HParams(dict(time_slice=10, latent_dim=128, num_message_passing_steps=3, mlp_layers=4, mlp_hidden=128, radius=0.2, scales=1,
+                         n_chan=128, kernel_size=3, res_scale=1, res_layers=3, teacher_forcing=True, interpolation="area", factor=0.3,
+                         step_size=40, loss="l1", lr=1e-3, weight_decay=1e-7))
+    m = mod.MAgNetCNN_2d(hp).eval()
+    _load_seeded(m, 51)
+    b = cnn_batch(B=2, W=12, N_side=9, nt=40, seed=51)
+    inp, hr_last, tt = b["lr_frames"][:, :10], b["hr_points"][:, 9], b["t"][:, :20]
+    with torch.no_grad():
+        feat = m.feature_encoding(inp)
+        z = m.continuous_decoder(inp, feat, b["cells"], b["coords"], tt)
+        out_hr, out_lr, hr_points = m.forward(inp, b["coords"], b["cells"], tt, hr_last)
+        m.validation_step(b, 0)
+    out = dict(batch=b, seed=51, hparams=dict(hp), feat=feat, z=z, out_hr=out_hr, out_lr=out_lr, hr_points=hr_points,
+               val_loss=m.logged["val_loss"])
+    m.train()
+    loss = m.training_step(b, 0)
+    loss.backward()
+    out["train_loss"] = loss.detach()
+    out["grad_norms"] = {k: p.grad.norm() for k, p in m.named_parameters()}
+    print("magnet_cnn_2d", tuple(out_hr.shape), float(out["val_loss"]), float(loss))
+    torch.save(out, os.path.join(OUT, "magnet_cnn_2d.pt"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "shapes":
         gen_magnet_shapes(rl.load())
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "cnn":
+        gen_magnet_cnn(rl.load())
         return
     ref = rl.load()
     torch.manual_seed(0)
@@ -285,6 +334,7 @@ def main():
     gen_mpnn(ref)
     gen_magnet(ref)
     gen_magnet_shapes(ref)
+    gen_magnet_cnn(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

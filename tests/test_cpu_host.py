@@ -112,3 +112,17 @@ def test_state_dicts_load_strictly_both_ways():
         a, b = ours(hp), theirs(hp)
         a.load_state_dict(b.state_dict(), strict=True)
         b.load_state_dict(a.state_dict(), strict=True)
+
+
+@pytest.mark.reference
+def test_magnet_cnn_state_dict_loads_strictly_both_ways(golden):
+    """MAgNet[CNN]_2d drop-in: same parameter names and shapes as models/magnet_cnn_2d.py."""
+    import importlib
+    from oracle import reference_loader as rl
+    from magnet_b200.magnet_cnn import MAgNetCNN_2d
+    rl.load()
+    theirs = importlib.import_module("models.magnet_cnn_2d").MAgNetCNN_2d
+    hp = rl.HParams(golden("magnet_cnn_2d.pt")["hparams"])
+    a, b = MAgNetCNN_2d(hp), theirs(hp)
+    a.load_state_dict(b.state_dict(), strict=True)
+    b.load_state_dict(a.state_dict(), strict=True)
