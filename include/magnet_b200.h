@@ -264,12 +264,13 @@ int mgb_inr_decode_bwd(const float* a, const float* xlr, const float* lr_coords,
  * mgb_inr_decode_fwd does, and every (query, time step) row goes straight through the projector MLP (packed as for
  * mgb_mlp_chain_fwd: n_layers Linears of width 128, ReLU between, n_out outputs) as tcgen05 tiles.  z [Q,T,128] never
  * exists.  y [Q*T, n_out].  ptr_x [n_samples+1]: offsets of the samples' low-res nodes (needed when idx is NULL; the grid
- * is built in the workspace by a few small launches). */
+ * is built in the workspace by a few small launches).  grid_ready != 0: the workspace still holds the grid an earlier call built
+ * over the same lr_coords (a rollout decodes every step over the same low-res mesh): nothing is rebuilt. */
 size_t mgb_inr_decode_fused_workspace(int64_t n_lowres, int n_samples);
 int mgb_inr_decode_fused(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
                          const float* wsmall, int ldw, const int64_t* idx, int k, const int64_t* ptr_x, int n_samples, int64_t n_query,
                          int nq_per_sample, int L, int T, int d, int mode, int n_layers, const float* packed, int n_out, float* y,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         int grid_ready, void* workspace, size_t workspace_bytes, void* stream);
 
 /* InstanceNorm alone (PyG InstanceNorm, models/mpnn_2d.py:63,70) — exposed for tests. */
 size_t mgb_instance_norm_workspace(int n_graphs, int max_nodes_per_graph);

@@ -274,7 +274,7 @@ size_t mgb_inr_decode_fused_workspace(int64_t n_lowres, int n_samples) { return 
 int mgb_inr_decode_fused(const float* a, const float* xlr, const float* lr_coords, const float* hr_coords, const float* t, int ldt,
                          const float* wsmall, int ldw, const int64_t* idx, int k, const int64_t* ptr_x, int n_samples, int64_t n_query,
                          int nq_per_sample, int L, int T, int d, int mode, int n_layers, const float* packed, int n_out, float* y,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         int grid_ready, void* workspace, size_t workspace_bytes, void* stream) {
     MGB_REQUIRE(n_layers >= 1 && n_layers <= 8, "inr_decode_fused: 1..8 projector layers (got %d)", n_layers);
     MGB_REQUIRE(d == 1 || d == 2, "inr_decode_fused: coordinate dimension must be 1 or 2");
     MlpChainArgs c{};
@@ -290,7 +290,7 @@ int mgb_inr_decode_fused(const float* a, const float* xlr, const float* lr_coord
         MGB_REQUIRE(ptr_x != nullptr, "inr_decode_fused: the in-kernel search needs the sample offsets of the low-res nodes");
         GridParams* gp; CellPoint* pts; int32_t* cell_start;
         MGB_TRY(build_grid_ws(lr_coords, (int64_t)n_samples * L, d, ptr_x, n_samples, 0.f, 2.0f, workspace, workspace_bytes, &gp, &pts,
-                              &cell_start, STREAM(stream)));
+                              &cell_start, STREAM(stream), grid_ready));
         f.gp = gp; f.pts = pts; f.cell_start = cell_start;
     }
     f.idx = idx; f.k = k; f.A = a; f.xlr = xlr; f.lr_coords = lr_coords; f.hr_coords = hr_coords; f.t = t; f.ldt = ldt;

@@ -188,7 +188,7 @@ radius_emit_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ 
 
 static int build_grid(const float* pos, int64_t n, int d, const int64_t* ptr, int n_samples, float h_min,
                       float target_ppc, int64_t max_cells, Workspace& ws, GridParams** gp_out, CellPoint** pts_out,
-                      int32_t** cell_start_out, cudaStream_t s) {
+                      int32_t** cell_start_out, cudaStream_t s, bool reuse = false) {
     int* bbox = ws.take<int>(4);
     GridParams* gp = ws.take<GridParams>(1);
     uint32_t* cell = ws.take<uint32_t>(n);
@@ -200,6 +200,8 @@ static int build_grid(const float* pos, int64_t n, int d, const int64_t* ptr, in
     size_t sort_bytes = sort_workspace_bytes(n);
     char* sort_ws = ws.take<char>(sort_bytes);
     MGB_WS_CHECK(ws);
+    *gp_out = gp; *pts_out = pts; *cell_start_out = cell_start;
+    if (reuse) return MGB_OK;            // the workspace still holds the grid of an earlier call over the same points
     bbox_init_kernel<<<1, 32, 0, s>>>(bbox);
     MGB_LAUNCH_CHECK();
     if (n > 0) {
@@ -299,9 +301,9 @@ size_t knn_workspace_bytes(int64_t nx, int n_samples) { return radius_workspace_
 size_t grid_workspace_bytes(int64_t n, int n_samples) { return radius_workspace_bytes(n, n_samples); }
 
 int build_grid_ws(const float* pos, int64_t n, int d, const int64_t* ptr, int n_samples, float h_min, float target_ppc, void* ws_ptr,
-                  size_t ws_bytes, GridParams** gp, CellPoint** pts, int32_t** cell_start, cudaStream_t s) {
+                  size_t ws_bytes, GridParams** gp, CellPoint** pts, int32_t** cell_start, cudaStream_t s, int reuse) {
     Workspace ws(ws_ptr, ws_bytes);
-    return build_grid(pos, n, d, ptr, n_samples, h_min, target_ppc, default_max_cells(n, n_samples), ws, gp, pts, cell_start, s);
+    return build_grid(pos, n, d, ptr, n_samples, h_min, target_ppc, default_max_cells(n, n_samples), ws, gp, pts, cell_start, s, reuse != 0);
 }
 
 int knn_search(const float* x, int64_t nx, const float* y, int64_t ny, int d, const int64_t* ptr_x, const int64_t* ptr_y,

@@ -109,6 +109,6 @@ __device__ __forceinline__ void knn_query(const CellPoint* __restrict__ pts, con
 // h_min > 0: cell edge >= h_min (radius search); h_min == 0: about target_ppc points per cell (kNN).
 size_t grid_workspace_bytes(int64_t n, int n_samples);
 int build_grid_ws(const float* pos, int64_t n, int d, const int64_t* ptr, int n_samples, float h_min, float target_ppc, void* ws,
-                  size_t ws_bytes, GridParams** gp, CellPoint** pts, int32_t** cell_start, cudaStream_t s);
+                  size_t ws_bytes, GridParams** gp, CellPoint** pts, int32_t** cell_start, cudaStream_t s, int reuse = 0);
 
 }  // namespace mgb

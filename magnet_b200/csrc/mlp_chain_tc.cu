@@ -22,7 +22,7 @@
 // layer 0 are not loaded but COMPUTED by the producers, row = (query q, time step i):
 //   z[q,i,:] = blend of the proj_head outputs of the two nearest low-res nodes (latent part factorised per node: A; relative
 //   coordinates, input value and time through the small proj_head columns), exactly the arithmetic of inr_decode_fwd_kernel;
-// two SEARCH warps run one tile ahead: per query of the tile they find the two nearest low-res nodes in the grid hash
+// two SEARCH warps run a pair ahead (each owns every other pair): per query of the tiles they find the two nearest low-res nodes in the grid hash
 // (knn_query, grid.cuh — or read a precomputed neighbour table) and leave a 48-byte record (nodes, relative coordinates,
 // blend weights) in shared memory.  z [Q,T,128] (5 KB per query) never exists: HBM sees the query coordinates in
 // and hr_points [Q,T] out, plus L2-resident gathers of A.
@@ -306,26 +306,39 @@ __global__ void __launch_bounds__(mc_threads<MODE>(), 1) mlp_chain_tc_kernel(con
     } else if (warp < MC_PROD_WARP0 && !(MODE == 1 && warp >= MC_SEARCH_WARP0 && warp < MC_SEARCH_WARP0 + 2)) {
         umma::reg_dec<56>();          // spare warps of the loader / search warpgroup
     } else if (MODE == 1 && warp < MC_PROD_WARP0) {
-        // =========================== search warps: warp 13 -> tile 0 of every pair, warp 14 -> tile 1 =============
+        // =========================== search warps: warp 13 -> both tiles of the even pairs, warp 14 -> of the odd pairs =====
+        // A query's ring search is a chain of dependent L2 loads (~20 us) whatever the lane count, so a warp that owned one tile
+        // of EVERY pair was exactly as slow as the pair itself (search-bound: 6.5 vs 5.2 ms per 2^20 queries).  Each warp now
+        // takes the queries of BOTH tiles of every other pair side by side in its lanes and has two pair periods to do so.
         umma::reg_dec<56>();
         const InrFuseArgs& f = a.inr;
-        const int t = warp - MC_SEARCH_WARP0;
+        const int w = warp - MC_SEARCH_WARP0;
         const GridParams gp = f.idx ? GridParams{} : *f.gp;
 #pragma unroll 1
-        for (int it = 0; it < np; ++it) {
-            const int64_t tile = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 2 + t;
-            if (tile >= n_tiles) continue;
-            const int qs = (it & 1) * 2 + t;
-            umma::mbar_wait_relaxed<500>(&q_empty[qs], ((it >> 1) & 1) ^ 1);
-            const int64_t r0 = tile * 128;
-            const int64_t r1 = (r0 + 127 < a.rows - 1) ? r0 + 127 : a.rows - 1;
-            const int64_t q0 = r0 / f.T;
-            const int nq = (int)(r1 / f.T - q0) + 1;
-            for (int jq = lane; jq < nq; jq += 32) {
-                if (f.d == 2) inr_build_record<2>(f, gp, q0 + jq, qrec + qs * MC_MAXQ + jq);
-                else inr_build_record<1>(f, gp, q0 + jq, qrec + qs * MC_MAXQ + jq);
+        for (int it = w; it < np; it += 2) {
+            int64_t q0[2];
+            int nq[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int64_t tile = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 2 + t;
+                nq[t] = 0;
+                q0[t] = 0;
+                if (tile >= n_tiles) continue;
+                umma::mbar_wait_relaxed<500>(&q_empty[(it & 1) * 2 + t], ((it >> 1) & 1) ^ 1);
+                const int64_t r0 = tile * 128;
+                const int64_t r1 = (r0 + 127 < a.rows - 1) ? r0 + 127 : a.rows - 1;
+                q0[t] = r0 / f.T;
+                nq[t] = (int)(r1 / f.T - q0[t]) + 1;
             }
-            umma::mbar_arrive(&q_full[qs]);
+            for (int j = lane; j < nq[0] + nq[1]; j += 32) {
+                const int t = j < nq[0] ? 0 : 1, jq = t ? j - nq[0] : j;
+                InrQRec* rec = qrec + ((it & 1) * 2 + t) * MC_MAXQ + jq;
+                if (f.d == 2) inr_build_record<2>(f, gp, q0[t] + jq, rec);
+                else inr_build_record<1>(f, gp, q0[t] + jq, rec);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t)
+                if (nq[t] > 0) umma::mbar_arrive(&q_full[(it & 1) * 2 + t]);
         }
     } else if (MODE == 1) {
         // =========================== producers (fused decoder): 16 rows = (query, time step) pairs per warp =========

@@ -310,7 +310,7 @@ class MAgNetGNN(LightningModule):
             return MF.inr_decode_fused(x_lr.reshape(B, T, L), lr_encoded.reshape(B * L, -1), lr_coords.reshape(B * L, -1),
                                        hr_coords.reshape(B * hr_coords.shape[1], -1), t[:, :T], self.proj_head.weight,
                                        self.proj_head.bias, lin, B, L, hr_coords.shape[1], self.codec_neighbors,
-                                       self.interpolation, cache_owner=self.projector)
+                                       self.interpolation, cache_owner=self.projector, grid_owner=lr_coords)
         z = self.continuous_decoder(x_lr, lr_encoded, lr_coords, hr_coords, t)
         return self.projector(z)
 
