@@ -299,7 +299,7 @@ def cpu_mp_layer(samples: int, steps: int, warmup: int, threads: int):
 def bench_mp_layer(env, clocks):
     from magnet_b200 import graph as MG, functional as MF
     from magnet_b200.mpnn import GNN_Layer
-    from magnet_b200.optim import FlatAdam, allreduce_flat_gradient
+    from magnet_b200.optim import FlatAdam, OverlappedFlatAllReduce
     args, dev, world, L = env.args, env.dev, env.world, env.L
     MF.set_precision(args.precision)
     w = make_workload(SAMPLES_PER_GPU, 1 + env.rank, dev)
@@ -320,6 +320,9 @@ def bench_mp_layer(env, clocks):
     # gradient buffer is what the all-reduce sends.  The step is part of the timed region: so is the re-packing of the
     # kernel-side weight copies that every update triggers.
     opt = FlatAdam(params, lr=1e-5, weight_decay=1e-8)
+    # the training all-reduce leaves in one bucket per layer from the gradient hooks, on a side stream, while the backward of
+    # the layers below is still running; finish() makes the compute stream wait for what is left
+    ar = OverlappedFlatAllReduce(opt, world, n_buckets=N_LAYERS) if world > 1 else None
 
     def step(x, u, pos, var, gy):
         h = x.detach().requires_grad_()
@@ -327,7 +330,7 @@ def bench_mp_layer(env, clocks):
         for m in layers:
             out = m(out, u, pos, var, ei, batch, plan=plan, segments=seg)
         out.backward(gy)
-        scale = allreduce_flat_gradient(opt, world) if world > 1 else 1.0     # one NCCL all-reduce of the flat gradient buffer
+        scale = ar.finish() if ar is not None else 1.0
         opt.step(grad_scale=scale)
         opt.zero_grad()
         return out

@@ -22,12 +22,14 @@ from . import _lib
 
 
 def ptr_from_batch(batch: Optional[torch.Tensor], n: int, device) -> torch.Tensor:
-    """int64 [B+1] sample offsets from a sorted batch vector (one host sync for B)."""
+    """int64 [B+1] sample offsets from a SORTED batch vector (torch_geometric's convention, models/mpnn_2d.py:237,249): one
+    binary-search launch; the sample count is the last entry + 1 (one 8-byte read instead of a max-reduction + histogram)."""
     if batch is None:
         return torch.tensor([0, n], dtype=torch.int64, device=device)
-    nb = int(batch.max().item()) + 1 if batch.numel() else 1
-    counts = torch.bincount(batch, minlength=nb)
-    return torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(torch.int64)
+    if batch.numel() == 0:
+        return torch.zeros(2, dtype=torch.int64, device=device)
+    nb = int(batch[-1].item()) + 1
+    return torch.searchsorted(batch.contiguous(), torch.arange(nb + 1, device=batch.device, dtype=batch.dtype)).to(torch.int64)
 
 
 def uniform_ptr(n_samples: int, n_per_sample: int, device) -> torch.Tensor:
