@@ -105,6 +105,8 @@ int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_featur
                    int act, const float* residual, float* y, float* y_pre, void* stream) {
     MGB_REQUIRE(rows >= 0 && rows < ((int64_t)1 << 31), "linear_fwd: row count out of range");
     MGB_REQUIRE(act >= 0 && act <= 2, "linear_fwd: unknown activation %d", act);
+    if (small_linear_ok(in_features, out_features) && residual == nullptr)      // a handful of inputs: one streaming kernel, no GEMM tiles
+        return small_linear_fwd(x, rows, in_features, wt, bias, act, y, y_pre, STREAM(stream));
     GemmArgs g{};
     g.a.p[0] = x; g.a.ld[0] = in_features; g.a.k[0] = in_features; g.a.nseg = 1;
     g.b = wt; g.ldb = out_features; g.bias = bias;
@@ -370,6 +372,7 @@ int mgb_linear_tc_bwd(const float* dy, const float* y_pre, int act, const float*
 }
 
 size_t mgb_linear_bwd_workspace(int64_t rows, int in_features, int out_features) {
+    if (small_linear_ok(in_features, out_features)) return small_linear_bwd_workspace(rows, in_features);
     return wgrad_workspace_bytes((int)rows, out_features, in_features) + 1024;
 }
 
@@ -378,6 +381,9 @@ int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x,
                    void* workspace, size_t workspace_bytes, void* stream) {
     MGB_REQUIRE(rows >= 0 && rows < ((int64_t)1 << 31), "linear_bwd: row count out of range");
     MGB_REQUIRE(act == 0 || y_pre != nullptr, "linear_bwd: an activation needs the saved pre-activation");
+    if (small_linear_ok(in_features, out_features))
+        return small_linear_bwd(dy, y_pre, act, x, rows, in_features, w, dx, dw, db, accumulate_params, workspace, workspace_bytes,
+                                STREAM(stream));
     if (dw) {
         WgradArgs wg{};
         wg.dy = dy; wg.lddy = out_features; wg.y_pre = act ? y_pre : nullptr; wg.y_act = act;

@@ -197,6 +197,12 @@ int decoder_fwd(DecArgs a, int hidden, float* out, cudaStream_t s);
 size_t decoder_bwd_workspace(int64_t n);
 int decoder_bwd(DecArgs a, int hidden, const float* dout, float* dh, float* du, int lddu, float* dw1, float* db1, float* dw2, float* db2,
                 void* ws, size_t ws_bytes, cudaStream_t s);
+// small_linear.cu (Linears with <= 16 input features and 128 outputs: streaming kernels, no GEMM tiles)
+bool small_linear_ok(int in_features, int out_features);
+int small_linear_fwd(const float* x, int64_t rows, int K, const float* wt, const float* bias, int act, float* y, float* y_pre, cudaStream_t s);
+size_t small_linear_bwd_workspace(int64_t rows, int K);
+int small_linear_bwd(const float* dy, const float* y_pre, int act, const float* x, int64_t rows, int K, const float* w, float* dx, float* dw,
+                     float* db, int accumulate, void* ws, size_t ws_bytes, cudaStream_t s);
 // optim.cu
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
               double weight_decay, int64_t step, double grad_scale, cudaStream_t s);

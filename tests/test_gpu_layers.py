@@ -417,3 +417,25 @@ def test_bundling_decoder_vs_torch_fp64(tw, swish):
     assert rel_err(hg.grad, h64.grad) < 1e-5 and rel_err(ug.grad, u64.grad) < 1e-6
     for a, b in ((d1.weight, c1.weight), (d1.bias, c1.bias), (d2.weight, c2.weight), (d2.bias, c2.bias)):
         assert rel_err(a.grad, b.grad) < 1e-5, (tuple(a.shape), rel_err(a.grad, b.grad))
+
+
+# ---- Linears with a handful of inputs (csrc/small_linear.cu): Encoder / embedding first layers -----------------------------------
+@pytest.mark.parametrize("K,act", [(1, "none"), (12, "relu"), (13, "swish"), (16, "relu")])
+def test_small_k_linear_vs_fp64(K, act):
+    """y = act(x W^T + b) for K <= 16 inputs and 128 outputs (models/magnet_gnn.py:20-35 first Linears: 13 / 12 features;
+    models/mpnn_2d.py:130-131): the streaming kernels behind mgb_linear_fwd / mgb_linear_bwd, values and all gradients."""
+    g = torch.Generator().manual_seed(400 + K)
+    rows = 4099
+    x, W, b = torch.randn(rows, K, generator=g), torch.randn(128, K, generator=g) / K ** 0.5, torch.randn(128, generator=g)
+    gy = torch.randn(rows, 128, generator=g)
+    x64, W64, b64 = (v.double().requires_grad_() for v in (x, W, b))
+    z = x64 @ W64.T + b64
+    want = {"none": z, "relu": z.clamp_min(0), "swish": z * torch.sigmoid(z)}[act]
+    want.backward(gy.double())
+    xg, Wg, bg = (v.to(DEV).requires_grad_() for v in (x, W, b))
+    got = MF.linear_act(xg, Wg, bg, act)
+    assert rel_err(got, want) < 1e-6
+    got.backward(gy.to(DEV))
+    assert rel_err(xg.grad, x64.grad) < 1e-5 and rel_err(Wg.grad, W64.grad) < 1e-5 and rel_err(bg.grad, b64.grad) < 1e-5
+    with torch.no_grad():                              # inference path: no saved pre-activation
+        assert torch.equal(MF.linear_act(xg, Wg, bg, act), got)
