@@ -390,8 +390,22 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
     partial[((int64_t)blockIdx.x * 2 + which) * 128 + c] = sum;
 }
 
+constexpr int LNB_STAGE = 256;       // first-stage groups of the parameter-gradient reduction
 size_t layernorm_bwd_workspace_bytes(int64_t rows, int cols) {
-    return align_up((size_t)ceil_div<int64_t>(rows > 0 ? rows : 1, LNB_ROWS) * 2 * 128 * sizeof(float)) + 256;
+    return align_up((size_t)ceil_div<int64_t>(rows > 0 ? rows : 1, LNB_ROWS) * 2 * 128 * sizeof(float)) +
+           align_up((size_t)LNB_STAGE * 2 * 128 * sizeof(float)) + 256;
+}
+
+// first stage over millions of edge rows: group g sums the partials of its contiguous range of blocks (fixed order); the
+// single-block kernel below then sums the LNB_STAGE group results — one block walking 131 k partial rows took 0.86 ms
+__global__ void __launch_bounds__(256)
+layernorm_param_stage_kernel(const float* __restrict__ partial, int64_t nblocks, float* __restrict__ staged) {
+    const int which = threadIdx.x >> 7, c = threadIdx.x & 127;
+    const int64_t per = ceil_div<int64_t>(nblocks, gridDim.x);
+    const int64_t b0 = (int64_t)blockIdx.x * per, b1 = b0 + per < nblocks ? b0 + per : nblocks;
+    float sum = 0.f;
+    for (int64_t b = b0; b < b1; ++b) sum += partial[(b * 2 + which) * 128 + c];
+    staged[((int64_t)blockIdx.x * 2 + which) * 128 + c] = sum;
 }
 
 __global__ void __launch_bounds__(256)
@@ -411,13 +425,20 @@ int launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, co
     const int64_t nb = ceil_div<int64_t>(rows > 0 ? rows : 1, LNB_ROWS);
     Workspace ws(ws_ptr, ws_bytes);
     float* partial = ws.take<float>((size_t)nb * 2 * 128);
+    float* staged = ws.take<float>((size_t)LNB_STAGE * 2 * 128);
     MGB_WS_CHECK(ws);
     if (rows == 0) { MGB_CUDA(cudaMemsetAsync(partial, 0, (size_t)nb * 2 * 128 * sizeof(float), s)); }
     else {
         layernorm_bwd_kernel<<<(unsigned)nb, 256, 0, s>>>(dy, x, gamma, stats, dx, partial, rows);
         MGB_LAUNCH_CHECK();
     }
-    layernorm_param_reduce_kernel<<<1, 256, 0, s>>>(partial, nb, dgamma, dbeta, accumulate_params);
+    if (nb > 4 * LNB_STAGE) {
+        layernorm_param_stage_kernel<<<LNB_STAGE, 256, 0, s>>>(partial, nb, staged);
+        MGB_LAUNCH_CHECK();
+        layernorm_param_reduce_kernel<<<1, 256, 0, s>>>(staged, LNB_STAGE, dgamma, dbeta, accumulate_params);
+    } else {
+        layernorm_param_reduce_kernel<<<1, 256, 0, s>>>(partial, nb, dgamma, dbeta, accumulate_params);
+    }
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }
