@@ -209,6 +209,16 @@ __device__ __forceinline__ void ib_mma_group(uint32_t d, int a_kind, uint64_t a,
     }
 }
 
+#ifdef MGB_TIMELINE
+__device__ long long* g_ib_timeline = nullptr;      // [pass 0..1][tile 0..3][role 0..2][event 0..31] clock64 of CTA 0
+#define IBTL(role, it_, ev) do { if (blockIdx.x == 0 && (it_) < 4 && (threadIdx.x & 31) == 0 && g_ib_timeline && (ev) < 32) g_ib_timeline[(((PASS) * 4 + (it_)) * 3 + (role)) * 32 + (ev)] = clock64(); } while (0)
+int set_ib_timeline_buffer(long long* p) {
+    return cudaMemcpyToSymbol(g_ib_timeline, &p, sizeof(p)) == cudaSuccess ? MGB_OK : MGB_ERR_CUDA;
+}
+#else
+#define IBTL(role, it_, ev) do { } while (0)
+#endif
+
 template <int PASS /*0 = A (upper layers), 1 = B (lower layers)*/, int NSPLIT>
 __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InEdgeBwdArgs a) {
     extern __shared__ unsigned char smem_raw[];
@@ -279,18 +289,24 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
 #pragma unroll
         for (int i = 0; i < (PASS == 0 ? IB_NVEC_A : IB_NVEC_B); ++i) acc_v[i] = 0.f;
         uint32_t tf = 0;                 // completed phases of t_full
+        int tl_it = 0, tl_ev = 0;        // (developer timeline: event counter of the current tile)
         auto wait_t = [&]() {
             umma::mbar_wait(t_full, tf & 1);
             ++tf;
             umma::tc_fence_after();
+            if (warp == 0) IBTL(0, tl_it, tl_ev++);
         };
         auto wait_t0 = [&](int it_) {
+            tl_it = it_; tl_ev = 0;
+            if (warp == 0) IBTL(0, tl_it, tl_ev++);
             umma::mbar_wait(t_full0, it_ & 1);
             umma::tc_fence_after();
+            if (warp == 0) IBTL(0, tl_it, tl_ev++);
         };
         auto signal = [&]() {
             umma::fence_async_smem();
             umma::tc_fence_before();
+            if (warp == 0) IBTL(0, tl_it, tl_ev++);
             umma::mbar_arrive(x_ready);
         };
 #pragma unroll 1
@@ -503,6 +519,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                 umma::tc_fence_before();
                 umma::mbar_arrive(&m_empty[slot]);
             }
+            if (warp == 0) IBTL(0, tl_it, tl_ev++);
             // ---- drain the weight-gradient accumulators into this CTA's partial (round-to-nearest adds, fixed order)
             if (((it + 1) % IB_DRAIN) == 0 || it + 1 == nt) {
 #pragma unroll 1
@@ -535,24 +552,30 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
         const uint64_t h_k = umma::desc_sw128(umma::smem_u32(h_img), 16, 1024), h_m = umma::desc_sw128(umma::smem_u32(h_img), 128 * 128, 1024);
         const uint32_t R1 = tmem, R2 = tmem + 128u, GA = tmem + 256u, GB = tmem + 384u;
         uint32_t wl = 0, xr = 0;         // weight loads issued, x_ready phases consumed
+        int ml_it = 0, ml_ev = 0;
         auto load_w = [&](int layer) {
             if (wl > 0) umma::mbar_wait(w_free, (wl - 1) & 1);          // the MMAs that read the previous images are done
+            IBTL(1, ml_it, ml_ev++);                                    // previous group complete
             if (lane == 0) load_w2_image(w_img, (const unsigned char*)a.wimg + (size_t)layer * 2 * TILE_BYTES, NSPLIT * TILE_BYTES, w_bar);
             umma::mbar_wait(w_bar, wl & 1);
             ++wl;
+            IBTL(1, ml_it, ml_ev++);                                    // weights landed
         };
         auto wait_x = [&]() {
             umma::mbar_wait(x_ready, xr & 1);
             ++xr;
             umma::tc_fence_after();
+            IBTL(1, ml_it, ml_ev++);                                    // operand ready
         };
 #pragma unroll 1
         for (int it = 0; it < nt; ++it) {
             const uint32_t g0 = (it % IB_DRAIN) == 0 ? 0u : 1u;        // first tile after a drain: the gradient accumulators restart
+            ml_it = it; ml_ev = 0;
             // ---- layer 0: R2 (= P + Q) += We e
             load_w(0);
             umma::mbar_wait(x_full, it & 1);
             umma::tc_fence_after();
+            IBTL(1, ml_it, ml_ev++);                                    // x_full
             if (umma::elect_one()) {
                 ib_mma_group<NSPLIT>(R2, 0, w_k, 0, x_k, id_kk, 1u);
                 umma::mma_commit(t_full0);
@@ -707,10 +730,12 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pq + sp * 256 + 224));
                 }
             }
+            if (pw == 0) IBTL(2, it, 0);                        // rows gathered, waiting for the slot
             if (it > 0) {
                 umma::mbar_wait(x_free, (it - 1) & 1);          // the previous tile's MMAs are done with the tile and with R2
                 umma::tc_fence_after();
             }
+            if (pw == 0) IBTL(2, it, 1);
             regs_to_image(hl);
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
@@ -732,6 +757,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
             }
             umma::fence_async_smem();
             umma::tc_fence_before();
+            if (pw == 0) IBTL(2, it, 2);
             umma::mbar_arrive(x_full);
             if (PASS == 1) {
                 // the dz2 tile (aggregation order, whole tiles) replaces the e tile once layer 0 has consumed it
