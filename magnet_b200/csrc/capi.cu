@@ -380,7 +380,7 @@ int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x,
                    int out_features, const float* w, float* dx, float* dw, float* db, int accumulate_params,
                    void* workspace, size_t workspace_bytes, void* stream) {
     MGB_REQUIRE(rows >= 0 && rows < ((int64_t)1 << 31), "linear_bwd: row count out of range");
-    MGB_REQUIRE(act == 0 || y_pre != nullptr, "linear_bwd: an activation needs the saved pre-activation");
+    MGB_REQUIRE(act == 0 || y_pre != nullptr || rows == 0, "linear_bwd: an activation needs the saved pre-activation");
     if (small_linear_ok(in_features, out_features))
         return small_linear_bwd(dy, y_pre, act, x, rows, in_features, w, dx, dw, db, accumulate_params, workspace, workspace_bytes,
                                 STREAM(stream));

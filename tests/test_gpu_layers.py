@@ -439,3 +439,18 @@ def test_small_k_linear_vs_fp64(K, act):
     assert rel_err(xg.grad, x64.grad) < 1e-5 and rel_err(Wg.grad, W64.grad) < 1e-5 and rel_err(bg.grad, b64.grad) < 1e-5
     with torch.no_grad():                              # inference path: no saved pre-activation
         assert torch.equal(MF.linear_act(xg, Wg, bg, act), got)
+
+
+def test_bundling_decoder_and_small_linear_on_empty_input():
+    """Zero rows: the streaming kernels launch nothing and the parameter gradients are zero."""
+    d1, d2 = torch.nn.Conv1d(1, 8, 16, stride=6).to(DEV), torch.nn.Conv1d(8, 1, 10).to(DEV)
+    h = torch.zeros(0, 128, device=DEV, requires_grad=True)
+    out = MF.bundling_decoder(h, torch.zeros(0, 10, device=DEV), d1, d2, torch.tensor(0.1, device=DEV), True)
+    assert out.shape == (0, 10)
+    out.sum().backward()
+    assert float(d1.weight.grad.abs().sum()) == 0.0 and float(d2.bias.grad.abs().sum()) == 0.0
+    W, b = torch.randn(128, 12, device=DEV, requires_grad=True), torch.randn(128, device=DEV, requires_grad=True)
+    y = MF.linear_act(torch.zeros(0, 12, device=DEV, requires_grad=True), W, b, "relu")
+    assert y.shape == (0, 128)
+    y.sum().backward()
+    assert float(W.grad.abs().sum()) == 0.0 and float(b.grad.abs().sum()) == 0.0
