@@ -16,7 +16,7 @@
  * PARITY UNPINNED: the reference holds no golden vectors or tests for these
  * functions; the points that decide results (strict '<', index-order
  * truncation, tie order, fp32 accumulation with nvcc's default FMA
- * contraction) are isolated by tests/test_oracle_graph.py.
+ * contraction) are isolated by tests/test_oracle_cpu.py.
  *
  * Arithmetic: fp32, dimension order, `dist += diff*diff`.  nvcc compiles that
  * to fma(diff, diff, dist) (default --fmad=true); fma_mode=1 mirrors it with
