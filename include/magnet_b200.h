@@ -136,6 +136,10 @@ int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_feature
 int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* packed,
                       const float* bias, int act, const float* residual, float* y, float* y_pre, int precision,
                       void* stream);
+/* The same Linear applied to cat([x0, x1], dim = 1) of two 128-column tensors (row strides ld0, ld1) without materialising the
+ * concatenation: the node function of InteractionNetwork reads cat([aggregated, x]) (models/magnet_gnn.py:84-86).  Inference. */
+int mgb_linear_tc_fwd2(const float* x0, int ld0, const float* x1, int ld1, int64_t rows, int out_features, const float* packed,
+                       const float* bias, int act, float* y, int precision, void* stream);
 /* A whole MLP of models/backbones/mlp.py:9-28 behind its first Linear — n_layers Linear(128, 128) + act, the last one
  * Linear(128, n_out <= 128) without activation — in one launch, forward only (inference / rollout): activations stay in
  * shared memory between the layers, arithmetic as mgb_linear_tc_fwd with precision 3.  x [rows, >=128] fp32 (row stride
@@ -168,6 +172,9 @@ int mgb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   double beta2, double eps, double weight_decay, int64_t step, double grad_scale, void* stream);
 int mgb_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int cols, float* y,
                       float* stats /* [rows,2] mean,rstd */, void* stream);
+/* y = LayerNorm(x) + residual in one pass (the `x_new + x` of InteractionNetwork.forward, models/magnet_gnn.py:88).  Inference. */
+int mgb_layernorm_residual_fwd(const float* x, const float* gamma, const float* beta, const float* residual, int64_t rows, int cols,
+                               float* y, void* stream);
 size_t mgb_layernorm_bwd_workspace(int64_t rows, int cols);
 int mgb_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* stats, int64_t rows, int cols,
                       float* dx, float* dgamma, float* dbeta, int accumulate_params, void* workspace,
@@ -204,6 +211,11 @@ int mgb_relu_mask(const float* dout, const float* out, int64_t n, float* dz, voi
 int mgb_segment_sum_rows(const float* rows, int cols, const int32_t* rowptr, const int32_t* idx, int64_t n_nodes, int mean,
                          float* out, int ld_out, void* stream);
 int mgb_gather_rows(const float* rows, const int64_t* index, const int32_t* rowptr, int64_t n_edges, float* out, void* stream);
+/* Node and edge features of MAgNetGNN._build_graph (models/magnet_gnn.py:298-308) in one launch:
+ *   node_features [N, C+d+1] = [u, x, t_last[row % n_samples]] (the time column is TILED over the rows),
+ *   edge_features [E, C+d]   = [u[s] - u[r], x[s] - x[r]] with s = edge_index[0], r = edge_index[1] (int64 [2,E]).  Inference. */
+int mgb_magnet_features(const float* u, int n_chan, const float* x, int d, const float* t_last, int n_samples, int64_t n_nodes,
+                        const int64_t* edge_index, int64_t n_edges, float* node_features, float* edge_features, void* stream);
 
 /* Fused edge function of InteractionNetwork (models/magnet_gnn.py:79-82 message, :54 aggr='mean'), forward:
  *   agg[i] = mean_{e: edge_index[1][e] = i} LayerNorm(MLP5(cat[x_i, x_j, e_scale * e_features[e]]))

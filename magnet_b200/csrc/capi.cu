@@ -181,6 +181,33 @@ int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_fea
     return launch_linear_tc(precision, a, STREAM(stream));
 }
 
+// the same Linear over cat([x0, x1], dim = 1) of two 128-column tensors without materialising the concatenation
+int mgb_linear_tc_fwd2(const float* x0, int ld0, const float* x1, int ld1, int64_t rows, int out_features, const float* packed,
+                       const float* bias, int act, float* y, int precision, void* stream) {
+    int nk, nm;
+    MGB_REQUIRE(linear_tc_shape(256, out_features, &nk, &nm), "linear_tc_fwd2: unsupported shape 256 -> %d", out_features);
+    MGB_REQUIRE(act >= 0 && act <= 2, "linear_tc_fwd2: unknown activation %d", act);
+    MGB_REQUIRE(precision >= 1 && precision <= 3, "linear_tc_fwd2: precision must be 1, 2 or 3");
+    MGB_REQUIRE(ld0 >= 128 && ld1 >= 128 && ld0 % 4 == 0 && ld1 % 4 == 0, "linear_tc_fwd2: row strides must be multiples of 4 floats, >= 128");
+    LinTcArgs a{};
+    if (precision == 3) {
+        int* dev_flag = nullptr;
+        volatile int* host_flag = f16_range_flag(&dev_flag);
+        if (host_flag && *host_flag) {
+            *host_flag = 0;
+            MGB_REQUIRE(false, "linear_tc_fwd2: an earlier fp16-split Linear met |x| >= 32768 (fp16 range); use the fp32 path (set_linear_tc(False)) for this data");
+        }
+        a.range_flag = dev_flag;
+    }
+    a.src[0] = x0; a.ld[0] = ld0; a.src[1] = x1; a.ld[1] = ld1;
+    a.nk = nk; a.nm = nm;
+    for (int m = 0; m < nm; ++m)
+        for (int kc = 0; kc < nk; ++kc) a.tile_of[m][kc] = m * nk + kc;
+    a.wimg = packed; a.bias = bias; a.act = act; a.n_out = out_features;
+    a.y = y; a.ldy = out_features; a.rows = rows;
+    return launch_linear_tc(precision, a, STREAM(stream));
+}
+
 // ---- a whole 128-wide MLP in one launch (mlp_chain_tc.cu): packed = [n_layers][hi | lo images] | [n_layers][128] biases
 size_t mgb_mlp_chain_packed_floats(int n_layers) {
     if (n_layers < 1 || n_layers > 8) return 0;
@@ -250,6 +277,11 @@ int mgb_in_edge_fwd(const float* e_features, float e_scale, const int32_t* perm,
     }
     return launch_in_edge_fwd(precision, e_features, e_scale, perm, pq, rowptr, dst, src, n_nodes, n_edges, packed, agg, dev_flag,
                               workspace, workspace_bytes, STREAM(stream));
+}
+
+int mgb_magnet_features(const float* u, int n_chan, const float* x, int d, const float* t_last, int n_samples, int64_t n_nodes,
+                        const int64_t* edge_index, int64_t n_edges, float* node_features, float* edge_features, void* stream) {
+    return magnet_features(u, n_chan, x, d, t_last, n_samples, n_nodes, edge_index, n_edges, node_features, edge_features, STREAM(stream));
 }
 
 size_t mgb_in_edge_bwd_workspace(int64_t n_edges) { return in_edge_bwd_workspace(n_edges); }
@@ -406,6 +438,11 @@ int mgb_linear_bwd(const float* dy, const float* y_pre, int act, const float* x,
 int mgb_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int cols, float* y,
                       float* stats, void* stream) {
     return launch_layernorm_fwd(x, gamma, beta, y, stats, rows, cols, STREAM(stream));
+}
+
+int mgb_layernorm_residual_fwd(const float* x, const float* gamma, const float* beta, const float* residual, int64_t rows, int cols,
+                               float* y, void* stream) {
+    return launch_layernorm_fwd(x, gamma, beta, y, nullptr, rows, cols, STREAM(stream), residual);
 }
 
 size_t mgb_layernorm_bwd_workspace(int64_t rows, int cols) { return layernorm_bwd_workspace_bytes(rows, cols); }

@@ -325,7 +325,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                     float* __restrict__ y, float* __restrict__ stats, int64_t rows) {
+                     const float* __restrict__ residual, float* __restrict__ y, float* __restrict__ stats, int64_t rows) {
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
@@ -339,15 +339,19 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     float4 o;
     o.x = dx * rstd * gm.x + bt.x; o.y = dy * rstd * gm.y + bt.y;
     o.z = dz * rstd * gm.z + bt.z; o.w = dw * rstd * gm.w + bt.w;
+    if (residual) {                       // x_new + x of InteractionNetwork.forward (models/magnet_gnn.py:88) in the same pass
+        const float4 r = *reinterpret_cast<const float4*>(residual + row * 128 + lane * 4);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
     *reinterpret_cast<float4*>(y + row * 128 + lane * 4) = o;
     if (stats && lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
 }
 
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats, int64_t rows,
-                         int cols, cudaStream_t s) {
+                         int cols, cudaStream_t s, const float* residual) {
     MGB_REQUIRE(cols == 128, "layernorm: only 128 channels are supported (got %d)", cols);
     if (rows == 0) return MGB_OK;
-    layernorm_fwd_kernel<<<(unsigned)ceil_div<int64_t>(rows * 32, 256), 256, 0, s>>>(x, gamma, beta, y, stats, rows);
+    layernorm_fwd_kernel<<<(unsigned)ceil_div<int64_t>(rows * 32, 256), 256, 0, s>>>(x, gamma, beta, residual, y, stats, rows);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }

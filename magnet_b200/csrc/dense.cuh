@@ -76,7 +76,7 @@ int launch_transpose(const float* in, int rows, int cols, int ld_in, float* out,
 
 // y = LayerNorm(x) * gamma + beta, eps 1e-5, biased variance (nn.LayerNorm(128))
 int launch_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* rstd_mean /*[rows][2]*/,
-                         int64_t rows, int cols, cudaStream_t s);
+                         int64_t rows, int cols, cudaStream_t s, const float* residual = nullptr);
 size_t layernorm_bwd_workspace_bytes(int64_t rows, int cols);
 int launch_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* rstd_mean, float* dx,
                          float* dgamma, float* dbeta, int accumulate_params, int64_t rows, int cols, void* ws,

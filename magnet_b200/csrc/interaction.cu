@@ -314,4 +314,41 @@ int inr_decode_bwd(const InrArgs& a, const float* dz, float* G, float* Sx, float
     return MGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// MAgNetGNN._build_graph features (models/magnet_gnn.py:298-308) in one launch instead of ten:
+//   node_features[r] = [u[r, :C], x[r, :d], t_last[r % B]]                    (the time column is TILED: quirk F7)
+//   edge_features[e] = [u[s_e] - u[r_e], x[s_e] - x[r_e]]                     s = edge_index[0], r = edge_index[1]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) magnet_features_kernel(const float* __restrict__ u, int C, const float* __restrict__ x, int d,
+                                                              const float* __restrict__ t_last, int B, int64_t n_nodes,
+                                                              const int64_t* __restrict__ edge_index, int64_t n_edges,
+                                                              float* __restrict__ nf, float* __restrict__ ef) {
+    const int wn = C + d + 1, we = C + d;
+    const int64_t total_n = n_nodes * wn, total = total_n + n_edges * we;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < total_n) {
+            const int64_t r = i / wn;
+            const int c = (int)(i - r * wn);
+            nf[i] = c < C ? u[r * C + c] : (c < C + d ? x[r * d + (c - C)] : t_last[r % B]);
+        } else {
+            const int64_t j = i - total_n, e = j / we;
+            const int c = (int)(j - e * we);
+            const int64_t sn = edge_index[e], rc = edge_index[n_edges + e];
+            ef[j] = c < C ? u[sn * C + c] - u[rc * C + c] : x[sn * d + (c - C)] - x[rc * d + (c - C)];
+        }
+    }
+}
+
+int magnet_features(const float* u, int C, const float* x, int d, const float* t_last, int B, int64_t n_nodes,
+                    const int64_t* edge_index, int64_t n_edges, float* nf, float* ef, cudaStream_t s) {
+    MGB_REQUIRE(C >= 1 && d >= 1 && B >= 1 && n_nodes >= 0 && n_edges >= 0, "magnet_features: bad sizes");
+    const int64_t total = n_nodes * (C + d + 1) + n_edges * (C + d);
+    if (total == 0) return MGB_OK;
+    const int64_t nb = ceil_div<int64_t>(total, 256);
+    const int blocks = (int)(nb < (int64_t)sm_count() * 16 ? nb : (int64_t)sm_count() * 16);
+    magnet_features_kernel<<<blocks, 256, 0, s>>>(u, C, x, d, t_last, B, n_nodes, edge_index, n_edges, nf, ef);
+    MGB_LAUNCH_CHECK();
+    return MGB_OK;
+}
+
 }  // namespace mgb

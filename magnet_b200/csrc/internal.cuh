@@ -72,6 +72,8 @@ int relu_mask(const float* dout, const float* out, int64_t n, float* dz, cudaStr
 int segment_sum_rows(const float* rows, int cols, const int32_t* rowptr, const int32_t* idx, int64_t n_nodes, int mean,
                      float* out, int ld_out, cudaStream_t s);
 int gather_rows(const float* rows, const int64_t* index, const int32_t* rowptr, int64_t n_edges, float* out, cudaStream_t s);
+int magnet_features(const float* u, int C, const float* x, int d, const float* t_last, int B, int64_t n_nodes,
+                    const int64_t* edge_index, int64_t n_edges, float* nf, float* ef, cudaStream_t s);
 struct InrArgs {
     const float* A;          // [B*L][128]
     const float* xlr;        // [B][T][L]

@@ -416,6 +416,51 @@ def linear_act(x, W, b, act: str = "none", residual=None, owner=None):
 
 
 @_lib.guard
+def magnet_features(u_, x_, t_last, edge_index):
+    """(node_features, edge_features) of MAgNetGNN._build_graph (models/magnet_gnn.py:298-308) in one launch (inference):
+    u_ [N,C], x_ [N,d], t_last [B] (tiled over the rows: quirk F7), edge_index int64 [2,E]."""
+    L = _lib.lib()
+    u_, x_, t_last = _lib.f32c(u_), _lib.f32c(x_), _lib.f32c(t_last)
+    ei = edge_index.contiguous()
+    N, C, d, E = u_.shape[0], u_.shape[1], x_.shape[1], ei.shape[1]
+    nf, ef = _empty((N, C + d + 1), u_), _empty((E, C + d), u_)
+    _lib.check(L.mgb_magnet_features(_lib.ptr(u_), C, _lib.ptr(x_), d, _lib.ptr(t_last), t_last.numel(), N, _lib.ptr(ei), E,
+                                     _lib.ptr(nf), _lib.ptr(ef), _lib.stream()), "magnet_features")
+    return nf, ef
+
+
+@_lib.guard
+def linear_act2(x0, x1, W, b, act: str = "none"):
+    """act(cat([x0, x1], -1) W^T + b) for two [rows, 128] tensors without the concatenation (inference; returns None when the
+    tensor-core path does not cover the shape and the caller should concatenate)."""
+    packed = _tc_weight_images(W)
+    if (packed is None or x0.shape != x1.shape or x0.shape[-1] != 128 or W.shape[1] != 256 or W.shape[0] > 256
+            or not _no_grad_needed(x0, x1, W, b)):
+        return None
+    L = _lib.lib()
+    a0, a1 = _lib.f32c(x0).reshape(-1, 128), _lib.f32c(x1).reshape(-1, 128)
+    rows, fout = a0.shape[0], W.shape[0]
+    y = _empty((rows, fout), a0)
+    _lib.check(L.mgb_linear_tc_fwd2(_lib.ptr(a0), 128, _lib.ptr(a1), 128, rows, fout, _lib.ptr(packed), _lib.ptr(_lib.f32c(b.detach())),
+                                    ACT[act], _lib.ptr(y), 2 if _precision == "bf16" else _LINEAR_TC_PRECISION, _lib.stream()),
+               "linear_tc_fwd2")
+    return y.reshape(*x0.shape[:-1], fout)
+
+
+@_lib.guard
+def layer_norm_residual(x, gamma, beta, residual):
+    """LayerNorm(x) + residual in one pass (inference)."""
+    if not _no_grad_needed(x, gamma, beta, residual) or x.shape[-1] != 128:
+        return layer_norm(x, gamma, beta) + residual
+    L = _lib.lib()
+    x2, r2 = _lib.f32c(x).reshape(-1, 128), _lib.f32c(residual).reshape(-1, 128)
+    y = _empty(x2.shape, x2)
+    _lib.check(L.mgb_layernorm_residual_fwd(_lib.ptr(x2), _lib.ptr(_lib.f32c(gamma.detach())), _lib.ptr(_lib.f32c(beta.detach())), _lib.ptr(r2),
+                                            x2.shape[0], 128, _lib.ptr(y), _lib.stream()), "layernorm_residual_fwd")
+    return y.reshape(x.shape)
+
+
+@_lib.guard
 def _layernorm_forward(x, gamma, beta):
     _lib.require_cuda(x, gamma)
     L = _lib.lib()

@@ -142,6 +142,18 @@ class InteractionNetwork(nn.Module):
             h0 = MF.edge_combine(p, q, r, edge_index, plan, "relu")      # ReLU of the first Linear, fused into the gather
             m = _mlp_ln(self.edge_fn, None, first_preact=h0)
             agg = MF.scatter_mean(m, edge_index, plan)
+        nlin = self.node_fn[0].linears()
+        h0 = MF.linear_act2(agg, x, nlin[0].weight, nlin[0].bias, "relu") if (not torch.is_grad_enabled() and
+                                                                             self.node_fn[0].activation == "relu") else None
+        if h0 is not None:
+            # inference: no cat([agg, x]), the MLP behind its first Linear as one launch, LayerNorm + residual in one pass
+            y = MF.mlp_chain(h0, nlin[1:], "relu", cache_owner=self.node_fn[0])
+            if y is None:
+                y = self.node_fn[0](None, first_preact=h0)
+            out = MF.layer_norm_residual(y, self.node_fn[1].weight, self.node_fn[1].bias, x)
+            if not return_e:
+                return out, None
+            return out, (e_features + e_features if e_scale == 1.0 else e_features * (2.0 * e_scale))
         x_new = _mlp_ln(self.node_fn, torch.cat([agg, x], dim=-1))
         if not return_e:
             return x_new + x, None
@@ -284,9 +296,12 @@ class MAgNetGNN(LightningModule):
         u_ = u.reshape(B * N, -1)
         x_ = x.reshape(B * N, -1)
         edge_index, plan = self._edges(x_, x if cache_key is None else cache_key, B, N)
-        senders, receivers = edge_index[0], edge_index[1]
-        node_features = torch.cat([u_, x_, t[:, -1:].repeat(N, 1)], dim=-1)       # time is TILED (quirk F7)
-        edge_features = torch.cat([u_[senders] - u_[receivers], x_[senders] - x_[receivers]], dim=-1)
+        if not torch.is_grad_enabled() and u_.is_cuda and u_.dtype == torch.float32:
+            node_features, edge_features = MF.magnet_features(u_, x_, t[:, -1], edge_index)       # one launch (inference)
+        else:
+            senders, receivers = edge_index[0], edge_index[1]
+            node_features = torch.cat([u_, x_, t[:, -1:].repeat(N, 1)], dim=-1)       # time is TILED (quirk F7)
+            edge_features = torch.cat([u_[senders] - u_[receivers], x_[senders] - x_[receivers]], dim=-1)
         if return_plan:
             return node_features, edge_index, edge_features, plan
         return node_features, edge_index, edge_features
