@@ -338,7 +338,7 @@ def bench_mp_layer(env, clocks):
     total_ms, launches = env.timed(lambda: step(d["x"], d["u"], d["pos"], d["var"], d["gy"]), args.steps, args.warmup, clocks)
     if args.steps * 0.025 < 0.12:
         time.sleep(0.12)          # a very short timed region: let the sample that covers it arrive before nvidia-smi is stopped
-    prof = {"edge_fwd": env.prof(0), "edge_bwd": env.prof(1)}
+    prof = {"edge_fwd": env.prof(0), "edge_bwd": env.prof(1), "node_gemm": env.prof(2), "wgrad": env.prof(3)}
     # ---- end to end: pinned host inputs -> H2D -> 5 layers fwd+bwd -> D2H of the result checksum ----
     # Every step copies its own inputs from pinned host memory (double-buffered on a side stream: the transfer of step k+1
     # overlaps the kernels of step k) and reads its result back (a training step's result is its loss-like scalar: 4 bytes).
@@ -402,6 +402,9 @@ def bench_mp_layer(env, clocks):
                 "executed_tflops": 3 * EXEC_FLOP_PER_EDGE_FWD * E / (bwd_ms * 1e-3) / 1e12 if bwd_ms > 0 else 0.0,
                 "edge_fwd_kernel_ms": fwd_ms,
                 "edge_fwd_algorithmic_tflops": FLOP_PER_EDGE_FWD * E / (fwd_ms * 1e-3) / 1e12 if fwd_ms > 0 else 0.0,
+                # node-level stages (row-wise Linears and weight gradients on [N,128] tensors): HBM-bound kernels
+                "node_linear_ms_per_step": prof["node_gemm"][0] / max(args.steps, 1), "node_linear_launches_per_step": prof["node_gemm"][1] // max(args.steps, 1),
+                "node_wgrad_ms_per_step": prof["wgrad"][0] / max(args.steps, 1), "node_wgrad_launches_per_step": prof["wgrad"][1] // max(args.steps, 1),
                 "note": {"fp32": "fp32 FFMA path (1e-5 contract) measured against the bf16 tensor peak",
                          "fp32_tc": "tcgen05 bf16 hi/lo split, 3 MMAs per product, fp32 accumulate (1e-5 contract)",
                          "bf16": "tcgen05 bf16 operands, fp32 accumulate (1e-2 contract)"}[args.precision]}

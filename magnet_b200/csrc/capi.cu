@@ -505,6 +505,7 @@ int mgb_inr_decode_bwd(const float* a, const float* xlr, const float* lr_coords,
 int mgb_debug_set_timeline(long long* p) { return mgb::set_timeline_buffer(p); }
 int mgb_debug_set_ie_timeline(long long* p) { return mgb::set_ie_timeline_buffer(p); }
 int mgb_debug_set_ib_timeline(long long* p) { return mgb::set_ib_timeline_buffer(p); }
+int mgb_debug_set_lt_timeline(long long* p) { return mgb::set_lt_timeline_buffer(p); }
 #endif
 
 int mgb_umma_selftest(const float* a, const float* b, int a_mn_major, int b_mn_major, int lbo_mn, int sbo_mn, float* d,

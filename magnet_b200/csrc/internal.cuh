@@ -145,6 +145,7 @@ int launch_tail_dgrad(const float* dy, int lddy, int ny, const float* pre, int l
 int set_timeline_buffer(long long* p);
 int set_ie_timeline_buffer(long long* p);
 int set_ib_timeline_buffer(long long* p);
+int set_lt_timeline_buffer(long long* p);
 #endif
 // mlp_chain_tc.cu (a whole 128-wide MLP in one launch, forward only)
 struct CellPoint;

@@ -16,9 +16,23 @@
 namespace mgb {
 
 constexpr int LT_EPI_WARPS = 8, LT_PROD_WARPS = 8;
-constexpr int LT_MMA_WARP = LT_EPI_WARPS, LT_PROD_WARP0 = LT_EPI_WARPS + 1;
-constexpr int LT_THREADS = (LT_EPI_WARPS + 1 + LT_PROD_WARPS) * 32;   // 544
+// whole warpgroups, so that registers can follow the work (setmaxnreg): warps 0-7 epilogue, 8 MMA issue, 9-11 idle,
+// 12-19 producers; 640 threads x 96 registers at launch -> 112 for the epilogue, 104 for the producers, 40 for the rest
+// (setmaxnreg.inc can only take what the CTA's own warps have released: (96 - 40) x 128 = 7168 >= 16 x 256 + 8 x 256)
+constexpr int LT_MMA_WARP = LT_EPI_WARPS, LT_PROD_WARP0 = LT_EPI_WARPS + 4;
+constexpr int LT_THREADS = (LT_PROD_WARP0 + LT_PROD_WARPS) * 32;      // 640
+constexpr int LT_REGS_EPI = 112, LT_REGS_PROD = 104, LT_REGS_IDLE = 40;
 constexpr int LT_TAIL = 16;
+
+#ifdef MGB_TIMELINE
+__device__ long long* g_lt_timeline = nullptr;      // [role 0..4][tile 0..7][event 0..3] of CTA 0 (tools/dev_lt_timeline.py); roles 3, 4: wgrad producer / MMA
+#define LTTL(role, it_, ev) do { if (blockIdx.x == 0 && (it_) < 8 && (threadIdx.x & 31) == 0 && g_lt_timeline) g_lt_timeline[((role) * 8 + (it_)) * 4 + (ev)] = clock64(); } while (0)
+int set_lt_timeline_buffer(long long* p) {
+    return cudaMemcpyToSymbol(g_lt_timeline, &p, sizeof(p)) == cudaSuccess ? MGB_OK : MGB_ERR_CUDA;
+}
+#else
+#define LTTL(role, it_, ev) do { } while (0)
+#endif
 
 // L2 prefetch of 16 rows x 512 bytes (64 lines of 128 bytes, two per lane): the row loads of the next tile and the 4-byte
 // residual loads of the epilogue then hit L2 instead of paying the HBM latency in the middle of the pipeline
@@ -80,9 +94,9 @@ int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int
     return MGB_OK;
 }
 
-// 2 weight tiles (always hi|lo) + one B stage + 2 tail tiles; with a single weight tile the second weight slot
-// serves as a second B stage
-constexpr size_t LINEAR_TC_SMEM = 1024 + (size_t)4 * TILE_BYTES + (size_t)2 * TILE_BYTES + 2 * 128 * LT_TAIL * sizeof(float) + 256;
+// 2 weight tiles (always hi|lo) + one B stage + 2 tail tiles + the tail weights; with a single weight tile the second
+// weight slot serves as a second B stage
+constexpr size_t LINEAR_TC_SMEM = 1024 + (size_t)4 * TILE_BYTES + (size_t)2 * TILE_BYTES + 4 * 128 * LT_TAIL * sizeof(float) + 256;
 
 // All role loops are kept small on purpose: the three roles of a CTA run at the same time and share the SM's
 // 32 KB instruction cache (a fully unrolled version of this kernel was 100 KB of SASS and fetch-bound).
@@ -96,7 +110,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
     unsigned char* w_img = base;                                        // [2 tiles][hi|lo]
     unsigned char* b_img = w_img + (size_t)4 * TILE_BYTES;               // B stage 0 (NSPLIT = 1: stages 0 and 1)
     float* tails = reinterpret_cast<float*>(b_img + (size_t)2 * TILE_BYTES);   // [2][128][LT_TAIL]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tails + 2 * 128 * LT_TAIL);
+    float* wts = tails + 2 * 128 * LT_TAIL;                                    // [2 output blocks][LT_TAIL][128] tail weights
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wts + 2 * 128 * LT_TAIL);
     uint64_t* full = bars;            // [2]
     uint64_t* empty = bars + 2;       // [2]
     uint64_t* tfull = bars + 4;       // [2] accumulators ready
@@ -134,115 +149,151 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
     const uint32_t tmem = *tmem_slot;
 
     if (warp < LT_EPI_WARPS) {
+        umma::reg_inc<LT_REGS_EPI>();
         // =========================== epilogue: thread = output channel within the block; warps 0-3 rows 0-63 of the
         // tile, warps 4-7 rows 64-127 ====================================================================
+        // Sixteen rows per step, software-pipelined: the TMEM load and the residual loads of the next step are in flight
+        // while this one is processed (two register sets alternate), and the first residual loads of a tile go out
+        // before its accumulator is waited for.  Addressing is one walking pointer per stream (y, y_pre, residual) and
+        // 32-bit row limits: with 64-bit index arithmetic per element the 4-byte accesses cost ~9 instructions each and
+        // the epilogue, not HBM, bound the kernel (ncu: 49 warp-instructions per output element before, round 2).
         const int n = tid & 127;
         const int hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int ldy = a.ldy, ldyp = a.ldyp, ldr = a.ldr, kt = a.kt, act = a.act;
+        float bias_m[2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int col = m * 128 + n;
+            const bool col_ok = m < a.nm && (a.n_out == 0 || col < a.n_out);
+            bias_m[m] = (a.bias && col_ok) ? a.bias[col] : 0.f;
+            // the tail weights of this thread's output column: wts[m][t][n] (both halves write the same values; a thread
+            // only ever reads what it wrote itself)
+            if (kt > 0) {
+                for (int t = 0; t < LT_TAIL; ++t)
+                    wts[(m * LT_TAIL + t) * 128 + n] = (col_ok && t < kt) ? a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st] : 0.f;
+            }
+        }
 #pragma unroll 1
         for (int it = 0; it < nt; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128;
             const int nr = (int)((a.rows - r0) < 128 ? (a.rows - r0) : 128);
-            const float* tl = tails + acc * 128 * LT_TAIL;
-            if (a.kt > 0) umma::mbar_wait(&tailfull[acc], aph);
-            umma::mbar_wait(&tfull[acc], aph);
-            umma::tc_fence_after();
+            const int rlim = nr - hf * 64;           // valid rows among the 64 of this half
+            const int64_t rb = r0 + hf * 64;
+            const float* tl = tails + acc * 128 * LT_TAIL + hf * 64 * LT_TAIL;
+            bool waited = false;
 #pragma unroll 1
             for (int m = 0; m < a.nm; ++m) {
                 const int col = m * 128 + n;
                 const bool col_ok = a.n_out == 0 || col < a.n_out;
-                const float bias = (a.bias && col_ok) ? a.bias[col] : 0.f;
-                float wt[LT_TAIL];
-#pragma unroll
-                for (int t = 0; t < LT_TAIL; ++t) wt[t] = 0.f;
-                if (a.kt > 0 && col_ok) {
-#pragma unroll
-                    for (int t = 0; t < LT_TAIL; ++t)
-                        if (t < a.kt) wt[t] = a.wtail[(int64_t)col * a.wt_sn + (int64_t)t * a.wt_st];
-                }
+                const float bias = m ? bias_m[1] : bias_m[0];
+                const float* wt = wts + m * LT_TAIL * 128 + n;
                 const bool last_m = m == a.nm - 1;
-                // residual values two chunks ahead of the chunk being processed (4-byte loads, one coalesced 128-byte
-                // line per warp and row: their latency must not sit between two chunks)
-                const float* rp = (a.residual && col_ok && (a.res_blocks == 0 || ((a.res_blocks >> m) & 1))) ? a.residual + (r0 + hf * 64) * a.ldr + col : nullptr;
-                const int rlim = nr - hf * 64;
-                float rn1[8], rn2[8];
+                const int vlim = col_ok ? rlim : 0;      // rows this thread stores
+                const bool has_res = a.residual && col_ok && (a.res_blocks == 0 || ((a.res_blocks >> m) & 1));
+                const float* rp = has_res ? a.residual + rb * ldr + col : nullptr;      // walks one step ahead of yo
+                float* yo = a.y + rb * ldy + col;
+                float* yp = a.y_pre ? a.y_pre + rb * ldyp + col : nullptr;
+                const uint32_t tacc = tmem + (uint32_t)((acc * 2 + m) * 128) + lane_base + (uint32_t)(hf * 64);
+                // residual values of rows c .. c+15 (4-byte loads, one coalesced 128-byte line per warp and row)
+                auto load_res = [&](float (&dst)[16], int c) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { rn1[i] = 0.f; rn2[i] = 0.f; }
-                if (rp) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        rn1[i] = i < rlim ? rp[(int64_t)i * a.ldr] : 0.f;
-                        rn2[i] = 8 + i < rlim ? rp[(int64_t)(8 + i) * a.ldr] : 0.f;
+                    for (int i = 0; i < 16; ++i) {
+                        dst[i] = 0.f;
+                        if (c + i < vlim) dst[i] = *rp;
+                        rp += ldr;
                     }
-                }
+                };
+                auto step = [&](int c, const uint32_t (&raw)[16], const float (&res)[16]) {
+                    if (c >= vlim) return;
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+                    if (kt > 0) {
 #pragma unroll 1
-                for (int cb = 0; cb < 64; cb += 8) {
-                    const int c0 = hf * 64 + cb;
-                    float v[8], res[8];
-                    if (rp) {
+                        for (int t4 = 0; t4 * 4 < kt; ++t4) {
+                            const float w0 = wt[(t4 * 4 + 0) * 128], w1 = wt[(t4 * 4 + 1) * 128], w2 = wt[(t4 * 4 + 2) * 128], w3 = wt[(t4 * 4 + 3) * 128];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { res[i] = rn1[i]; rn1[i] = rn2[i]; }
-                        if (cb + 16 < 64) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) rn2[i] = cb + 16 + i < rlim ? rp[(int64_t)(cb + 16 + i) * a.ldr] : 0.f;
-                        }
-                    }
-                    umma::tmem_ld8(tmem + (uint32_t)((acc * 2 + m) * 128) + lane_base + c0, v);
-                    if (last_m && cb + 8 >= 64 && a.kt == 0) {
-                        umma::tc_fence_before();
-                        umma::mbar_arrive(&tempty[acc]);
-                    }
-                    if (c0 >= nr) continue;
-                    if (a.kt > 0) {
-#pragma unroll
-                        for (int t4 = 0; t4 < LT_TAIL / 4; ++t4) {
-                            if (t4 * 4 < a.kt) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const float4 x = *reinterpret_cast<const float4*>(tl + (c0 + i) * LT_TAIL + t4 * 4);
-                                    v[i] = fmaf(x.x, wt[t4 * 4 + 0], v[i]);
-                                    v[i] = fmaf(x.y, wt[t4 * 4 + 1], v[i]);
-                                    v[i] = fmaf(x.z, wt[t4 * 4 + 2], v[i]);
-                                    v[i] = fmaf(x.w, wt[t4 * 4 + 3], v[i]);
-                                }
+                            for (int i = 0; i < 16; ++i) {
+                                const float4 x = *reinterpret_cast<const float4*>(tl + (c + i) * LT_TAIL + t4 * 4);
+                                v[i] = fmaf(x.x, w0, v[i]);
+                                v[i] = fmaf(x.y, w1, v[i]);
+                                v[i] = fmaf(x.z, w2, v[i]);
+                                v[i] = fmaf(x.w, w3, v[i]);
                             }
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] += bias;
-                    const int lim = col_ok ? nr - c0 : 0;
-                    const int64_t row0 = r0 + c0;
-                    if (a.y_pre) {
-                        float* yp = a.y_pre + row0 * a.ldyp + col;
+                    for (int i = 0; i < 16; ++i) v[i] += bias;
+                    const int lim = vlim - c;
+                    if (yp) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (i < lim) yp[(int64_t)i * a.ldyp] = v[i];
+                        for (int i = 0; i < 16; ++i) {
+                            if (i < lim) *yp = v[i];
+                            yp += ldyp;
+                        }
                     }
-                    if (a.act == ACT_SWISH) {
+                    if (act == ACT_SWISH) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = swish_tc<FAST>(v[i]);
-                    } else if (a.act == ACT_RELU) {
+                        for (int i = 0; i < 16; ++i) v[i] = swish_tc<FAST>(v[i]);
+                    } else if (act == ACT_RELU) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                     }
-                    if (rp) {
+                    if (has_res) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] += res[i];
+                        for (int i = 0; i < 16; ++i) v[i] += res[i];
                     }
-                    float* yo = a.y + row0 * a.ldy + col;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i < lim) yo[(int64_t)i * a.ldy] = v[i];
+                    for (int i = 0; i < 16; ++i) {
+                        if (i < lim) *yo = v[i];
+                        yo += ldy;
+                    }
+                };
+                uint32_t va[16], vb[16];
+                float ra[16], rc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { ra[i] = 0.f; rc[i] = 0.f; }
+                if (has_res) load_res(ra, 0);
+                if (!waited) {
+                    if (warp == 0) LTTL(2, it, 0);
+                    if (kt > 0) umma::mbar_wait(&tailfull[acc], aph);
+                    umma::mbar_wait(&tfull[acc], aph);
+                    umma::tc_fence_after();
+                    waited = true;
+                    if (warp == 0) LTTL(2, it, 1);
+                }
+                umma::tmem_ld16_issue(tacc, va);
+#pragma unroll 1
+                for (int c = 0; c < 64; c += 32) {
+                    if (has_res) load_res(rc, c + 16);
+                    umma::tmem_ld_wait16(va);
+                    if (warp == 0 && c == 0 && m == 0) LTTL(2, it, 2);
+                    umma::tmem_ld16_issue(tacc + (uint32_t)(c + 16), vb);
+                    step(c, va, ra);
+                    if (has_res && c + 32 < 64) load_res(ra, c + 32);
+                    umma::tmem_ld_wait16(vb);
+                    if (c + 32 < 64) {
+                        umma::tmem_ld16_issue(tacc + (uint32_t)(c + 32), va);
+                    } else if (last_m && kt == 0) {      // this thread's part of the accumulators is in registers: hand them back
+                        umma::tc_fence_before();
+                        umma::mbar_arrive(&tempty[acc]);
+                    }
+                    step(c + 16, vb, rc);
                 }
             }
-            if (a.kt > 0) {          // the tail tile is read until the end: release accumulators and tail together
+            if (kt > 0) {          // the tail tile is read until the end: release accumulators and tail together
                 umma::tc_fence_before();
                 umma::mbar_arrive(&tempty[acc]);
             }
+            if (warp == 0) LTTL(2, it, 3);
         }
+    } else if (warp < LT_PROD_WARP0 && warp != LT_MMA_WARP) {
+        umma::reg_dec<LT_REGS_IDLE>();          // padding warps of the MMA warpgroup
     } else if (warp == LT_MMA_WARP) {
+        umma::reg_dec<LT_REGS_IDLE>();
         // =========================== MMA issue ====================================================
         if (lane == 0) load_w2_image(w_img, (const unsigned char*)a.wimg, (uint32_t)(n_wtiles * 2 * TILE_BYTES), wbar);   // global images always hold hi|lo
         umma::mbar_wait(wbar, 0);
@@ -263,6 +314,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                 const int s = sc % bstages;
                 umma::mbar_wait(&full[s], (sc / bstages) & 1);
                 umma::tc_fence_after();
+                LTTL(1, it, kc == 0 ? 0 : 2);
                 if (umma::elect_one()) {
                     const uint64_t bd = s ? b_d1 : b_d0;
 #pragma unroll 1
@@ -287,21 +339,36 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                     if (kc == a.nk - 1) umma::mma_commit(&tfull[acc]);
                 }
                 __syncwarp();
+                LTTL(1, it, kc == 0 ? 1 : 3);
             }
         }
     } else {
+        umma::reg_inc<LT_REGS_PROD>();
         // =========================== producers: 16 rows per warp ===================================
         // x rows -> (optional act'(pre) / act) -> bf16 hi/lo in place in the registers the rows came in, all before the
-        // stage is waited for; only the stores follow its release
+        // stage is waited for; only the stores follow its release.  Rows are reached through one walking pointer that
+        // stops at the warp's last valid row (rows past the end repeat it and are zeroed afterwards).
         const int pw = warp - LT_PROD_WARP0;
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
+        // this lane's slot of the tail tile: t = lane & 15 for every element e = j*32 + lane it writes (row j*2 + lane / 16)
+        const float* tail_p = nullptr;
+        int tail_ld = 0;
+        if (a.kt > 0 && (lane & 15) < a.kt) {
+            int tt = lane & 15, seg = 0;
+            while (tt >= a.tk[seg]) { tt -= a.tk[seg]; ++seg; }
+            tail_p = a.tsrc[seg] + tt;
+            tail_ld = a.tld[seg];
+        }
         int sc = 0;
 #pragma unroll 1
         for (int it = 0; it < nt; ++it) {
             const int acc = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + pw * 16;
+            const int64_t left = a.rows - r0;
+            const int nv = left >= 16 ? 16 : (left > 0 ? (int)left : 0);       // valid rows of this warp
+            const int64_t rfirst = nv > 0 ? r0 : a.rows - 1;
             {
                 const int64_t rn = r0 + (int64_t)gridDim.x * 128;      // this warp's rows of the CTA's next tile
                 for (int kc = 0; kc < a.nk; ++kc) prefetch_rows16(a.src[kc], a.ld[kc], rn, a.rows, lane);
@@ -310,53 +377,54 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
             }
             if (a.kt > 0) {
                 umma::mbar_wait(&tempty[acc], aph ^ 1);
-                float* tl = tails + acc * 128 * LT_TAIL + pw * 16 * LT_TAIL;
+                float* tl = tails + acc * 128 * LT_TAIL + pw * 16 * LT_TAIL + lane;
                 // 16 rows x 16 tail slots = 256 values, 8 per lane
-#pragma unroll 1
+                const float* tp = tail_p ? tail_p + (r0 + (lane >> 4)) * tail_ld : nullptr;
+                const int rr = lane >> 4;
+#pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int e = j * 32 + lane, r = e >> 4, t = e & 15;
                     float v = 0.f;
-                    if (r0 + r < a.rows && t < a.kt) {
-                        int tt = t, seg = 0;
-                        while (tt >= a.tk[seg]) { tt -= a.tk[seg]; ++seg; }
-                        v = a.tsrc[seg][(r0 + r) * a.tld[seg] + tt];
-                    }
-                    tl[r * LT_TAIL + t] = v;
+                    if (tp && j * 2 + rr < nv) v = *tp;
+                    if (tp) tp += 2 * tail_ld;
+                    tl[j * 32] = v;
                 }
                 umma::mbar_arrive(&tailfull[acc]);
             }
 #pragma unroll 1
             for (int kc = 0; kc < a.nk; ++kc, ++sc) {
                 const int s = sc % bstages;
-                const float* src = a.src[kc] + lane * 4;
                 const int ld = a.ld[kc];
                 float4 x[16];
+                {
+                    const float* p = a.src[kc] + rfirst * ld + lane * 4;
 #pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                    x[r] = *reinterpret_cast<const float4*>(src + row * ld);
+                    for (int r = 0; r < 16; ++r) {
+                        x[r] = *reinterpret_cast<const float4*>(p);
+                        if (r + 1 < nv) p += ld;
+                    }
                 }
                 if (kc == 0 && a.pre) {
-                    const float* pre = a.pre + lane * 4;
+                    const float* p = a.pre + rfirst * a.ldpre + lane * 4;
+                    const int ldp = a.ldpre;
                     if (a.pre_act == ACT_SWISH) {
 #pragma unroll 4
                         for (int r = 0; r < 16; ++r) {
-                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldpre);
-                            x[r].x *= swish_grad_tc<FAST>(p.x);
-                            x[r].y *= swish_grad_tc<FAST>(p.y);
-                            x[r].z *= swish_grad_tc<FAST>(p.z);
-                            x[r].w *= swish_grad_tc<FAST>(p.w);
+                            const float4 q = *reinterpret_cast<const float4*>(p);
+                            if (r + 1 < nv) p += ldp;
+                            x[r].x *= swish_grad_tc<FAST>(q.x);
+                            x[r].y *= swish_grad_tc<FAST>(q.y);
+                            x[r].z *= swish_grad_tc<FAST>(q.z);
+                            x[r].w *= swish_grad_tc<FAST>(q.w);
                         }
                     } else if (a.pre_act == ACT_RELU) {
 #pragma unroll 4
                         for (int r = 0; r < 16; ++r) {
-                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldpre);
-                            x[r].x = p.x > 0.f ? x[r].x : 0.f;
-                            x[r].y = p.y > 0.f ? x[r].y : 0.f;
-                            x[r].z = p.z > 0.f ? x[r].z : 0.f;
-                            x[r].w = p.w > 0.f ? x[r].w : 0.f;
+                            const float4 q = *reinterpret_cast<const float4*>(p);
+                            if (r + 1 < nv) p += ldp;
+                            x[r].x = q.x > 0.f ? x[r].x : 0.f;
+                            x[r].y = q.y > 0.f ? x[r].y : 0.f;
+                            x[r].z = q.z > 0.f ? x[r].z : 0.f;
+                            x[r].w = q.w > 0.f ? x[r].w : 0.f;
                         }
                     }
                 }
@@ -373,11 +441,15 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                         x[r].z = fmaxf(x[r].z, 0.f); x[r].w = fmaxf(x[r].w, 0.f);
                     }
                 }
+                if (nv < 16) {        // the last tile of the problem only
+#pragma unroll
+                    for (int r = 0; r < 16; ++r)
+                        if (r >= nv) x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
                 uint4 hl[16];
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
-                    float4 h = x[r];
-                    if (r0 + r >= a.rows) h = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 h = x[r];
                     if (NSPLIT == 1) {
                         hl[r].x = umma::pack_bf16(h.x, h.y);
                         hl[r].y = umma::pack_bf16(h.z, h.w);
@@ -393,7 +465,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                         }
                     }
                 }
+                if (pw == 0 && kc == 0) LTTL(0, it, 0);
                 umma::mbar_wait(&empty[s], ((sc / bstages) & 1) ^ 1);
+                if (pw == 0 && kc == 0) LTTL(0, it, 1);
                 unsigned char* img = b_stage(s);
 #pragma unroll
                 for (int r = 0; r < 16; ++r) {
@@ -403,6 +477,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                 }
                 umma::fence_async_smem();
                 umma::mbar_arrive(&full[s]);
+                if (pw == 0) LTTL(0, it, kc == 0 ? 2 : 3);
             }
         }
     }
@@ -488,13 +563,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
     const uint32_t tmem = *tmem_slot;
 
     if (warp < LT_EPI_WARPS) {
+        umma::reg_dec<LT_REGS_IDLE + 24>();
         // =========================== drain: thread = output channel n; warps 0-3 columns 0-63, warps 4-7 columns 64-127
         const int n = tid & 127, hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const int ngroups = (nt + GROUP - 1) / GROUP;
 #pragma unroll 1
         for (int grp = 0; grp < ngroups; ++grp) {
-            umma::mbar_wait(d_full, grp & 1);
+            umma::mbar_wait_relaxed<500>(d_full, grp & 1);       // a group is eight row tiles away: do not poll in the producers' issue slots
             umma::tc_fence_after();
 #pragma unroll 1
             for (int ac = 0; ac < nacc; ++ac) {
@@ -520,7 +596,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                 }
             }
         }
+    } else if (warp < LT_PROD_WARP0 && warp != LT_MMA_WARP) {
+        umma::reg_dec<LT_REGS_IDLE>();          // padding warps of the MMA warpgroup
     } else if (warp == LT_MMA_WARP) {
+        umma::reg_dec<LT_REGS_IDLE>();
         const uint32_t idesc = umma::idesc_bf16(128, 128, 1, 1);
         const uint64_t y_d = umma::desc_sw128(umma::smem_u32(y_img), 128 * 128, 1024);
         const uint64_t x_d0 = umma::desc_sw128(umma::smem_u32(x_stage(0)), 128 * 128, 1024);
@@ -534,11 +613,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
             const bool last = it == nt - 1;
             if (first_in_group) umma::mbar_wait(d_empty, (grp & 1) ^ 1);
             umma::mbar_wait(y_full, it & 1);
+            LTTL(4, it, 0);
 #pragma unroll 1
             for (int xi = 0; xi < nxt; ++xi, ++sc) {
                 const int s = sc % xstages;
                 umma::mbar_wait(&x_full[s], (sc / xstages) & 1);
                 umma::tc_fence_after();
+                LTTL(4, it, xi == 0 ? 1 : 2);
                 if (umma::elect_one()) {
                     const uint64_t xd = s ? x_d1 : x_d0;
 #pragma unroll 1
@@ -561,20 +642,26 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                     }
                 }
                 __syncwarp();
+                if (xi == nxt - 1) LTTL(4, it, 3);
             }
         }
     } else {
+        umma::reg_inc<152>();
         // =========================== producers: 16 rows per warp ===================================
         const int pw = warp - LT_PROD_WARP0;
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
         // 16 rows of one operand tile: converted in place in the registers the rows came in; only the stores follow the wait
-        auto store_tile = [&](float4 (&x)[16], int64_t r0, unsigned char* img, uint64_t* bar, uint32_t parity) {
+        auto store_tile = [&](float4 (&x)[16], int nv, unsigned char* img, uint64_t* bar, uint32_t parity) {
+            if (nv < 16) {        // the last tile of the problem only
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    if (r >= nv) x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             uint4 hl[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
-                float4 h = x[r];
-                if (r0 + r >= a.rows) h = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 h = x[r];
                 if (NSPLIT == 1) {
                     hl[r].x = umma::pack_bf16(h.x, h.y);
                     hl[r].y = umma::pack_bf16(h.z, h.w);
@@ -591,6 +678,14 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                 if (NSPLIT == 2) *reinterpret_cast<uint2*>(img + TILE_BYTES + off) = make_uint2(hl[r].z, hl[r].w);
             }
             umma::fence_async_smem();
+        };
+        // 16 rows x this lane's four columns through one walking pointer that stops at the warp's last valid row
+        auto load_rows = [&](float4 (&x)[16], const float* p, int ld, int nv) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                x[r] = *reinterpret_cast<const float4*>(p);
+                if (r + 1 < nv) p += ld;
+            }
         };
         // this lane's four columns of the tail tile: source pointer (column already applied) and row stride, or a constant
         const float* tp[4];
@@ -611,6 +706,9 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
 #pragma unroll 1
         for (int it = 0; it < nt; ++it) {
             const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + pw * 16;
+            const int64_t left = a.rows - r0;
+            const int nv = left >= 16 ? 16 : (left > 0 ? (int)left : 0);       // valid rows of this warp
+            const int64_t rfirst = nv > 0 ? r0 : a.rows - 1;
             {
                 const int64_t rn = r0 + (int64_t)gridDim.x * 128;      // this warp's rows of the CTA's next tile
                 for (int yi = 0; yi < a.ny; ++yi) {
@@ -622,33 +720,29 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
             float4 x[16];
 #pragma unroll 1
             for (int yi = 0; yi < a.ny; ++yi) {
-                const float* dy = a.dy + yi * 128 + lane * 4;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                    x[r] = *reinterpret_cast<const float4*>(dy + row * a.lddy);
-                }
+                load_rows(x, a.dy + rfirst * a.lddy + yi * 128 + lane * 4, a.lddy, nv);
                 if (a.y_pre) {
-                    const float* pre = a.y_pre + yi * 128 + lane * 4;
+                    const float* p = a.y_pre + rfirst * a.ldyp + yi * 128 + lane * 4;
+                    const int ldp = a.ldyp;
                     if (a.y_act == ACT_SWISH) {
 #pragma unroll 4
                         for (int r = 0; r < 16; ++r) {
-                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldyp);
-                            x[r].x *= swish_grad_tc<FAST>(p.x);
-                            x[r].y *= swish_grad_tc<FAST>(p.y);
-                            x[r].z *= swish_grad_tc<FAST>(p.z);
-                            x[r].w *= swish_grad_tc<FAST>(p.w);
+                            const float4 q = *reinterpret_cast<const float4*>(p);
+                            if (r + 1 < nv) p += ldp;
+                            x[r].x *= swish_grad_tc<FAST>(q.x);
+                            x[r].y *= swish_grad_tc<FAST>(q.y);
+                            x[r].z *= swish_grad_tc<FAST>(q.z);
+                            x[r].w *= swish_grad_tc<FAST>(q.w);
                         }
                     } else if (a.y_act == ACT_RELU) {
 #pragma unroll 4
                         for (int r = 0; r < 16; ++r) {
-                            const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                            const float4 p = *reinterpret_cast<const float4*>(pre + row * a.ldyp);
-                            x[r].x = p.x > 0.f ? x[r].x : 0.f;
-                            x[r].y = p.y > 0.f ? x[r].y : 0.f;
-                            x[r].z = p.z > 0.f ? x[r].z : 0.f;
-                            x[r].w = p.w > 0.f ? x[r].w : 0.f;
+                            const float4 q = *reinterpret_cast<const float4*>(p);
+                            if (r + 1 < nv) p += ldp;
+                            x[r].x = q.x > 0.f ? x[r].x : 0.f;
+                            x[r].y = q.y > 0.f ? x[r].y : 0.f;
+                            x[r].z = q.z > 0.f ? x[r].z : 0.f;
+                            x[r].w = q.w > 0.f ? x[r].w : 0.f;
                         }
                     }
                 }
@@ -656,25 +750,22 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
-                        if (r0 + r < a.rows) { t.x += x[r].x; t.y += x[r].y; t.z += x[r].z; t.w += x[r].w; }
+                        if (r < nv) { t.x += x[r].x; t.y += x[r].y; t.z += x[r].z; t.w += x[r].w; }
                     }
                     float4& b = yi ? bsum[1] : bsum[0];
                     b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w;
                 }
                 // every Y' tile of the row tile is released together (after the last MMA of the previous row tile)
-                store_tile(x, r0, y_img + (size_t)yi * 2 * TILE_BYTES, y_empty, (it & 1) ^ 1);
+                if (pw == 0 && yi == 0) LTTL(3, it, 0);
+                store_tile(x, nv, y_img + (size_t)yi * 2 * TILE_BYTES, y_empty, (it & 1) ^ 1);
             }
             umma::mbar_arrive(y_full);
+            if (pw == 0) LTTL(3, it, 1);
 #pragma unroll 1
             for (int xi = 0; xi < nxt; ++xi, ++sc) {
                 const int s = sc % xstages;
                 if (xi < a.nx) {
-                    const float* src = a.x[xi] + lane * 4;
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                        x[r] = *reinterpret_cast<const float4*>(src + row * a.ldx[xi]);
-                    }
+                    load_rows(x, a.x[xi] + rfirst * a.ldx[xi] + lane * 4, a.ldx[xi], nv);
                     if (a.x_act[xi] == ACT_SWISH) {
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
@@ -689,18 +780,28 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                         }
                     }
                 } else {
-                    // tail tile: columns [0, kt) = the small-K sources, the rest 0
+                    // tail tile: columns [0, kt) = the small-K sources, the rest 0 (lanes >= 4 hold constants only)
+                    const float* q0 = tp[0] ? tp[0] + rfirst * tl[0] : nullptr;
+                    const float* q1 = tp[1] ? tp[1] + rfirst * tl[1] : nullptr;
+                    const float* q2 = tp[2] ? tp[2] + rfirst * tl[2] : nullptr;
+                    const float* q3 = tp[3] ? tp[3] + rfirst * tl[3] : nullptr;
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
-                        const int64_t row = r0 + r < a.rows ? r0 + r : a.rows - 1;
-                        x[r].x = tp[0] ? tp[0][row * tl[0]] : tone[0];
-                        x[r].y = tp[1] ? tp[1][row * tl[1]] : tone[1];
-                        x[r].z = tp[2] ? tp[2][row * tl[2]] : tone[2];
-                        x[r].w = tp[3] ? tp[3][row * tl[3]] : tone[3];
+                        x[r].x = q0 ? *q0 : tone[0];
+                        x[r].y = q1 ? *q1 : tone[1];
+                        x[r].z = q2 ? *q2 : tone[2];
+                        x[r].w = q3 ? *q3 : tone[3];
+                        if (r + 1 < nv) {
+                            if (q0) q0 += tl[0];
+                            if (q1) q1 += tl[1];
+                            if (q2) q2 += tl[2];
+                            if (q3) q3 += tl[3];
+                        }
                     }
                 }
-                store_tile(x, r0, x_stage(s), &x_empty[s], ((sc / xstages) & 1) ^ 1);
+                store_tile(x, nv, x_stage(s), &x_empty[s], ((sc / xstages) & 1) ^ 1);
                 umma::mbar_arrive(&x_full[s]);
+                if (pw == 0) LTTL(3, it, xi == 0 ? 2 : 3);
             }
         }
         if (a.bias_partial) {
