@@ -404,27 +404,34 @@ __global__ void __launch_bounds__(LT_THREADS, 1) linear_tc_kernel(const LinTcArg
                     }
                 }
                 if (kc == 0 && a.pre) {
+                    // pre-activation rows in two halves of eight, the first requested together with the x rows: two exposed
+                    // memory latencies per tile instead of five
                     const float* p = a.pre + rfirst * a.ldpre + lane * 4;
                     const int ldp = a.ldpre;
-                    if (a.pre_act == ACT_SWISH) {
-#pragma unroll 4
-                        for (int r = 0; r < 16; ++r) {
-                            const float4 q = *reinterpret_cast<const float4*>(p);
-                            if (r + 1 < nv) p += ldp;
-                            x[r].x *= swish_grad_tc<FAST>(q.x);
-                            x[r].y *= swish_grad_tc<FAST>(q.y);
-                            x[r].z *= swish_grad_tc<FAST>(q.z);
-                            x[r].w *= swish_grad_tc<FAST>(q.w);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float4 q[8];
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) {
+                            q[r] = *reinterpret_cast<const float4*>(p);
+                            if (h * 8 + r + 1 < nv) p += ldp;
                         }
-                    } else if (a.pre_act == ACT_RELU) {
-#pragma unroll 4
-                        for (int r = 0; r < 16; ++r) {
-                            const float4 q = *reinterpret_cast<const float4*>(p);
-                            if (r + 1 < nv) p += ldp;
-                            x[r].x = q.x > 0.f ? x[r].x : 0.f;
-                            x[r].y = q.y > 0.f ? x[r].y : 0.f;
-                            x[r].z = q.z > 0.f ? x[r].z : 0.f;
-                            x[r].w = q.w > 0.f ? x[r].w : 0.f;
+                        if (a.pre_act == ACT_SWISH) {
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                x[h * 8 + r].x *= swish_grad_tc<FAST>(q[r].x);
+                                x[h * 8 + r].y *= swish_grad_tc<FAST>(q[r].y);
+                                x[h * 8 + r].z *= swish_grad_tc<FAST>(q[r].z);
+                                x[h * 8 + r].w *= swish_grad_tc<FAST>(q[r].w);
+                            }
+                        } else if (a.pre_act == ACT_RELU) {
+#pragma unroll
+                            for (int r = 0; r < 8; ++r) {
+                                x[h * 8 + r].x = q[r].x > 0.f ? x[h * 8 + r].x : 0.f;
+                                x[h * 8 + r].y = q[r].y > 0.f ? x[h * 8 + r].y : 0.f;
+                                x[h * 8 + r].z = q[r].z > 0.f ? x[h * 8 + r].z : 0.f;
+                                x[h * 8 + r].w = q[r].w > 0.f ? x[h * 8 + r].w : 0.f;
+                            }
                         }
                     }
                 }
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
     const uint32_t tmem = *tmem_slot;
 
     if (warp < LT_EPI_WARPS) {
-        umma::reg_dec<LT_REGS_IDLE + 24>();
+        umma::reg_dec<LT_REGS_IDLE + 24>();      // 64: with 40 for the MMA warpgroup this leaves 152 for the producers (640 x 96 in the pool)
         // =========================== drain: thread = output channel n; warps 0-3 columns 0-63, warps 4-7 columns 64-127
         const int n = tid & 127, hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -652,13 +659,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
         const uint32_t lane_blk = (uint32_t)(lane >> 4) * (128u * 128u) + (uint32_t)(lane & 1) * 8u;
         const uint32_t lane_chunk = (uint32_t)(lane & 15) >> 1;
         // 16 rows of one operand tile: converted in place in the registers the rows came in; only the stores follow the wait
-        auto store_tile = [&](float4 (&x)[16], int nv, unsigned char* img, uint64_t* bar, uint32_t parity) {
+        // 16 rows of one operand tile: rows past the end are zeroed, the split happens in the registers the rows came in
+        auto convert = [&](float4 (&x)[16], int nv, uint4 (&hl)[16]) {
             if (nv < 16) {        // the last tile of the problem only
 #pragma unroll
                 for (int r = 0; r < 16; ++r)
                     if (r >= nv) x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            uint4 hl[16];
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const float4 h = x[r];
@@ -670,7 +677,8 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                     split2_bf16(h.z, h.w, hl[r].y, hl[r].w);
                 }
             }
-            umma::mbar_wait(bar, parity);
+        };
+        auto store = [&](const uint4 (&hl)[16], unsigned char* img) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const uint32_t off = lane_blk + (uint32_t)(pw * 16 + r) * 128u + ((lane_chunk ^ (uint32_t)(r & 7)) << 4);
@@ -701,8 +709,35 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                 tp[u] = a.tsrc[seg] + tt; tl[u] = a.tld[seg];
             }
         }
+        // X operand xi of a row tile: a 128-column source, or the tail tile (columns [0, kt) = the small-K sources, the rest 0;
+        // lanes >= 4 hold constants only)
+        auto load_x = [&](float4 (&x)[16], int xi, int64_t rfirst, int nv) {
+            if (xi < a.nx) {
+                load_rows(x, a.x[xi] + rfirst * a.ldx[xi] + lane * 4, a.ldx[xi], nv);
+            } else {
+                const float* q0 = tp[0] ? tp[0] + rfirst * tl[0] : nullptr;
+                const float* q1 = tp[1] ? tp[1] + rfirst * tl[1] : nullptr;
+                const float* q2 = tp[2] ? tp[2] + rfirst * tl[2] : nullptr;
+                const float* q3 = tp[3] ? tp[3] + rfirst * tl[3] : nullptr;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    x[r].x = q0 ? *q0 : tone[0];
+                    x[r].y = q1 ? *q1 : tone[1];
+                    x[r].z = q2 ? *q2 : tone[2];
+                    x[r].w = q3 ? *q3 : tone[3];
+                    if (r + 1 < nv) {
+                        if (q0) q0 += tl[0];
+                        if (q1) q1 += tl[1];
+                        if (q2) q2 += tl[2];
+                        if (q3) q3 += tl[3];
+                    }
+                }
+            }
+        };
         float4 bsum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};     // column sums of Y' (this warp's rows)
         int sc = 0;
+        // (measured and dropped: requesting the rows of the NEXT operand before the stage of the current one is waited for --
+        // the two live row sets spill at 168 registers and the weight-gradient launches got 19 % slower)
 #pragma unroll 1
         for (int it = 0; it < nt; ++it) {
             const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + pw * 16;
@@ -718,31 +753,30 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                 for (int xi = 0; xi < a.nx; ++xi) prefetch_rows16(a.x[xi], a.ldx[xi], rn, a.rows, lane);
             }
             float4 x[16];
+            uint4 hl[16];
 #pragma unroll 1
             for (int yi = 0; yi < a.ny; ++yi) {
                 load_rows(x, a.dy + rfirst * a.lddy + yi * 128 + lane * 4, a.lddy, nv);
                 if (a.y_pre) {
-                    const float* p = a.y_pre + rfirst * a.ldyp + yi * 128 + lane * 4;
-                    const int ldp = a.ldyp;
+                    // the pre-activation rows are requested together with the dy rows: one exposed memory latency per
+                    // Y' tile instead of five (timeline: ~2 k cycles each under load)
+                    float4 q[16];
+                    load_rows(q, a.y_pre + rfirst * a.ldyp + yi * 128 + lane * 4, a.ldyp, nv);
                     if (a.y_act == ACT_SWISH) {
-#pragma unroll 4
+#pragma unroll
                         for (int r = 0; r < 16; ++r) {
-                            const float4 q = *reinterpret_cast<const float4*>(p);
-                            if (r + 1 < nv) p += ldp;
-                            x[r].x *= swish_grad_tc<FAST>(q.x);
-                            x[r].y *= swish_grad_tc<FAST>(q.y);
-                            x[r].z *= swish_grad_tc<FAST>(q.z);
-                            x[r].w *= swish_grad_tc<FAST>(q.w);
+                            x[r].x *= swish_grad_tc<FAST>(q[r].x);
+                            x[r].y *= swish_grad_tc<FAST>(q[r].y);
+                            x[r].z *= swish_grad_tc<FAST>(q[r].z);
+                            x[r].w *= swish_grad_tc<FAST>(q[r].w);
                         }
                     } else if (a.y_act == ACT_RELU) {
-#pragma unroll 4
+#pragma unroll
                         for (int r = 0; r < 16; ++r) {
-                            const float4 q = *reinterpret_cast<const float4*>(p);
-                            if (r + 1 < nv) p += ldp;
-                            x[r].x = q.x > 0.f ? x[r].x : 0.f;
-                            x[r].y = q.y > 0.f ? x[r].y : 0.f;
-                            x[r].z = q.z > 0.f ? x[r].z : 0.f;
-                            x[r].w = q.w > 0.f ? x[r].w : 0.f;
+                            x[r].x = q[r].x > 0.f ? x[r].x : 0.f;
+                            x[r].y = q[r].y > 0.f ? x[r].y : 0.f;
+                            x[r].z = q[r].z > 0.f ? x[r].z : 0.f;
+                            x[r].w = q[r].w > 0.f ? x[r].w : 0.f;
                         }
                     }
                 }
@@ -755,17 +789,19 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                     float4& b = yi ? bsum[1] : bsum[0];
                     b.x += t.x; b.y += t.y; b.z += t.z; b.w += t.w;
                 }
+                convert(x, nv, hl);
                 // every Y' tile of the row tile is released together (after the last MMA of the previous row tile)
                 if (pw == 0 && yi == 0) LTTL(3, it, 0);
-                store_tile(x, nv, y_img + (size_t)yi * 2 * TILE_BYTES, y_empty, (it & 1) ^ 1);
+                umma::mbar_wait(y_empty, (it & 1) ^ 1);
+                store(hl, y_img + (size_t)yi * 2 * TILE_BYTES);
             }
             umma::mbar_arrive(y_full);
             if (pw == 0) LTTL(3, it, 1);
 #pragma unroll 1
             for (int xi = 0; xi < nxt; ++xi, ++sc) {
                 const int s = sc % xstages;
+                load_x(x, xi, rfirst, nv);
                 if (xi < a.nx) {
-                    load_rows(x, a.x[xi] + rfirst * a.ldx[xi] + lane * 4, a.ldx[xi], nv);
                     if (a.x_act[xi] == ACT_SWISH) {
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
@@ -779,27 +815,10 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                             x[r].z = fmaxf(x[r].z, 0.f); x[r].w = fmaxf(x[r].w, 0.f);
                         }
                     }
-                } else {
-                    // tail tile: columns [0, kt) = the small-K sources, the rest 0 (lanes >= 4 hold constants only)
-                    const float* q0 = tp[0] ? tp[0] + rfirst * tl[0] : nullptr;
-                    const float* q1 = tp[1] ? tp[1] + rfirst * tl[1] : nullptr;
-                    const float* q2 = tp[2] ? tp[2] + rfirst * tl[2] : nullptr;
-                    const float* q3 = tp[3] ? tp[3] + rfirst * tl[3] : nullptr;
-#pragma unroll
-                    for (int r = 0; r < 16; ++r) {
-                        x[r].x = q0 ? *q0 : tone[0];
-                        x[r].y = q1 ? *q1 : tone[1];
-                        x[r].z = q2 ? *q2 : tone[2];
-                        x[r].w = q3 ? *q3 : tone[3];
-                        if (r + 1 < nv) {
-                            if (q0) q0 += tl[0];
-                            if (q1) q1 += tl[1];
-                            if (q2) q2 += tl[2];
-                            if (q3) q3 += tl[3];
-                        }
-                    }
                 }
-                store_tile(x, nv, x_stage(s), &x_empty[s], ((sc / xstages) & 1) ^ 1);
+                convert(x, nv, hl);
+                umma::mbar_wait(&x_empty[s], ((sc / xstages) & 1) ^ 1);
+                store(hl, x_stage(s));
                 umma::mbar_arrive(&x_full[s]);
                 if (pw == 0) LTTL(3, it, xi == 0 ? 2 : 3);
             }
