@@ -116,6 +116,19 @@ int mgb_gnn_layer_bwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
                       float* db3, float* dW4, float* db4, int accumulate_params, int precision, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* GNN_Layer.update (models/mpnn_2d.py:81-90; models/mpnn.py:81-90) without the InstanceNorm, as ONE launch (what
+ * mgb_gnn_layer_fwd runs between the edge kernel and the InstanceNorm; exported for tests and for callers with their own
+ * aggregation):
+ *   y1_pre = [x, agg, var] W3^T + b3;   y2_pre = Swish(y1_pre) W4^T + b4;   out = x + Swish(y2_pre)
+ * x, agg [N,128]; var [N,nv], nv <= 4; W3 [128, 256+nv], W4 [128,128] in PyTorch layout.  packed:
+ * mgb_gnn_node_update_packed_floats() floats filled by mgb_gnn_node_update_pack (tensor-memory operand images of W3 / W4 and
+ * the var columns of W3; re-run when the parameters change).  precision 1 (bf16 hi/lo split, fp32 contract) or 2 (bf16). */
+size_t mgb_gnn_node_update_packed_floats(void);
+int mgb_gnn_node_update_pack(const float* W3, const float* W4, int nv, float* packed, void* stream);
+int mgb_gnn_node_update_fwd(const float* x, const float* agg, const float* var, int nv, int64_t n_nodes, const float* packed,
+                            const float* b3, const float* b4, float* y1_pre, float* y2_pre, float* out, int precision,
+                            void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row-wise dense stages (nn.Linear + activation, nn.LayerNorm) used by embedding_mlp
  * (models/mpnn_2d.py:130-135), MLP (models/backbones/mlp.py:9-28), Encoder/Decoder/projector

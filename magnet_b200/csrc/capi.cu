@@ -77,6 +77,31 @@ int mgb_gnn_layer_fwd(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, 
     return gnn_layer_fwd(sh, io, workspace, workspace_bytes, STREAM(stream));
 }
 
+// packed block of the stand-alone node update: three tensor-memory weight images (H*H floats each) + the var columns of W3 [128][4]
+size_t mgb_gnn_node_update_packed_floats(void) { return (size_t)3 * 128 * 128 + 128 * 4; }
+int mgb_gnn_node_update_pack(const float* W3, const float* W4, int nv, float* packed, void* stream) {
+    MGB_REQUIRE(nv >= 0 && nv <= 4, "node_update: at most 4 var columns");
+    cudaStream_t s = STREAM(stream);
+    MGB_TRY(pack_weight_tmem_bf16(W3, 256 + nv, 0, packed, s));
+    MGB_TRY(pack_weight_tmem_bf16(W3, 256 + nv, 128, packed + 128 * 128, s));
+    MGB_TRY(pack_weight_tmem_bf16(W4, 128, 0, packed + 2 * 128 * 128, s));
+    MGB_CUDA(cudaMemsetAsync(packed + 3 * 128 * 128, 0, 128 * 4 * sizeof(float), s));
+    if (nv > 0)
+        MGB_CUDA(cudaMemcpy2DAsync(packed + 3 * 128 * 128, 4 * sizeof(float), W3 + 256, (size_t)(256 + nv) * sizeof(float), (size_t)nv * sizeof(float),
+                                   128, cudaMemcpyDeviceToDevice, s));
+    return MGB_OK;
+}
+int mgb_gnn_node_update_fwd(const float* x, const float* agg, const float* var, int nv, int64_t n_nodes, const float* packed,
+                            const float* b3, const float* b4, float* y1_pre, float* y2_pre, float* out, int precision,
+                            void* stream) {
+    MGB_REQUIRE(precision == 1 || precision == 2, "node_update: precision must be 1 (bf16 hi/lo split) or 2 (bf16)");
+    NodeUpdateArgs a{};
+    a.x = x; a.agg = agg; a.rows = n_nodes; a.var = var; a.nv = nv;
+    a.wimg = packed; a.w3tail = packed + 3 * 128 * 128; a.wt_sn = 4; a.wt_st = 1;
+    a.b3 = b3; a.b4 = b4; a.y1_pre = y1_pre; a.y2_pre = y2_pre; a.out = out;
+    return launch_node_update_tc(precision, a, STREAM(stream));
+}
+
 size_t mgb_gnn_layer_bwd_workspace(int64_t n_nodes, int64_t n_edges, int tw, int dp, int nv, int n_graphs,
                                    int max_nodes_per_graph) {
     return gnn_layer_bwd_workspace(n_nodes, n_edges, tw, dp, nv, n_graphs, max_nodes_per_graph);
@@ -506,6 +531,7 @@ int mgb_debug_set_timeline(long long* p) { return mgb::set_timeline_buffer(p); }
 int mgb_debug_set_ie_timeline(long long* p) { return mgb::set_ie_timeline_buffer(p); }
 int mgb_debug_set_ib_timeline(long long* p) { return mgb::set_ib_timeline_buffer(p); }
 int mgb_debug_set_lt_timeline(long long* p) { return mgb::set_lt_timeline_buffer(p); }
+int mgb_debug_set_nu_timeline(long long* p) { return mgb::set_nu_timeline_buffer(p); }
 #endif
 
 int mgb_umma_selftest(const float* a, const float* b, int a_mn_major, int b_mn_major, int lbo_mn, int sbo_mn, float* d,

@@ -497,6 +497,7 @@ struct GnnPacked {
     float* img_pq;  // weight tiles (hi|lo images, H*H floats each) of the node-level Linears for linear_tc.cu:
     float* img_w3;  //   Wcat rows P / Q x columns [0,128);  W3 columns [0,128) / [128,256);  W4
     float* img_w4;
+    float* wtm;     // W3[:, 0:128], W3[:, 128:256], W4 in tensor-memory order (bf16 hi | lo, 16384 words each) for node_update_tc.cu
 };
 static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) {
     size_t off = 0;
@@ -511,6 +512,8 @@ static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) 
     float* i1 = take((size_t)2 * H * H);
     float* i2 = take((size_t)2 * H * H);
     float* i3 = take((size_t)H * H);
+    float* i4 = take((size_t)3 * H * H);
+    if (p) { p->wtm = i4; }
     if (p) { p->wcat_t = a; p->wcat = b; p->bcat = c; p->w2t = d; p->w3t = e; p->w4t = f; p->w2img = g;
              p->img_pq = i1; p->img_w3 = i2; p->img_w4 = i3; }
     return off;
@@ -537,7 +540,16 @@ int gnn_layer_pack(const float* W1, const float* b1, const float* W2, const floa
     MGB_TRY(pack_weight_tile(W3, sh.K3(), H, sh.K3(), 0, 0, p.img_w3, s));
     MGB_TRY(pack_weight_tile(W3, sh.K3(), H, sh.K3(), 0, H, p.img_w3 + H * H, s));
     MGB_TRY(pack_weight_tile(W4, H, H, H, 0, 0, p.img_w4, s));
+    MGB_TRY(pack_weight_tmem_bf16(W3, sh.K3(), 0, p.wtm, s));
+    MGB_TRY(pack_weight_tmem_bf16(W3, sh.K3(), H, p.wtm + H * H, s));
+    MGB_TRY(pack_weight_tmem_bf16(W4, H, 0, p.wtm + 2 * H * H, s));
     return MGB_OK;
+}
+
+// developer switch (MGB_NODE_UPDATE=0: update_net_1 / update_net_2 as two launches of linear_tc.cu, the round-1 path)
+static bool fused_node_update() {
+    static const bool on = [] { const char* e = getenv("MGB_NODE_UPDATE"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 static int edge_grid(int64_t n_tiles, int ctas_per_sm) {
@@ -616,7 +628,14 @@ int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, siz
         }
     }
     // 3. update net
-    if (tc_nodes) {
+    if (tc_nodes && sh.nv <= 4 && fused_node_update()) {
+        // both Linears, the Swish between them and the residual in one launch (node_update_tc.cu)
+        NodeUpdateArgs a{};
+        a.x = io.x; a.agg = io.agg; a.rows = N; a.var = io.var; a.nv = sh.nv;
+        a.wimg = p.wtm; a.w3tail = p.w3t + (size_t)2 * H * H; a.wt_sn = 1; a.wt_st = H;
+        a.b3 = io.b3; a.b4 = io.b4; a.y1_pre = io.y1_pre; a.y2_pre = io.y2_pre; a.out = out;
+        MGB_TRY(launch_node_update_tc(sh.precision, a, s));
+    } else if (tc_nodes) {
         LinTcArgs a{};
         a.src[0] = io.x; a.ld[0] = H; a.src[1] = io.agg; a.ld[1] = H; a.nk = 2;
         a.tsrc[0] = io.var; a.tld[0] = sh.nv; a.tk[0] = sh.nv; a.kt = sh.nv;

@@ -133,6 +133,17 @@ struct WgradTcArgs {
 struct WgradTcOut {          // destination of accumulator (y, x): dw[n*lddw + k], n < n_valid, k < k_valid
     float* dw; int lddw; int n_valid, k_valid; int accumulate;
 };
+// node_update_tc.cu (update_net_1 + update_net_2 + residual of GNN_Layer in one launch, forward)
+struct NodeUpdateArgs {
+    const float* x; const float* agg; int64_t rows;        // [N,128] each
+    const float* var; int nv;                               // [N,nv], nv <= 4
+    const void* wimg;                                       // W3[:, 0:128], W3[:, 128:256], W4 in tensor-memory order (pack_weight_tmem_bf16), 64 KB each
+    const float* w3tail; int wt_sn, wt_st;                  // W3[n, 256 + t] at w3tail[n*wt_sn + t*wt_st]
+    const float* b3; const float* b4;
+    float* y1_pre; float* y2_pre; float* out;               // [N,128]
+};
+int pack_weight_tmem_bf16(const float* W, int ld, int c0, void* out, cudaStream_t s);
+int launch_node_update_tc(int precision, const NodeUpdateArgs& a, cudaStream_t s);
 int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s, int f16 = 0);
 int pack_weight_tmem(const float* W, int ld, int n_rows, int n_cols, void* out, cudaStream_t s);
 int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s);
@@ -146,6 +157,7 @@ int set_timeline_buffer(long long* p);
 int set_ie_timeline_buffer(long long* p);
 int set_ib_timeline_buffer(long long* p);
 int set_lt_timeline_buffer(long long* p);
+int set_nu_timeline_buffer(long long* p);
 #endif
 // mlp_chain_tc.cu (a whole 128-wide MLP in one launch, forward only)
 struct CellPoint;

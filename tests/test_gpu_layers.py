@@ -454,3 +454,38 @@ def test_bundling_decoder_and_small_linear_on_empty_input():
     assert y.shape == (0, 128)
     y.sum().backward()
     assert float(W.grad.abs().sum()) == 0.0 and float(b.grad.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("rows,nv,precision,tol", [(1, 1, 1, TOL), (127, 1, 1, TOL), (128, 1, 1, TOL), (129, 1, 1, TOL), (777, 3, 1, TOL),
+                                                   (148 * 128 + 65, 1, 1, TOL), (40000, 0, 1, TOL), (5000, 1, 2, 1e-2)])
+def test_fused_node_update_vs_fp64(rows, nv, precision, tol):
+    """GNN_Layer.update (models/mpnn_2d.py:81-90) without the InstanceNorm as one launch (mgb_gnn_node_update_fwd): both
+    Linears, the Swish between them and the residual, against an fp64 evaluation; row counts around the 128-row tile, more
+    tiles than CTAs, no / several equation variables.  Rerun: bit-identical."""
+    from magnet_b200 import _lib
+    L = _lib.lib()
+    g = S._gen(rows + nv)
+    x = torch.randn(rows, 128, generator=g)
+    agg = torch.randn(rows, 128, generator=g) * 0.5
+    var = torch.rand(rows, max(nv, 1), generator=g)[:, :nv].contiguous()
+    W3 = torch.randn(128, 256 + nv, generator=g) / 16
+    W4 = torch.randn(128, 128, generator=g) / 11
+    b3, b4 = torch.randn(128, generator=g) * 0.1, torch.randn(128, generator=g) * 0.1
+    d = {k: v.to(DEV) for k, v in dict(x=x, agg=agg, var=var, W3=W3, W4=W4, b3=b3, b4=b4).items()}
+    packed = torch.empty(L.mgb_gnn_node_update_packed_floats(), device=DEV)
+    _lib.check(L.mgb_gnn_node_update_pack(_lib.ptr(d["W3"]), _lib.ptr(d["W4"]), nv, _lib.ptr(packed), _lib.stream()), "pack")
+    outs = []
+    for _ in range(2):
+        y1, y2, out = (torch.full((rows, 128), float("nan"), device=DEV) for _ in range(3))
+        _lib.check(L.mgb_gnn_node_update_fwd(_lib.ptr(d["x"]), _lib.ptr(d["agg"]), _lib.ptr(d["var"]) if nv else None, nv, rows,
+                                             _lib.ptr(packed), _lib.ptr(d["b3"]), _lib.ptr(d["b4"]), _lib.ptr(y1), _lib.ptr(y2),
+                                             _lib.ptr(out), precision, _lib.stream()), "node_update_fwd")
+        outs.append((y1, y2, out))
+    sw = lambda v: v * torch.sigmoid(v)
+    z1 = torch.cat([x, agg, var], 1).double() @ W3.double().T + b3.double()
+    z2 = sw(z1) @ W4.double().T + b4.double()
+    want = x.double() + sw(z2)
+    for got, ref in zip(outs[0], (z1, z2, want)):
+        assert rel_err(got, ref) < tol
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
