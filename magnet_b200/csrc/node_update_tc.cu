@@ -141,7 +141,17 @@ __global__ void __launch_bounds__(NU_THREADS, 1) node_update_tc_kernel(const Nod
             // ---------------- first Linear: y1_pre, Swish -> operand image of the second ----------------
             {
                 float* yp = a.y1_pre + rb * 128 + n;
-                const float* vp = a.var + rb * nv;
+                // var of this half's 64 rows: lane l holds rows l and l + 32 (coalesced, requested before the accumulator is
+                // waited for); row i's value reaches every lane by shuffle
+                float vr[2][NU_MAXV];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+                    for (int t = 0; t < NU_MAXV; ++t) {
+                        const int row = h2 * 32 + lane;
+                        vr[h2][t] = (t < nv && row < rlim) ? a.var[(rb + row) * nv + t] : 0.f;
+                    }
+                }
                 umma::mbar_wait(d_full, 0);
                 umma::tc_fence_after();
                 if (warp == 0) NUTL(2, it, 0);
@@ -154,11 +164,11 @@ __global__ void __launch_bounds__(NU_THREADS, 1) node_update_tc_kernel(const Nod
                     for (int i = 0; i < 16; ++i) v[i] += b3;
                     if (nv > 0) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            if (c + i < rlim) {
+                        for (int t = 0; t < NU_MAXV; ++t) {
+                            if (t < nv) {
+                                const float src = c < 32 ? vr[0][t] : vr[1][t];
 #pragma unroll
-                                for (int t = 0; t < NU_MAXV; ++t)
-                                    if (t < nv) v[i] = fmaf(vp[(c + i) * nv + t], wv[t], v[i]);
+                                for (int i = 0; i < 16; ++i) v[i] = fmaf(__shfl_sync(0xffffffffu, src, (c & 31) + i), wv[t], v[i]);
                             }
                         }
                     }
@@ -206,29 +216,37 @@ __global__ void __launch_bounds__(NU_THREADS, 1) node_update_tc_kernel(const Nod
                 umma::mbar_wait(d_full, 1);
                 umma::tc_fence_after();
                 if (warp == 0) NUTL(2, it, 2);
-#pragma unroll 1
+                // the whole accumulator part of this thread goes to registers first and the accumulator back to the MMA warp:
+                // the first Linear of the next tile runs under this tile's stores (HBM-bound: 128 KB out, 64 KB in per tile)
+                float v[64];
+                {
+                    float t0[16], t1[16], t2[16], t3[16];
+                    umma::tmem_ld16(tacc, t0);
+                    umma::tmem_ld16(tacc + 16u, t1);
+                    umma::tmem_ld16(tacc + 32u, t2);
+                    umma::tmem_ld16(tacc + 48u, t3);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { v[i] = t0[i]; v[16 + i] = t1[i]; v[32 + i] = t2[i]; v[48 + i] = t3[i]; }
+                }
+                umma::tc_fence_before();
+                umma::mbar_arrive(acc_free);
+#pragma unroll
                 for (int c = 0; c < 64; c += 16) {
-                    float v[16];
-                    umma::tmem_ld16(tacc + (uint32_t)c, v);
-                    if (c + 16 >= 64) {              // this thread's part of the accumulator is in registers
-                        umma::tc_fence_before();
-                        umma::mbar_arrive(acc_free);
-                    }
                     const int lim = rlim - c;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += b4;
+                    for (int i = 0; i < 16; ++i) v[c + i] += b4;
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (i < lim) yp[(c + i) * 128] = v[i];
+                        if (i < lim) yp[(c + i) * 128] = v[c + i];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = swish_tc<FAST>(v[i]) + res[i];
+                    for (int i = 0; i < 16; ++i) v[c + i] = swish_tc<FAST>(v[c + i]) + res[i];
                     if (c + 16 < 64) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) res[i] = c + 16 + i < rlim ? xp[(c + 16 + i) * 128] : 0.f;
                     }
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
-                        if (i < lim) yo[(c + i) * 128] = v[i];
+                        if (i < lim) yo[(c + i) * 128] = v[c + i];
                 }
                 if (warp == 0) NUTL(2, it, 3);
             }
