@@ -498,6 +498,9 @@ struct GnnPacked {
     float* img_w3;  //   Wcat rows P / Q x columns [0,128);  W3 columns [0,128) / [128,256);  W4
     float* img_w4;
     float* wtm;     // W3[:, 0:128], W3[:, 128:256], W4 in tensor-memory order (bf16 hi | lo, 16384 words each) for node_update_tc.cu
+    float* wtm_pq;  // linear_ts.cu, same order: Wcat rows P / Q x columns [0,128)   (P | Q = [x,..] Wcat^T)
+    float* wtm_dc;  //   W3^T output blocks [0,128) / [128,256)                        (dc = d1' W3)
+    float* wtm_dx;  //   Wcat^T K-tiles P / Q                                          (dx = dP Wcat[:128] + dQ Wcat[128:])
 };
 static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) {
     size_t off = 0;
@@ -513,7 +516,10 @@ static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) 
     float* i2 = take((size_t)2 * H * H);
     float* i3 = take((size_t)H * H);
     float* i4 = take((size_t)3 * H * H);
-    if (p) { p->wtm = i4; }
+    float* i5 = take((size_t)2 * H * H);
+    float* i6 = take((size_t)2 * H * H);
+    float* i7 = take((size_t)2 * H * H);
+    if (p) { p->wtm = i4; p->wtm_pq = i5; p->wtm_dc = i6; p->wtm_dx = i7; }
     if (p) { p->wcat_t = a; p->wcat = b; p->bcat = c; p->w2t = d; p->w3t = e; p->w4t = f; p->w2img = g;
              p->img_pq = i1; p->img_w3 = i2; p->img_w4 = i3; }
     return off;
@@ -543,9 +549,20 @@ int gnn_layer_pack(const float* W1, const float* b1, const float* W2, const floa
     MGB_TRY(pack_weight_tmem_bf16(W3, sh.K3(), 0, p.wtm, s));
     MGB_TRY(pack_weight_tmem_bf16(W3, sh.K3(), H, p.wtm + H * H, s));
     MGB_TRY(pack_weight_tmem_bf16(W4, H, 0, p.wtm + 2 * H * H, s));
+    MGB_TRY(pack_weight_tmem_bf16(p.wcat, sh.Kc(), 0, p.wtm_pq, s));                              // A[n][k] = Wcat[n][k], P rows
+    MGB_TRY(pack_weight_tmem_bf16(p.wcat + (size_t)H * sh.Kc(), sh.Kc(), 0, p.wtm_pq + H * H, s));   // Q rows
+    MGB_TRY(pack_weight_tmem_bf16(p.w3t, H, 0, p.wtm_dc, s));                                     // A[j][n] = W3[n][j], j < 128
+    MGB_TRY(pack_weight_tmem_bf16(p.w3t + (size_t)H * H, H, 0, p.wtm_dc + H * H, s));                //   j in [128, 256)
+    MGB_TRY(pack_weight_tmem_bf16(p.wcat_t, 2 * H, 0, p.wtm_dx, s));                              // A[k][n] = Wcat[n][k], n < 128
+    MGB_TRY(pack_weight_tmem_bf16(p.wcat_t, 2 * H, H, p.wtm_dx + H * H, s));                       //   n in [128, 256)
     return MGB_OK;
 }
 
+// developer switch (MGB_TS_LINEARS=0: the P | Q Linear and the two-tile data gradients through linear_tc.cu, the round-1 path)
+static bool ts_linears() {
+    static const bool on = [] { const char* e = getenv("MGB_TS_LINEARS"); return !(e && e[0] == '0'); }();
+    return on;
+}
 // developer switch (MGB_NODE_UPDATE=0: update_net_1 / update_net_2 as two launches of linear_tc.cu, the round-1 path)
 static bool fused_node_update() {
     static const bool on = [] { const char* e = getenv("MGB_NODE_UPDATE"); return !(e && e[0] == '0'); }();
@@ -591,7 +608,8 @@ int gnn_layer_fwd(const GnnLayerShape& sh, const GnnFwdIO& io, void* ws_ptr, siz
         a.kt = kt_pq; a.wtail = p.wcat + H; a.wt_sn = sh.Kc(); a.wt_st = 1;
         a.wimg = p.img_pq; a.nm = 2; a.tile_of[0][0] = 0; a.tile_of[1][0] = 1;
         a.bias = p.bcat; a.act = ACT_NONE; a.y = io.pq; a.ldy = 2 * H; a.rows = N;
-        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+        if (ts_linears()) { a.wimg = p.wtm_pq; MGB_TRY(launch_linear_ts(sh.precision, a, s)); }
+        else MGB_TRY(launch_linear_tc(sh.precision, a, s));
     } else {
         GemmArgs g{};
         g.a.p[0] = io.x; g.a.ld[0] = H; g.a.k[0] = H;
@@ -798,7 +816,8 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         a.wimg = p.img_w3; a.nm = 2; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[1][0] = 1;
         a.act = ACT_NONE; a.y = dc; a.ldy = ldc; a.rows = N;
         if (fuse_dx) { a.residual = d0; a.ldr = H; a.res_blocks = 1; }      // dc[:, :H] += d0 (the residual branch of the update)
-        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+        if (ts_linears()) { a.wimg = p.wtm_dc; a.a_trans = 0; MGB_TRY(launch_linear_ts(sh.precision, a, s)); }
+        else MGB_TRY(launch_linear_tc(sh.precision, a, s));
         if (io.dvar)      // the tail columns of dc feed dvar only
             MGB_TRY(launch_tail_dgrad(d1, H, H, io.y1_pre, H, ACT_SWISH, io.W3 + 2 * H, sh.K3(), 1, sh.nv, N, dc + 2 * H, ldc, s));
     } else {
@@ -879,7 +898,8 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         a.wimg = p.img_pq; a.nm = 1; a.a_trans = 1; a.tile_of[0][0] = 0; a.tile_of[0][1] = 1;
         a.act = ACT_NONE; a.y = dxc; a.ldy = ldx; a.rows = N;
         if (fuse_dx) { a.y = io.dx; a.ldy = H; a.residual = dc; a.ldr = ldc; }   // dx = dPQ Wcat[:, :H] + (d0 + dc[:, :H]): no assembly pass
-        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+        if (ts_linears()) { a.wimg = p.wtm_dx; a.a_trans = 0; MGB_TRY(launch_linear_ts(sh.precision, a, s)); }
+        else MGB_TRY(launch_linear_tc(sh.precision, a, s));
         if (io.du || io.dpos || io.dvar)      // the tail columns of dxc feed du / dpos / dvar only
             MGB_TRY(launch_tail_dgrad(dpq, 2 * H, 2 * H, nullptr, 0, ACT_NONE, p.wcat + H, sh.Kc(), 1, kt_pq, N, dxc + H, ldx, s));
     } else {

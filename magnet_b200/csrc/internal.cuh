@@ -147,6 +147,10 @@ int launch_node_update_tc(int precision, const NodeUpdateArgs& a, cudaStream_t s
 int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s, int f16 = 0);
 int pack_weight_tmem(const float* W, int ld, int n_rows, int n_cols, void* out, cudaStream_t s);
 int launch_linear_tc(int precision, const LinTcArgs& a, cudaStream_t s);
+// linear_ts.cu: the same contract with the weights in tensor memory (a.wimg = tiles in pack_weight_tmem_bf16 order), for the
+// shapes linear_ts_covers accepts (no activation, no pre-activation copy, all output columns valid, weights not transposed)
+bool linear_ts_covers(const LinTcArgs& a);
+int launch_linear_ts(int precision, const LinTcArgs& a, cudaStream_t s);
 size_t wgrad_tc_workspace(int64_t rows);
 int launch_wgrad_tc(int precision, WgradTcArgs a, const WgradTcOut* outs /*[ny][nx + tail]*/, void* ws, size_t ws_bytes,
                     cudaStream_t s);

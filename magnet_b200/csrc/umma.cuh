@@ -197,6 +197,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// the same for 16 consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------
 // instruction descriptor, kind::f16: bf16 x bf16 -> fp32, dense; *_mn = 1 for an MN-major operand
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) {

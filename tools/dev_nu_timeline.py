@@ -46,3 +46,17 @@ f = lambda v: f"{int(v) - t0:7d}" if v > 0 else "      -"
 for it in range(7):
     print(f"tile {it}: prod x_conv {f(t[0, it, 0])} x_full {f(t[0, it, 1])} a_conv {f(t[0, it, 2])} a_full {f(t[0, it, 3])} | mma x_ready {f(t[1, it, 0])} A_issued {f(t[1, it, 1])}"
           f" h_ready {f(t[1, it, 2])} B_issued {f(t[1, it, 3])} | epi A_done {f(t[2, it, 0])} h_written {f(t[2, it, 1])} B_done {f(t[2, it, 2])} stored {f(t[2, it, 3])}")
+
+# ---- the P|Q Linear of the same forward (the only linear_tc_kernel launch of a forward layer) ----
+with torch.no_grad():
+    tl = torch.zeros(5 * 8 * 4, dtype=torch.int64, device=dev)
+    L.mgb_debug_set_nu_timeline(ctypes.c_void_p(0))
+    L.mgb_debug_set_lt_timeline.argtypes = [ctypes.c_void_p]
+    L.mgb_debug_set_lt_timeline(ctypes.c_void_p(tl.data_ptr()))
+    layer(x, u, p2, var, ei, batch, plan=plan, segments=seg)
+    torch.cuda.synchronize()
+t = tl.cpu().reshape(5, 8, 4)[:3]
+t0 = int(t[t > 0].min())
+for it in range(7):
+    print(f"PQ tile {it}: prod converted {f(t[0, it, 0])} stage_free {f(t[0, it, 1])} full {f(t[0, it, 2])} | mma ready {f(t[1, it, 0])} issued {f(t[1, it, 1])}"
+          f" | epi wait {f(t[2, it, 0])} acc_ready {f(t[2, it, 1])} first_ld {f(t[2, it, 2])} done {f(t[2, it, 3])}")
