@@ -501,6 +501,7 @@ struct GnnPacked {
     float* wtm_pq;  // linear_ts.cu, same order: Wcat rows P / Q x columns [0,128)   (P | Q = [x,..] Wcat^T)
     float* wtm_dc;  //   W3^T output blocks [0,128) / [128,256)                        (dc = d1' W3)
     float* wtm_dx;  //   Wcat^T K-tiles P / Q                                          (dx = dP Wcat[:128] + dQ Wcat[128:])
+    float* wtm_d1;  //   W4^T                                                          (d1 = d0' W4)
 };
 static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) {
     size_t off = 0;
@@ -519,7 +520,8 @@ static size_t packed_layout(const GnnLayerShape& sh, float* base, GnnPacked* p) 
     float* i5 = take((size_t)2 * H * H);
     float* i6 = take((size_t)2 * H * H);
     float* i7 = take((size_t)2 * H * H);
-    if (p) { p->wtm = i4; p->wtm_pq = i5; p->wtm_dc = i6; p->wtm_dx = i7; }
+    float* i8 = take((size_t)H * H);
+    if (p) { p->wtm = i4; p->wtm_pq = i5; p->wtm_dc = i6; p->wtm_dx = i7; p->wtm_d1 = i8; }
     if (p) { p->wcat_t = a; p->wcat = b; p->bcat = c; p->w2t = d; p->w3t = e; p->w4t = f; p->w2img = g;
              p->img_pq = i1; p->img_w3 = i2; p->img_w4 = i3; }
     return off;
@@ -555,6 +557,7 @@ int gnn_layer_pack(const float* W1, const float* b1, const float* W2, const floa
     MGB_TRY(pack_weight_tmem_bf16(p.w3t + (size_t)H * H, H, 0, p.wtm_dc + H * H, s));                //   j in [128, 256)
     MGB_TRY(pack_weight_tmem_bf16(p.wcat_t, 2 * H, 0, p.wtm_dx, s));                              // A[k][n] = Wcat[n][k], n < 128
     MGB_TRY(pack_weight_tmem_bf16(p.wcat_t, 2 * H, H, p.wtm_dx + H * H, s));                       //   n in [128, 256)
+    MGB_TRY(pack_weight_tmem_bf16(p.w4t, H, 0, p.wtm_d1, s));                                      // A[k][n] = W4[n][k]
     return MGB_OK;
 }
 
@@ -788,7 +791,8 @@ int gnn_layer_bwd(const GnnLayerShape& sh, const GnnBwdIO& io, void* ws_ptr, siz
         a.src[0] = d0; a.ld[0] = H; a.nk = 1; a.pre = io.y2_pre; a.ldpre = H; a.pre_act = ACT_SWISH;
         a.wimg = p.img_w4; a.nm = 1; a.a_trans = 1; a.tile_of[0][0] = 0;
         a.act = ACT_NONE; a.y = d1; a.ldy = H; a.rows = N;
-        MGB_TRY(launch_linear_tc(sh.precision, a, s));
+        if (ts_linears()) { a.wimg = p.wtm_d1; a.a_trans = 0; MGB_TRY(launch_linear_ts(sh.precision, a, s)); }
+        else MGB_TRY(launch_linear_tc(sh.precision, a, s));
     } else {
         WgradArgs w{};
         w.dy = d0; w.lddy = H; w.y_pre = io.y2_pre; w.y_act = ACT_SWISH;
