@@ -142,7 +142,8 @@ int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_featur
  * (mgb_linear_tc_packed_floats returns 0 for anything else).  precision: 1 bf16 hi/lo split (16 significant bits),
  * 2 plain bf16 (1e-2 contract), 3 fp16 hi/lo split (22 significant bits; inputs and weights must be O(1), |x| < 65504).
  * packed = swizzled 16-bit images of W [out, in] (row stride ldw) in the format of `precision`, built once per weight
- * version by mgb_linear_tc_pack. */
+ * version by mgb_linear_tc_pack; for the shapes mgb_linear_tc_bwd covers and precision 1 / 2 the block also holds the blocks of
+ * W^T in tensor-memory operand order (the data gradient runs with its weights resident in tensor memory). */
 size_t mgb_linear_tc_packed_floats(int in_features, int out_features);
 int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, int precision, float* packed,
                        void* stream);

@@ -150,10 +150,14 @@ static bool linear_tc_shape(int in_features, int out_features, int* nk, int* nm)
     return *nk * *nm <= 2;
 }
 
+static bool linear_ts_bwd_shape(int in_features, int out_features) { return out_features == 128 && (in_features == 128 || in_features == 256); }
+
 size_t mgb_linear_tc_packed_floats(int in_features, int out_features) {
     int nk, nm;
     if (!linear_tc_shape(in_features, out_features, &nk, &nm)) return 0;
-    return (size_t)nk * nm * 2 * 128 * 128 / 2;       // per tile: two bf16 images (hi | lo) of 128 x 128
+    // per tile: two 16-bit images (hi | lo) of 128 x 128; then, for the shapes mgb_linear_tc_bwd covers, the blocks of W^T in
+    // tensor-memory order (bf16 hi | lo, linear_ts.cu) for the data gradient
+    return (size_t)nk * nm * 2 * 128 * 128 / 2 + (linear_ts_bwd_shape(in_features, out_features) ? (size_t)nk * 128 * 128 : 0);
 }
 
 int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, int precision, float* packed, void* stream) {
@@ -162,6 +166,9 @@ int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_feature
     for (int m = 0; m < nm; ++m)
         for (int kc = 0; kc < nk; ++kc)
             MGB_TRY(pack_weight_tile(W, ldw, out_features, in_features, m * 128, kc * 128, packed + (size_t)(m * nk + kc) * 128 * 128, STREAM(stream), precision == 3));
+    if (linear_ts_bwd_shape(in_features, out_features) && precision != 3)
+        for (int kc = 0; kc < nk; ++kc)      // A_kc[k][n] = W[n][kc*128 + k]
+            MGB_TRY(pack_weight_tmem_bf16(W, ldw, kc * 128, packed + (size_t)(nk * nm + kc) * 128 * 128, STREAM(stream), 1));
     return MGB_OK;
 }
 
@@ -420,10 +427,12 @@ int mgb_linear_tc_bwd(const float* dy, const float* y_pre, int act, const float*
     if (dx) {
         LinTcArgs a{};
         a.src[0] = dy; a.ld[0] = 128; a.nk = 1; a.pre = act ? y_pre : nullptr; a.ldpre = 128; a.pre_act = act;
-        a.wimg = packed; a.nm = nk; a.a_trans = 1;
+        a.nm = nk;
         for (int m = 0; m < nk; ++m) a.tile_of[m][0] = m;
-        a.act = ACT_NONE; a.y = dx; a.ldy = in_features; a.rows = rows; a.n_out = in_features;
-        MGB_TRY(launch_linear_tc(precision, a, STREAM(stream)));
+        a.act = ACT_NONE; a.y = dx; a.ldy = in_features; a.rows = rows;
+        // weights in tensor memory (linear_ts.cu): the W^T blocks sit behind the nk swizzled images of the packed block
+        a.wimg = packed + (size_t)nk * 128 * 128;
+        MGB_TRY(launch_linear_ts(precision, a, STREAM(stream)));
     }
     return MGB_OK;
 }

@@ -142,7 +142,7 @@ struct NodeUpdateArgs {
     const float* b3; const float* b4;
     float* y1_pre; float* y2_pre; float* out;               // [N,128]
 };
-int pack_weight_tmem_bf16(const float* W, int ld, int c0, void* out, cudaStream_t s);
+int pack_weight_tmem_bf16(const float* W, int ld, int c0, void* out, cudaStream_t s, int trans = 0);
 int launch_node_update_tc(int precision, const NodeUpdateArgs& a, cudaStream_t s);
 int pack_weight_tile(const float* W, int ld, int n_rows, int n_cols, int r0, int c0, void* img, cudaStream_t s, int f16 = 0);
 int pack_weight_tmem(const float* W, int ld, int n_rows, int n_cols, void* out, cudaStream_t s);

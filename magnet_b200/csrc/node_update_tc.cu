@@ -41,11 +41,13 @@ template <int NSPLIT> constexpr size_t node_update_smem() { return 1024 + (size_
 // W [128][ld] (columns c0 .. c0+127) -> bf16 hi | lo pairs in the order the loader warps read it: 32-bit word j of row m =
 // elements (2j, 2j+1); chunk (j / 32) x w4 ((j % 32) / 4) x m x 4 words (coalesced 16-byte loads per thread m); 8192 words
 // hi, then 8192 words lo (same layout as pack_weight_tmem_kernel, linear_tc.cu, with bf16 instead of fp16 halves)
-__global__ void pack_weight_tmem_bf16_kernel(const float* __restrict__ W, int ld, int c0, uint32_t* __restrict__ out) {
+__global__ void pack_weight_tmem_bf16_kernel(const float* __restrict__ W, int ld, int c0, int trans, uint32_t* __restrict__ out) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= 128 * 64) return;
     const int m = idx >> 6, j = idx & 63;
-    const float v0 = W[(int64_t)m * ld + c0 + 2 * j], v1 = W[(int64_t)m * ld + c0 + 2 * j + 1];
+    // trans = 0: A[m][k] = W[m][c0 + k];  trans = 1: A[m][k] = W[k][c0 + m] (the block of W^T: data gradients)
+    const float v0 = trans ? W[(int64_t)(2 * j) * ld + c0 + m] : W[(int64_t)m * ld + c0 + 2 * j];
+    const float v1 = trans ? W[(int64_t)(2 * j + 1) * ld + c0 + m] : W[(int64_t)m * ld + c0 + 2 * j + 1];
     uint32_t hi, lo;
     split2_bf16(v0, v1, hi, lo);
     const int word = (((j >> 5) * 8 + ((j & 31) >> 2)) * 128 + m) * 4 + (j & 3);
@@ -53,8 +55,8 @@ __global__ void pack_weight_tmem_bf16_kernel(const float* __restrict__ W, int ld
     out[8192 + word] = lo;
 }
 
-int pack_weight_tmem_bf16(const float* W, int ld, int c0, void* out, cudaStream_t s) {
-    pack_weight_tmem_bf16_kernel<<<32, 256, 0, s>>>(W, ld, c0, (uint32_t*)out);
+int pack_weight_tmem_bf16(const float* W, int ld, int c0, void* out, cudaStream_t s, int trans) {
+    pack_weight_tmem_bf16_kernel<<<32, 256, 0, s>>>(W, ld, c0, trans, (uint32_t*)out);
     MGB_LAUNCH_CHECK();
     return MGB_OK;
 }
