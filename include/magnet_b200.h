@@ -144,6 +144,11 @@ int mgb_linear_fwd(const float* x, int64_t rows, int in_features, int out_featur
  * packed = swizzled 16-bit images of W [out, in] (row stride ldw) in the format of `precision`, built once per weight
  * version by mgb_linear_tc_pack; for the shapes mgb_linear_tc_bwd covers and precision 1 / 2 the block also holds the blocks of
  * W^T in tensor-memory operand order (the data gradient runs with its weights resident in tensor memory). */
+/* fp16 range guard of the precision-3 kernels (mgb_linear_tc_fwd*, mgb_mlp_chain_fwd, mgb_inr_decode_fused, the InteractionNetwork
+ * kernels): a kernel that meets |x| >= 32768 raises a host-mapped flag; the next precision-3 call fails with an error, and
+ * mgb_f16_range_check() returns 1 (clearing the flag) so that a caller can test at its own synchronisation points — synchronise
+ * the stream first for an answer that covers everything issued so far. */
+int mgb_f16_range_check(void);
 size_t mgb_linear_tc_packed_floats(int in_features, int out_features);
 int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_features, int precision, float* packed,
                        void* stream);

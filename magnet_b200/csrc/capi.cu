@@ -1,4 +1,5 @@
 // magnet_b200 — extern "C" entry points (see include/magnet_b200.h for the contract).
+#include <mutex>
 #include "internal.cuh"
 #include "grid.cuh"
 #include "../../include/magnet_b200.h"
@@ -178,13 +179,25 @@ int mgb_linear_tc_pack(const float* W, int ldw, int in_features, int out_feature
 static int* f16_range_flag(int** dev_ptr) {
     static int* host = nullptr;
     static int* dev = nullptr;
-    if (!host) {
-        if (cudaHostAlloc((void**)&host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { host = nullptr; return nullptr; }
+    static std::once_flag once;          // forward runs on the caller's thread, backward on PyTorch's autograd thread
+    std::call_once(once, [] {
+        if (cudaHostAlloc((void**)&host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { host = nullptr; return; }
         *host = 0;
         if (cudaHostGetDevicePointer((void**)&dev, host, 0) != cudaSuccess) dev = nullptr;
-    }
+    });
     if (dev_ptr) *dev_ptr = dev;
     return host;
+}
+
+// 1 (and the flag is cleared) when a fp16-split kernel has met |x| >= 32768 since the last check.  Reads host memory only; for an
+// answer that covers the calls issued so far the caller synchronises their stream first (a natural point: before results are used).
+int mgb_f16_range_check(void) {
+    volatile int* host_flag = f16_range_flag(nullptr);
+    if (host_flag && *host_flag) {
+        *host_flag = 0;
+        return 1;
+    }
+    return 0;
 }
 
 int mgb_linear_tc_fwd(const float* x, int64_t rows, int in_features, int out_features, const float* packed, const float* bias,

@@ -265,6 +265,17 @@ _linear_tc = True
 _LINEAR_TC_PRECISION = 3      # fp16 hi/lo split (include/magnet_b200.h); the per-edge kernels keep the bf16 split
 
 
+def check_fp16_range(sync: bool = False) -> None:
+    """Raise if a fp16-split kernel (the default arithmetic of the MAgNet MLPs) has met |x| >= 32768 since the last check.
+    ``sync=True`` synchronises the current stream first, so the answer covers every call issued so far; without it the check
+    costs one host read and reports what has already executed.  The models call it at the end of ``forward``."""
+    if sync:
+        torch.cuda.current_stream().synchronize()
+    if _lib.lib().mgb_f16_range_check():
+        raise RuntimeError("magnet_b200: a fp16-split tensor-core kernel met |x| >= 32768 (outside the fp16 range); results of this "
+                           "forward are not valid — use functional.set_linear_tc(False) (fp32 FFMA Linears) for this data")
+
+
 def set_linear_tc(on: bool) -> bool:
     """Route eligible nn.Linear forwards through the tcgen05 kernel; returns the previous setting."""
     global _linear_tc

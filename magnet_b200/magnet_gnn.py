@@ -336,8 +336,14 @@ class MAgNetGNN(LightningModule):
         if self.cuda_graph and not torch.is_grad_enabled() and x_lr.is_cuda and not torch.cuda.is_current_stream_capturing():
             out = self._forward_graphed(x_lr, lr_coords, hr_coords, t, hr_last)
             if out is not None:
+                MF.check_fp16_range()
                 return out
-        return self._forward_impl(x_lr, lr_coords, hr_coords, t, hr_last)
+        out = self._forward_impl(x_lr, lr_coords, hr_coords, t, hr_last)
+        # fp16-split range guard: one host read, no synchronisation — reports what has executed so far, i.e. at the latest on
+        # the next forward of a rollout; MF.check_fp16_range(sync=True) before results are consumed gives the exact answer
+        if x_lr.is_cuda and not torch.cuda.is_current_stream_capturing():
+            MF.check_fp16_range()
+        return out
 
     def _forward_graphed(self, x_lr, lr_coords, hr_coords, t, hr_last):
         """Replay of the captured forward for this (shapes, mesh tensors, parameter versions, arithmetic mode).  The first

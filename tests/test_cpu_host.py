@@ -52,9 +52,11 @@ def test_cpu_tensors_fail_loudly():
 
 def test_new_entry_points_reject_bad_arguments_without_gpu():
     L = _lib.lib()
-    # tensor-core Linear: only 128/256 inputs and <= 256 outputs, at most two weight tiles
-    assert L.mgb_linear_tc_packed_floats(128, 128) == 128 * 128 and L.mgb_linear_tc_packed_floats(128, 1) == 128 * 128
-    assert L.mgb_linear_tc_packed_floats(256, 128) == 2 * 128 * 128 and L.mgb_linear_tc_packed_floats(128, 256) == 2 * 128 * 128
+    # tensor-core Linear: only 128/256 inputs and <= 256 outputs, at most two weight tiles (128 x 128 floats per tile: two 16-bit
+    # images); the shapes mgb_linear_tc_bwd covers (128 outputs) carry the W^T blocks in tensor-memory order behind the images
+    assert L.mgb_linear_tc_packed_floats(128, 128) == 2 * 128 * 128 and L.mgb_linear_tc_packed_floats(128, 1) == 128 * 128
+    assert L.mgb_linear_tc_packed_floats(256, 128) == 4 * 128 * 128 and L.mgb_linear_tc_packed_floats(128, 256) == 2 * 128 * 128
+    assert L.mgb_gnn_node_update_packed_floats() == 3 * 128 * 128 + 128 * 4 and L.mgb_f16_range_check() in (0, 1)
     assert L.mgb_linear_tc_packed_floats(13, 128) == 0 and L.mgb_linear_tc_packed_floats(256, 256) == 0
     rc = L.mgb_linear_tc_fwd(None, 10, 13, 128, None, None, 0, None, None, None, 3, None)
     assert rc == -1 and "unsupported shape" in _lib.last_error()
