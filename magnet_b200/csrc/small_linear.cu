@@ -38,42 +38,61 @@ __global__ void __launch_bounds__(SL_WARPS * 32) small_linear_fwd_kernel(const f
     }
 }
 
-// partial layout per warp: [K][128] weight gradients (k-major, like wt) followed by [128] bias gradients
-template <int K>
+// partial layout per warp: [K][128] weight gradients (k-major, like wt) followed by [128] bias gradients.
+// DX = false (the input is data: raw edge / node features) drops the weight slice from the registers and keeps the gradient
+// rows of FOUR rows per warp in flight: with one row (1 KB) per warp and ~120 registers the kernel had 16 KB in flight per SM
+// against the ~43 KB that 6.4 TB/s x 1 us needs, and ran at 0.4 of the HBM bound on the 12.6 M-row edge encoder.
+template <int K, bool DX>
 __global__ void __launch_bounds__(SL_WARPS * 32) small_linear_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y_pre, int act,
                                                                         const float* __restrict__ x, int64_t rows, int ldx,
                                                                         const float* __restrict__ wt, float* __restrict__ dx,
                                                                         float* __restrict__ partial) {
+    constexpr int U = DX ? 1 : 4;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float4 wk[K], gw[K];
+    float4 wk[DX ? K : 1], gw[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        wk[k] = reinterpret_cast<const float4*>(wt + k * 128)[lane];
+        if (DX) wk[k] = reinterpret_cast<const float4*>(wt + k * 128)[lane];
         gw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = (int64_t)blockIdx.x * SL_WARPS + w; r < rows; r += (int64_t)gridDim.x * SL_WARPS) {
-        float4 g = reinterpret_cast<const float4*>(dy + r * 128)[lane];
-        if (act != ACT_NONE) {
-            const float4 z = reinterpret_cast<const float4*>(y_pre + r * 128)[lane];
-            g.x *= act_grad(act, z.x); g.y *= act_grad(act, z.y); g.z *= act_grad(act, z.z); g.w *= act_grad(act, z.w);
+    const int64_t stride = (int64_t)gridDim.x * SL_WARPS;
+    for (int64_t r0 = (int64_t)blockIdx.x * SL_WARPS + w; r0 < rows; r0 += stride * U) {
+        float4 gq[U], zq[U];
+        float xq[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = r0 + u * stride;
+            const bool ok = r < rows;
+            gq[u] = ok ? reinterpret_cast<const float4*>(dy + r * 128)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            zq[u] = (ok && act != ACT_NONE) ? reinterpret_cast<const float4*>(y_pre + r * 128)[lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            xq[u] = (ok && lane < K) ? x[r * ldx + lane] : 0.f;
         }
-        const float xv = lane < K ? x[r * ldx + lane] : 0.f;
-        gb.x += g.x; gb.y += g.y; gb.z += g.z; gb.w += g.w;
-        float mine = 0.f;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float xk = __shfl_sync(0xffffffffu, xv, k);
-            gw[k].x = fmaf(g.x, xk, gw[k].x); gw[k].y = fmaf(g.y, xk, gw[k].y);
-            gw[k].z = fmaf(g.z, xk, gw[k].z); gw[k].w = fmaf(g.w, xk, gw[k].w);
-            if (dx) {
-                float s = (g.x * wk[k].x + g.y * wk[k].y) + (g.z * wk[k].z + g.w * wk[k].w);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == k) mine = s;
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = r0 + u * stride;
+            float4 g = gq[u];
+            if (act != ACT_NONE) {
+                const float4 z = zq[u];
+                g.x *= act_grad(act, z.x); g.y *= act_grad(act, z.y); g.z *= act_grad(act, z.z); g.w *= act_grad(act, z.w);
             }
+            const float xv = xq[u];
+            gb.x += g.x; gb.y += g.y; gb.z += g.z; gb.w += g.w;
+            float mine = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float xk = __shfl_sync(0xffffffffu, xv, k);
+                gw[k].x = fmaf(g.x, xk, gw[k].x); gw[k].y = fmaf(g.y, xk, gw[k].y);
+                gw[k].z = fmaf(g.z, xk, gw[k].z); gw[k].w = fmaf(g.w, xk, gw[k].w);
+                if (DX) {
+                    float s = (g.x * wk[k].x + g.y * wk[k].y) + (g.z * wk[k].z + g.w * wk[k].w);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == k) mine = s;
+                }
+            }
+            if (DX && lane < K && r < rows) dx[r * ldx + lane] = mine;
         }
-        if (dx && lane < K) dx[r * ldx + lane] = mine;
     }
     float* p = partial + ((size_t)blockIdx.x * SL_WARPS + w) * (K + 1) * 128;
 #pragma unroll
@@ -140,7 +159,8 @@ int small_linear_bwd(const float* dy, const float* y_pre, int act, const float* 
     float* wt = ws.take<float>((size_t)K * 128);
     MGB_WS_CHECK(ws);
     MGB_TRY(launch_transpose(w, 128, K, K, wt, 128, s));
-    SL_DISPATCH(K, (small_linear_bwd_kernel<KK><<<grid, SL_WARPS * 32, 0, s>>>(dy, y_pre, act, x, rows, K, wt, dx, partial)));
+    if (dx) { SL_DISPATCH(K, (small_linear_bwd_kernel<KK, true><<<grid, SL_WARPS * 32, 0, s>>>(dy, y_pre, act, x, rows, K, wt, dx, partial))); }
+    else { SL_DISPATCH(K, (small_linear_bwd_kernel<KK, false><<<grid, SL_WARPS * 32, 0, s>>>(dy, y_pre, act, x, rows, K, wt, dx, partial))); }
     MGB_LAUNCH_CHECK();
     small_linear_reduce_kernel<<<ceil_div((K + 1) * 128, 256), 256, 0, s>>>(partial, grid * SL_WARPS, K, dw, K, db, accumulate);
     MGB_LAUNCH_CHECK();
