@@ -34,8 +34,10 @@ namespace mgb {
 
 constexpr int IB_TE = 128;                       // edge positions per tile
 constexpr int IB_EPI_WARPS = 8, IB_PROD_WARPS = 8;
-constexpr int IB_MMA_WARP = IB_EPI_WARPS, IB_META_WARP = IB_EPI_WARPS + 1, IB_PROD_WARP0 = IB_EPI_WARPS + 2;
-constexpr int IB_THREADS = (IB_PROD_WARP0 + IB_PROD_WARPS) * 32;      // 576
+// whole warpgroups, so that registers can follow the work (setmaxnreg): warps 0-7 epilogue, 8 MMA, 9 metadata, 10-11 idle,
+// 12-19 producers; 640 threads x 96 registers at launch -> 120 epilogue / 40 MMA warpgroup / 96 producers
+constexpr int IB_MMA_WARP = IB_EPI_WARPS, IB_META_WARP = IB_EPI_WARPS + 1, IB_PROD_WARP0 = IB_EPI_WARPS + 4;
+constexpr int IB_THREADS = (IB_PROD_WARP0 + IB_PROD_WARPS) * 32;      // 640
 constexpr int IB_FLUSH = 64;                     // positions per epilogue warp = granularity of the stored partial sums
 constexpr int IB_DRAIN = 8;                      // tiles between drains of the weight-gradient accumulators
 constexpr int IB_NVEC_A = 5, IB_NVEC_B = 1;      // per-channel vector gradients of pass A (db4, db3, db2, dgamma, dbeta) / B (db1)
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
     const float gs = ib_scale(a.gmax_bits), inv_gs = 1.0f / gs;
 
     if (warp < IB_EPI_WARPS) {
+        umma::reg_inc<120>();        // (120 - 96) x 256 <= (96 - 40) x 128 released by the MMA warpgroup
         // =========================== epilogue: thread = channel n; warps 0-3 positions 0-63, warps 4-7 positions 64-127 ====
         const int n = tid & 127, hf = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -541,7 +544,10 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
         constexpr int NV = PASS == 0 ? IB_NVEC_A : IB_NVEC_B;
 #pragma unroll
         for (int i = 0; i < NV; ++i) a.vpart[(((size_t)blockIdx.x * 2 + hf) * NV + i) * 128 + n] = acc_v[i] * inv_gs;
+    } else if (warp < IB_PROD_WARP0 && warp != IB_MMA_WARP && warp != IB_META_WARP) {
+        umma::reg_dec<40>();          // padding warps of the MMA / metadata warpgroup
     } else if (warp == IB_MMA_WARP) {
+        umma::reg_dec<40>();
         // =========================== MMA issue + weight loads =======================================
         const uint32_t id_kk = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 0) : umma::idesc_bf16(128, 128, 0, 0);   // A K-major,  B K-major
         const uint32_t id_km = NSPLIT == 2 ? umma::idesc_f16(128, 128, 0, 1) : umma::idesc_bf16(128, 128, 0, 1);   // A K-major,  B MN-major
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
             }
         }
     } else if (warp == IB_META_WARP) {
+        umma::reg_dec<40>();
         // =========================== pass B: segment metadata + COO rows, one tile ahead ===============================
         if (PASS == 1) {
 #pragma unroll 1
