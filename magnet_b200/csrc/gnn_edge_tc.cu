@@ -180,16 +180,21 @@ __global__ void __launch_bounds__(FW_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
             umma::tc_fence_after();
             float sum = 0.f;
 #pragma unroll 1
-            for (int cb = 0; cb < 64; cb += 8) {
-                const int c0 = pos0 + cb;
-                float v[8];
-                umma::tmem_ld8(tmem + (uint32_t)(acc * TCE) + lane_base + c0, v);
-                if (cb + 8 >= 64) {               // this thread's part of the accumulator is in registers: hand it back
+            for (int cb16 = 0; cb16 < 64; cb16 += 16) {
+                // sixteen positions per TMEM round trip, processed as two chunks of eight
+                float v16[16];
+                umma::tmem_ld16(tmem + (uint32_t)(acc * TCE) + lane_base + pos0 + cb16, v16);
+                if (cb16 + 16 >= 64) {            // this thread's part of the accumulator is in registers: hand it back
                     umma::tc_fence_before();
                     umma::mbar_arrive(&tempty[acc]);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = swish_tc<FAST>(v[i] + bias);
+            for (int hh = 0; hh < 2; ++hh) {
+                const int cb = cb16 + hh * 8;
+                const int c0 = pos0 + cb;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = swish_tc<FAST>(v16[hh * 8 + i] + bias);
                 // segmented mean over the destination-sorted positions: one pass per stored sum (segment end or
                 // sub-tile end); positions past the end of the edge list carry Swish(bias) but belong to no segment
                 uint32_t fm = (M->flushmask[c0 >> 5] >> (c0 & 31)) & 0xffu, todo = 0xffu;
@@ -214,6 +219,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) gnn_edge_fwd_tc_kernel(const Ed
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     if (todo & (1u << i)) sum += v[i];
+            }
             }
             umma::mbar_arrive(&mempty[ms]);
         }
@@ -641,16 +647,21 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
             float g = j < nseg ? gt[0] * M->seginv[j] : 0.f;
             const uint32_t emw = M->endmask[half];
 #pragma unroll 1
-            for (int cb = 0; cb < 32; cb += 8) {
-                const int c0 = pos0 + cb;
-                float v[8];
-                umma::tmem_ld8(tm_d1 + (uint32_t)(s * BTE) + lane_base + c0, v);
-                if (cb + 8 >= 32) {              // this thread's part of D1[s] is in registers: MMA1 of tile it+2 may overwrite it
+            for (int cb16 = 0; cb16 < 32; cb16 += 16) {
+                // sixteen positions per TMEM round trip, processed as two chunks of eight
+                float v16[16];
+                umma::tmem_ld16(tm_d1 + (uint32_t)(s * BTE) + lane_base + pos0 + cb16, v16);
+                if (cb16 + 16 >= 32) {           // this thread's part of D1[s] is in registers: MMA1 of tile it+2 may overwrite it
                     umma::tc_fence_before();
                     umma::mbar_arrive(&d1_empty[s]);
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = swish_grad_tc<FAST>(v[i] + bias);
+            for (int hh = 0; hh < 2; ++hh) {
+                const int cb = cb16 + hh * 8;
+                const int c0 = pos0 + cb;
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = swish_grad_tc<FAST>(v16[hh * 8 + i] + bias);
                 // dagg[dst]/deg is constant along a segment: one pass per segment that intersects the chunk (usually one)
                 uint32_t em = (emw >> cb) & 0xffu, todo = 0xffu;
                 if (em == 0) {                   // the common case: one segment covers the chunk
@@ -686,6 +697,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) gnn_edge_bwd_tc_kernel(const Ed
                     *reinterpret_cast<uint4*>(dz_row + off) = hi;
                     *reinterpret_cast<uint4*>(dz_row + BW_ZB + off) = lo;
                 }
+            }
             }
             umma::fence_async_smem();
             umma::tc_fence_before();
