@@ -360,6 +360,10 @@ bool linear_ts_covers(const LinTcArgs& a) {
 int launch_linear_ts(int precision, const LinTcArgs& a, cudaStream_t s) {
     MGB_REQUIRE(linear_ts_covers(a), "linear_ts: shape / epilogue not covered");
     MGB_REQUIRE(a.rows < ((int64_t)1 << 31), "linear_ts: row count out of range");
+    for (int kc = 0; kc < a.nk; ++kc)
+        MGB_REQUIRE(((uintptr_t)a.src[kc] % 16) == 0 && a.ld[kc] % 4 == 0, "linear_ts: source rows must be 16-byte aligned");
+    MGB_REQUIRE(a.pre == nullptr || (((uintptr_t)a.pre % 16) == 0 && a.ldpre % 4 == 0), "linear_ts: pre-activation rows must be 16-byte aligned");
+    MGB_REQUIRE(((uintptr_t)a.wimg % 16) == 0, "linear_ts: packed weights must be 16-byte aligned");
     if (a.rows <= 0) return MGB_OK;
     const int64_t tiles = ceil_div<int64_t>(a.rows, 128);
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());

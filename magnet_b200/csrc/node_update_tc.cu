@@ -381,6 +381,9 @@ __global__ void __launch_bounds__(NU_THREADS, 1) node_update_tc_kernel(const Nod
 int launch_node_update_tc(int precision, const NodeUpdateArgs& a, cudaStream_t s) {
     MGB_REQUIRE(a.nv >= 0 && a.nv <= NU_MAXV, "node_update: at most %d var columns", NU_MAXV);
     MGB_REQUIRE(a.rows < ((int64_t)1 << 31), "node_update: row count out of range");
+    MGB_REQUIRE(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.agg % 16) == 0 && ((uintptr_t)a.wimg % 16) == 0,
+                "node_update: x / agg / packed weights must be 16-byte aligned");
+    MGB_REQUIRE(a.nv == 0 || a.var != nullptr, "node_update: var is NULL but nv = %d", a.nv);
     if (a.rows <= 0) return MGB_OK;
     const int64_t tiles = ceil_div<int64_t>(a.rows, 128);
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());

@@ -128,3 +128,17 @@ def test_magnet_cnn_state_dict_loads_strictly_both_ways(golden):
     a, b = MAgNetCNN_2d(hp), theirs(hp)
     a.load_state_dict(b.state_dict(), strict=True)
     b.load_state_dict(a.state_dict(), strict=True)
+
+
+def test_node_update_entry_rejects_bad_arguments_without_gpu():
+    """mgb_gnn_node_update_fwd / pack (GNN_Layer.update, models/mpnn_2d.py:81-90): argument checks run before any launch."""
+    L = _lib.lib()
+    rc = L.mgb_gnn_node_update_fwd(None, None, None, 7, 100, None, None, None, None, None, None, 1, None)
+    assert rc == -1 and "var columns" in _lib.last_error()
+    rc = L.mgb_gnn_node_update_fwd(None, None, None, 1, 100, None, None, None, None, None, None, 5, None)
+    assert rc == -1 and "precision" in _lib.last_error()
+    rc = L.mgb_gnn_node_update_fwd(None, None, None, 1, 100, None, None, None, None, None, None, 1, None)
+    assert rc == -1 and "var is NULL" in _lib.last_error()
+    assert L.mgb_gnn_node_update_fwd(None, None, None, 0, 0, None, None, None, None, None, None, 1, None) == 0      # no rows: nothing to do
+    rc = L.mgb_gnn_node_update_pack(None, None, 9, None, None)
+    assert rc == -1 and "var columns" in _lib.last_error()
