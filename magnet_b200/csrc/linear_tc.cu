@@ -584,20 +584,20 @@ __global__ void __launch_bounds__(LT_THREADS, 1) wgrad_tc_kernel(const WgradTcAr
                 float* out = a.partial + (((int64_t)blockIdx.x * nacc + ac) * 128 + n) * 128 + hf * 64;
 #pragma unroll 1
                 for (int c0 = 0; c0 < 64; c0 += 16) {
+                    float4* o = reinterpret_cast<float4*>(out + c0);
+                    float4 old[4];       // requested before the accumulator columns: the L2 latency overlaps the TMEM round trip
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) old[q4] = grp > 0 ? o[q4] : make_float4(0.f, 0.f, 0.f, 0.f);
                     float v[16];
                     umma::tmem_ld16(tmem + (uint32_t)(ac * 128 + hf * 64) + lane_base + c0, v);
                     if (ac == nacc - 1 && c0 + 16 >= 64) {
                         umma::tc_fence_before();
                         umma::mbar_arrive(d_empty);
                     }
-                    float4* o = reinterpret_cast<float4*>(out + c0);
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         float4 w = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-                        if (grp > 0) {
-                            const float4 old = o[q4];
-                            w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
-                        }
+                        w.x += old[q4].x; w.y += old[q4].y; w.z += old[q4].z; w.w += old[q4].w;
                         o[q4] = w;
                     }
                 }
