@@ -68,7 +68,7 @@ struct InEdgeBwdArgs {
     float* wpart;              // [grid][2][128][128] partial weight gradients of this pass (zeroed by the launcher)
     float* vpart;              // [grid][2 halves][NVEC][128] partial per-channel gradients of this pass
     int* range_flag;
-    int dbg;                   // developer switch (MGB_IB_DEBUG): 1 / 2 / 3 = pass A stores y / dy / dz3 instead of dz2
+    int dbg;                   // developer build only (-DMGB_IB_DEBUG; env MGB_IB_DEBUG = 1 / 2 / 3: pass A stores y / dy / dz3 instead of dz2)
 };
 
 __device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -211,6 +211,14 @@ __device__ __forceinline__ void ib_mma_group(uint32_t d, int a_kind, uint64_t a,
     }
 }
 
+// The intermediate-quantity dumps of tools/dev_in_bwd_dbg.py exist in the developer build only: as a run-time switch their
+// per-position tests were 5 % of the instructions of pass A (ncu source view).
+#ifdef MGB_IB_DEBUG
+#define IB_DBG(a) ((a).dbg)
+#else
+#define IB_DBG(a) 0
+#endif
+
 #ifdef MGB_TIMELINE
 __device__ long long* g_ib_timeline = nullptr;      // [pass 0..1][tile 0..3][role 0..2][event 0..31] clock64 of CTA 0
 #define IBTL(role, it_, ev) do { if (blockIdx.x == 0 && (it_) < 4 && (threadIdx.x & 31) == 0 && g_ib_timeline && (ev) < 32) g_ib_timeline[(((PASS) * 4 + (it_)) * 3 + (role)) * 32 + (ev)] = clock64(); } while (0)
@@ -326,19 +334,19 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                 // ---- recompute: h0 (accumulator R2, initialised with P + Q), h1 -> working tile; h2 -> retained tile;
                 // h3 -> working tile + tensor memory (A operand of dW4)
                 wait_t0(it);
-                if (a.dbg == 4) dump(R2, 0.f);
+                if (IB_DBG(a) == 4) dump(R2, 0.f);
                 ib_relu_epilogue<NSPLIT>(R2, 0.f, x_img, hf, n, 0u, a.range_flag, true);
                 signal();
                 wait_t();
-                if (a.dbg == 5) dump(R1, b1);
+                if (IB_DBG(a) == 5) dump(R1, b1);
                 ib_relu_epilogue<NSPLIT>(R1, b1, x_img, hf, n, 0u, a.range_flag, true);
                 signal();
                 wait_t();
-                if (a.dbg == 6) dump(R1, b2);
+                if (IB_DBG(a) == 6) dump(R1, b2);
                 const uint2 mask2 = ib_relu_epilogue<NSPLIT>(R1, b2, h_img, hf, n, 0u, a.range_flag, true);
                 signal();
                 wait_t();
-                if (a.dbg == 7) dump(R1, b3);
+                if (IB_DBG(a) == 7) dump(R1, b3);
                 const uint2 mask3 = ib_relu_epilogue<NSPLIT>(R1, b3, x_img, hf, n, TS, a.range_flag, true);
                 signal();
                 // ---- y = D + b4: LayerNorm forward statistics and backward, dy -> working tile
@@ -362,7 +370,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                     for (int i = 0; i < 16; ++i) {
                         const int e = c0 + i;
                         *reinterpret_cast<float*>(x_img + e * 512 + ((((n >> 2) ^ (e & 31))) << 4) + (n & 3) * 4) = v[i] + b4;
-                        if (a.dbg == 1) a.dz2[(tile * IB_TE + e) * 128 + n] = v[i] + b4;
+                        if (IB_DBG(a) == 1) a.dz2[(tile * IB_TE + e) * 128 + n] = v[i] + b4;
                     }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                             acc_v[4] += dm;
                             acc_v[0] += dy;
                             v[i] = dy;
-                            if (a.dbg == 2) a.dz2[(tile * IB_TE + e) * 128 + n] = dy;
+                            if (IB_DBG(a) == 2) a.dz2[(tile * IB_TE + e) * 128 + n] = dy;
                         }
                         if (NSPLIT == 2) {
 #pragma unroll
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                 // ---- dz3 = (W4^T dy) . [z3 > 0] -> working tile
                 wait_t();
                 acc_v[1] += ib_mask_epilogue<NSPLIT>(R1, mask3, x_img, hf, n, a.range_flag);
-                if (a.dbg == 3) {
+                if (IB_DBG(a) == 3) {
                     float v[32];
                     for (int cb = 0; cb < 64; cb += 32) {
                         umma::tmem_ld32(R1 + (uint32_t)cb, v);
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(IB_THREADS, 1) in_edge_bwd_tc_kernel(const InE
                         for (int i = 0; i < 32; ++i) {
                             const float z = (m >> i) & 1u ? v[i] : 0.f;
                             sum += z;
-                            if (a.dbg == 0) out[(cb + i) * 128] = z;
+                            if (IB_DBG(a) == 0) out[(cb + i) * 128] = z;
                         }
                     }
                     acc_v[2] += sum;
@@ -863,7 +871,11 @@ int launch_in_edge_bwd(int precision, const float* dagg, const float* e, float e
     a.beta = a.gamma + 128;
     a.dagg = dagg; a.gmax_bits = gmax; a.dz2 = dz2; a.dz0 = dz0; a.dpq = dpq; a.part_head = part_head; a.part_tail = part_tail;
     a.range_flag = range_flag;
+#ifdef MGB_IB_DEBUG
     { const char* dbg = getenv("MGB_IB_DEBUG"); a.dbg = dbg ? atoi(dbg) : 0; }
+#else
+    a.dbg = 0;
+#endif
     float* vpart_b = vpart + (size_t)grid * 2 * IB_NVEC_A * 128;
     {
         ProfScope prof(PROF_IN_EDGE_BWD, s);

@@ -1,5 +1,7 @@
 """Dev helper (GPU): calls mgb_in_edge_bwd directly and compares its intermediates (dz2 in the workspace, dz0, dP, weight / vector
-gradients) with an fp64 torch evaluation of the same chain.  usage: python tools/dev_in_bwd_dbg.py [nodes] [e_scale]"""
+gradients) with an fp64 torch evaluation of the same chain.  usage: python tools/dev_in_bwd_dbg.py [nodes] [e_scale]
+The MGB_IB_DEBUG=1..7 dumps of intermediate quantities need the developer build:
+  MGB_VARIANT=dbg MGB_NVCC_EXTRA=-DMGB_IB_DEBUG python -m magnet_b200.build;  MGB_VARIANT=dbg MGB_IB_DEBUG=2 python tools/dev_in_bwd_dbg.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
